@@ -1,0 +1,226 @@
+"""ctypes binding of the C ABI in include/fadtk_b200.h (csrc/libfadtk_b200.so).
+
+PyTorch tensors are only containers here: every call passes ``tensor.data_ptr()`` and the
+current CUDA stream.  There is no CPU fallback - if the shared library or a B200 is missing
+the import of a compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+_LIB_PATH = Path(__file__).parent / "csrc" / "libfadtk_b200.so"
+_lib = None
+
+c_ll = C.c_longlong
+c_vp = C.c_void_p
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class VggishWeights(C.Structure):
+    _fields_ = [("conv1_w_host", c_vp), ("conv1_b_host", c_vp),
+                ("conv_w_host", c_vp * 5), ("conv_b_host", c_vp * 5),
+                ("fc_w_host", c_vp * 3), ("fc_b_host", c_vp * 3)]
+
+
+# name -> (restype, argtypes); mirrors include/fadtk_b200.h one to one
+SIGNATURES = {
+    "fad_version": (C.c_int, []),
+    "fad_last_error": (C.c_char_p, []),
+    "fad_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "fad_destroy": (C.c_int, [c_vp]),
+    "fad_vggish_load": (C.c_int, [c_vp, C.POINTER(VggishWeights)]),
+    "fad_vggish_num_examples": (c_ll, [c_ll]),
+    "fad_vggish_plan": (c_ll, [c_vp, c_ll, c_vp, c_ll, c_vp]),
+    "fad_vggish_forward": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "fad_vggish_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, C.c_int, c_vp]),
+    "fad_umma_layer": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "fad_stats_acc_len": (C.c_size_t, [C.c_int]),
+    "fad_stats_accumulate": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
+    "fad_stats_accumulate_gather": (C.c_int, [c_vp, c_vp, c_ll, c_vp, c_ll, C.c_int, c_vp, c_vp, c_vp]),
+    "fad_stats_finalize": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "fad_frechet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "fad_launch_count": (c_ll, [c_vp]),
+}
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def lib():
+    """Load the shared library (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise NativeError(
+                f"{_LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "fadtk_b200 has no CPU fallback.")
+        _lib = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise NativeError(lib().fad_last_error().decode())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class Engine:
+    """One native handle bound to one CUDA device."""
+
+    def __init__(self, device: int | None = None, max_examples: int = 2048):
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device visible: fadtk_b200 has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.max_examples = int(max_examples)
+        h = c_vp()
+        _check(lib().fad_create(self.device, self.max_examples, C.byref(h)))
+        self._h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fad_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def torch_device(self):
+        return torch.device("cuda", self.device)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().fad_launch_count(self._h))
+
+    # ------------------------------------------------------------------ VGGish
+    def vggish_load(self, packed: dict):
+        """``packed`` comes from fadtk_b200.weights.pack_vggish (CPU tensors)."""
+        w = VggishWeights()
+        keep = {k: v.contiguous() for k, v in packed.items()}
+        w.conv1_w_host = keep["conv1.w"].data_ptr()
+        w.conv1_b_host = keep["conv1.b"].data_ptr()
+        for i in range(5):
+            w.conv_w_host[i] = keep[f"conv{i + 2}.w"].data_ptr()
+            w.conv_b_host[i] = keep[f"conv{i + 2}.b"].data_ptr()
+        for i in range(3):
+            w.fc_w_host[i] = keep[f"fc{i + 1}.w"].data_ptr()
+            w.fc_b_host[i] = keep[f"fc{i + 1}.b"].data_ptr()
+        _check(lib().fad_vggish_load(self._h, C.byref(w)))
+
+    @staticmethod
+    def vggish_plan(clip_offsets: np.ndarray):
+        """-> (ex_start int64 [n_examples], rows_per_clip int64 [n_clips])"""
+        off = np.ascontiguousarray(clip_offsets, dtype=np.int64)
+        n_clips = off.shape[0] - 1
+        rows = np.empty(n_clips, dtype=np.int64)
+        n = lib().fad_vggish_plan(off.ctypes.data, n_clips, None, 0, rows.ctypes.data)
+        ex = np.empty(n, dtype=np.int64)
+        lib().fad_vggish_plan(off.ctypes.data, n_clips, ex.ctypes.data, n, None)
+        return ex, rows
+
+    def vggish_forward(self, pcm: torch.Tensor, ex_start: torch.Tensor, out: torch.Tensor | None = None):
+        """pcm int16 [samples] (cuda), ex_start int64 [n] (cuda) -> fp16 [n, 128] (cuda)."""
+        assert pcm.dtype == torch.int16 and pcm.is_cuda and pcm.is_contiguous()
+        assert ex_start.dtype == torch.int64 and ex_start.is_cuda
+        n = ex_start.shape[0]
+        if out is None:
+            out = torch.empty((n, 128), dtype=torch.float16, device=pcm.device)
+        assert out.dtype == torch.float16 and out.is_contiguous() and out.shape[0] >= n
+        _check(lib().fad_vggish_forward(self._h, pcm.data_ptr(), ex_start.data_ptr(), n,
+                                        out.data_ptr(), _stream()))
+        return out[:n]
+
+    def vggish_logmel(self, pcm, ex_start, use_double=True):
+        n = ex_start.shape[0]
+        out = torch.empty((n, 96, 64), dtype=torch.float32, device=pcm.device)
+        _check(lib().fad_vggish_logmel(self._h, pcm.data_ptr(), ex_start.data_ptr(), n,
+                                       out.data_ptr(), int(use_double), _stream()))
+        return out
+
+    def umma_layer(self, x, w, bias, taps, relu, pool, want_f32=False):
+        """x fp16 NHWC [NB,H,W,Cin]; w fp16 [Cout, taps*Cin]; bias fp32 [Cout]."""
+        nb, hh, ww, cin = x.shape
+        cout = w.shape[0]
+        oh, ow = (hh // 2, ww // 2) if pool else (hh, ww)
+        out = torch.empty((nb, oh, ow, cout), dtype=torch.float16, device=x.device)
+        out32 = torch.empty((nb, oh, ow, cout), dtype=torch.float32, device=x.device) if want_f32 else None
+        _check(lib().fad_umma_layer(self._h, x.data_ptr(), nb, hh, ww, cin, w.data_ptr(), bias.data_ptr(),
+                                    cout, taps, int(relu), int(pool), out.data_ptr(), _ptr(out32), _stream()))
+        return (out, out32) if want_f32 else out
+
+    # -------------------------------------------------------------- statistics
+    @staticmethod
+    def stats_acc_len(d: int) -> int:
+        return int(lib().fad_stats_acc_len(d))
+
+    def stats_new(self, d: int) -> torch.Tensor:
+        return torch.zeros(self.stats_acc_len(d), dtype=torch.float64, device=self.torch_device)
+
+    def stats_accumulate(self, emb, shift, acc, simt=False):
+        assert emb.dtype == torch.float16 and emb.is_contiguous() and shift.dtype == torch.float16
+        n, d = emb.shape
+        _check(lib().fad_stats_accumulate(self._h, emb.data_ptr(), n, d, shift.data_ptr(),
+                                          acc.data_ptr(), int(simt), _stream()))
+        return acc
+
+    def stats_accumulate_gather(self, emb, idx, shift, acc):
+        assert emb.dtype == torch.float16 and emb.is_contiguous() and idx.dtype == torch.int64
+        n, d = emb.shape
+        _check(lib().fad_stats_accumulate_gather(self._h, emb.data_ptr(), n, idx.data_ptr(), idx.shape[0], d,
+                                                 shift.data_ptr(), acc.data_ptr(), _stream()))
+        return acc
+
+    def stats_finalize(self, acc, shift, d):
+        mu = torch.empty(d, dtype=torch.float64, device=acc.device)
+        cov = torch.empty((d, d), dtype=torch.float64, device=acc.device)
+        _check(lib().fad_stats_finalize(self._h, acc.data_ptr(), shift.data_ptr(), d,
+                                        mu.data_ptr(), cov.data_ptr(), _stream()))
+        return mu, cov
+
+    # ----------------------------------------------------------------- Frechet
+    def frechet(self, mu1, cov1, mu2, cov2, iters: int = 0) -> torch.Tensor:
+        """fp64 cuda tensors -> fp64 [8] cuda: FAD, tr sqrt, residual, iters, |dmu|^2, trC1, trC2."""
+        d = mu1.shape[0]
+        for t in (mu1, cov1, mu2, cov2):
+            assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+        out = torch.zeros(8, dtype=torch.float64, device=mu1.device)
+        _check(lib().fad_frechet(self._h, mu1.data_ptr(), cov1.data_ptr(), mu2.data_ptr(), cov2.data_ptr(),
+                                 d, iters, out.data_ptr(), _stream()))
+        return out
+
+
+_engines: dict = {}
+
+
+def engine(device: int | None = None, max_examples: int | None = None) -> Engine:
+    """Process-wide engine per device (created lazily)."""
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _engines:
+        me = max_examples or int(os.environ.get("FADTK_MAX_EXAMPLES", "2048"))
+        _engines[dev] = Engine(dev, me)
+    return _engines[dev]

@@ -1,0 +1,247 @@
+// Implicit-GEMM 3x3 convolution / fully-connected layer on tcgen05 tensor cores.
+//
+//   D[128 pixels, N_TILE channels] = sum over (tap, 64-channel block) of
+//         X_tap[128 pixels, 64 ch] (fp16, K-major, TMA im2col-by-coordinates)
+//       x W[N_TILE, (tap, 64 ch)]^T (fp16, K-major)
+//   epilogue: + bias, ReLU, optional 2x2 max-pool, fp32 -> fp16, NHWC store.
+//
+// Replaces the cuDNN / cuBLAS calls behind torchvggish's ``features`` and ``embeddings``
+// (reference call site fadtk/model_loader.py:107-108; shapes in SURVEY.md appendix A, K3/K4).
+//
+// Data movement: activations are NHWC fp16 in HBM.  One output tile covers a
+// BW x BH x BN box of pixels (BW*BH*BN = 128); for filter tap (kh, kw) the A operand is the
+// same box shifted by (kh-1, kw-1), fetched with ONE 4-D TMA whose out-of-bounds elements are
+// zero-filled by hardware - that is the conv padding, and there is no im2col buffer.  TMA
+// writes the 128-byte swizzled K-major layout tcgen05.mma consumes directly.
+//
+// Warp roles (256 threads, persistent over tiles):
+//   warp 0  TMA producer (one elected lane)        warp 2  TMEM allocator
+//   warp 1  MMA issuer   (one elected lane)        warps 4-7  epilogue (TMEM lane quarter = warp%4)
+// Pipelines: smem ring full[]/empty[] (TMA <-> MMA), TMEM double buffer
+// tmem_full[]/tmem_empty[] (MMA <-> epilogue) so tile i's epilogue overlaps tile i+1's MMAs.
+#pragma once
+#include "sm100.cuh"
+
+namespace fad {
+
+struct ConvGemmParams {
+    int taps;        // 9 (conv3x3, pad 1) or 1 (fully connected / 1x1)
+    int cblks;       // Cin / 64
+    int box_w, box_h, box_n;   // pixel box of one tile, product == 128
+    int tiles_w, tiles_h;      // tiles per image along W and H
+    int img_groups;            // ceil(NB / box_n)
+    int n_tiles;               // Cout / N_TILE
+    int H, W, NB, Cout;
+    int relu, pool;
+    const float* bias;         // [Cout]
+    __half* out;               // NHWC fp16 [NB, H(/2), W(/2), Cout]
+    float* out_f32;            // optional fp32 copy of the un-pooled output (may be null)
+};
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                        // fp16 elements per 128-B swizzled row
+constexpr int kConvGemmThreads = 256;
+constexpr uint32_t kABytes = kTileM * kBlockK * 2; // 16 KiB per stage
+
+template <int N_TILE>
+__host__ __device__ constexpr uint32_t conv_gemm_stage_bytes() { return kABytes + N_TILE * kBlockK * 2; }
+
+template <int N_TILE, int STAGES>
+__host__ __device__ constexpr uint32_t conv_gemm_smem_bytes() {
+    return STAGES * conv_gemm_stage_bytes<N_TILE>() + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(kConvGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
+                 const __grid_constant__ CUtensorMap map_w,
+                 const ConvGemmParams p)
+{
+    using namespace sm100;
+    constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE>();
+    constexpr uint32_t kTmemCols = 2 * N_TILE;          // double-buffered fp32 accumulator
+    constexpr uint32_t kIdesc = make_idesc(FMT_F16, kTileM, N_TILE);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ksteps = p.taps * p.cblks;
+    const int m_tiles = p.img_groups * p.tiles_h * p.tiles_w;
+    const int total_tiles = m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_base_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int m = tile / p.n_tiles;
+                const int w0 = (m % p.tiles_w) * p.box_w;
+                const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.box_h;
+                const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.box_n;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const int tap = ks / p.cblks;
+                    const int cb = ks - tap * p.cblks;
+                    int dh = 0, dw = 0;
+                    if (p.taps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], kStageBytes);
+                    uint8_t* st = smem + s * kStageBytes;
+                    tma_load_4d(st, &map_x, &full[s], cb * kBlockK, w0 + dw, h0 + dh, n0);
+                    tma_load_2d(st + kABytes, &map_w, &full[s], ks * kBlockK, nt * N_TILE);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer
+        if (elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * N_TILE;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                    const uint64_t a_desc = kmajor_sw128_desc(a_addr);
+                    const uint64_t b_desc = kmajor_sw128_desc(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // +32 B along K inside the 128-B swizzle atom == +2 in the 16-B address field
+                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks | k) != 0);
+                    }
+                    umma_commit(&empty[s]);               // smem slot free once these MMAs retire
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);             // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue
+        const int q = warp & 3;                           // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;                      // row of the tile == TMEM lane
+        const int bw = p.box_w, bh = p.box_h;
+        const int pw = r % bw;
+        const int phh = (r / bw) % bh;
+        const int pn = r / (bw * bh);
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int m = tile / p.n_tiles;
+            const int w = (m % p.tiles_w) * bw + pw;
+            const int h = ((m / p.tiles_w) % p.tiles_h) * bh + phh;
+            const int n = (m / (p.tiles_w * p.tiles_h)) * p.box_n + pn;
+            const bool valid = n < p.NB;
+
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after_sync();
+            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * N_TILE;
+            const int ch0 = nt * N_TILE;
+#pragma unroll 1
+            for (int c = 0; c < N_TILE / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c * 32, v);
+                tmem_ld_wait();
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ch0 + c * 32);
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(bias4 + j);
+                    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                uint32_t h2[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h2[j] = pack_half2(f[2 * j], f[2 * j + 1]);
+
+                if (!p.pool) {
+                    if (valid) {
+                        const size_t pix = (size_t(n) * p.H + h) * p.W + w;
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+                        if (p.out_f32) {
+                            float4* d32 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + ch0 + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                d32[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
+                    }
+                } else {
+                    // 2x2 max-pool: partners are lane^1 (w) and lane^box_w (h), box_w in {8,16}
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t o = __shfl_xor_sync(0xffffffffu, h2[j], 1);
+                        h2[j] = hmax2_u32(h2[j], o);
+                        o = __shfl_xor_sync(0xffffffffu, h2[j], bw);
+                        h2[j] = hmax2_u32(h2[j], o);
+                    }
+                    // the four lanes of a 2x2 group now hold the same 32 channels; each stores 8
+                    const int sub = (pw & 1) | ((phh & 1) << 1);
+                    uint4 o;
+                    o.x = sub == 0 ? h2[0] : sub == 1 ? h2[4] : sub == 2 ? h2[8]  : h2[12];
+                    o.y = sub == 0 ? h2[1] : sub == 1 ? h2[5] : sub == 2 ? h2[9]  : h2[13];
+                    o.z = sub == 0 ? h2[2] : sub == 1 ? h2[6] : sub == 2 ? h2[10] : h2[14];
+                    o.w = sub == 0 ? h2[3] : sub == 1 ? h2[7] : sub == 2 ? h2[11] : h2[15];
+                    if (valid) {
+                        const size_t pix = (size_t(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+                        *reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + c * 32 + sub * 8) = o;
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace fad

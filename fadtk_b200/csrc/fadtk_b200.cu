@@ -1,0 +1,579 @@
+// Host side of the C ABI declared in include/fadtk_b200.h: owns device weights and workspaces,
+// encodes TMA descriptors, launches the sm_100a kernels.  No torch, no CUTLASS.
+#include "../../include/fadtk_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "frontend.cuh"
+#include "stats.cuh"
+#include "frechet.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) { g_err = m; return 1; }
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp16 tensor, innermost dimension first; 128-B swizzle, zero fill out of bounds.
+int encode_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                    gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+        return fail(buf);
+    }
+    return 0;
+}
+
+struct LayerGeom {
+    int taps, Cin, Cout, H, W, relu, pool;
+    int box_w, box_h, box_n, n_tile;
+};
+
+int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu, int pool) {
+    g.taps = taps; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.relu = relu; g.pool = pool;
+    if (Cin % 64 != 0) return fail("Cin must be a multiple of 64");
+    if (taps != 1 && taps != 9) return fail("taps must be 1 or 9");
+    if (H == 1 && W == 1) { g.box_w = 1; g.box_h = 1; g.box_n = 128; }
+    else {
+        g.box_w = W < 16 ? W : 16;
+        if (g.box_w != 8 && g.box_w != 16) return fail("W must be 8 or a multiple of 16");
+        if (W % g.box_w != 0) return fail("W must be a multiple of the 16-pixel box");
+        int bh = 1;
+        while (bh * 2 <= 128 / g.box_w && H % (bh * 2) == 0) bh *= 2;
+        g.box_h = bh;
+        g.box_n = 128 / (g.box_w * g.box_h);
+    }
+    if (pool && (g.box_h % 2 != 0 || g.box_w % 2 != 0)) return fail("pooling needs even tile boxes");
+    if (Cout % 256 == 0) g.n_tile = 256;
+    else if (Cout % 128 == 0) g.n_tile = 128;
+    else return fail("Cout must be a multiple of 128");
+    return 0;
+}
+
+}  // namespace
+
+struct fad_handle {
+    int device = 0;
+    int num_sms = 0;
+    int max_examples = 0;
+    long long launches = 0;
+
+    // front-end tables
+    double *d_twiddle = nullptr, *d_hann = nullptr, *d_melw = nullptr;
+    int *d_mel_start = nullptr, *d_mel_count = nullptr;
+
+    // VGGish parameters (device)
+    bool vgg_loaded = false;
+    float *conv1_w = nullptr, *conv1_b = nullptr;
+    __half* conv_w[5] = {};
+    float* conv_b[5] = {};
+    __half* fc_w[3] = {};
+    float* fc_b[3] = {};
+
+    // activations (device), sized for max_examples
+    float* logmel = nullptr;
+    __half* act[9] = {};       // act[0]=conv1 out ... act[5]=conv6 out (flattened), act[6..7]=fc1, fc2 out
+
+    // per-layer cached descriptors for the fixed VGGish pipeline
+    CUtensorMap map_x[8], map_w[8];
+    LayerGeom geom[8];
+
+    // statistics workspace
+    double *ws_tiles = nullptr, *ws_sums = nullptr;
+    size_t ws_tiles_cap = 0, ws_sums_cap = 0;
+    __half* gather_buf = nullptr;
+    size_t gather_cap = 0;
+
+    // Frechet workspace (fp64 d x d matrices)
+    double* fr_buf = nullptr;
+    size_t fr_cap = 0;
+    double* fr_scal = nullptr;   // 32 doubles
+};
+
+namespace {
+
+template <int N_TILE, int STAGES>
+int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw,
+                     const fad::ConvGemmParams& p, cudaStream_t st) {
+    static bool attr_set = false;
+    constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES>();
+    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES>;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int total = p.img_groups * p.tiles_h * p.tiles_w * p.n_tiles;
+    if (total == 0) return 0;
+    const int grid = total < h->num_sms ? total : h->num_sms;
+    kern<<<grid, fad::kConvGemmThreads, smem, st>>>(mx, mw, p);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const void* w,
+                      CUtensorMap* mx, CUtensorMap* mw) {
+    const uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)nb_dim};
+    const uint64_t xs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.W * g.Cin * 2, (uint64_t)g.H * g.W * g.Cin * 2};
+    const uint32_t xb[4] = {64, (uint32_t)g.box_w, (uint32_t)g.box_h, (uint32_t)g.box_n};
+    if (encode_f16_map(mx, x, 4, xd, xs, xb)) return 1;
+    const uint64_t K = (uint64_t)g.taps * g.Cin;
+    const uint64_t wd[2] = {K, (uint64_t)g.Cout};
+    const uint64_t ws[1] = {K * 2};
+    const uint32_t wb[2] = {64, (uint32_t)g.n_tile};
+    return encode_f16_map(mw, w, 2, wd, ws, wb);
+}
+
+int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CUtensorMap& mw,
+              int NB, const float* bias, void* out, float* out_f32, cudaStream_t st) {
+    fad::ConvGemmParams p;
+    p.taps = g.taps; p.cblks = g.Cin / 64;
+    p.box_w = g.box_w; p.box_h = g.box_h; p.box_n = g.box_n;
+    p.tiles_w = g.W / g.box_w; p.tiles_h = g.H / g.box_h;
+    p.img_groups = (NB + g.box_n - 1) / g.box_n;
+    p.n_tiles = g.Cout / g.n_tile;
+    p.H = g.H; p.W = g.W; p.NB = NB; p.Cout = g.Cout;
+    p.relu = g.relu; p.pool = g.pool;
+    p.bias = bias; p.out = reinterpret_cast<__half*>(out); p.out_f32 = out_f32;
+    if (g.n_tile == 256) return launch_conv_gemm<256, 4>(h, mx, mw, p, st);
+    return launch_conv_gemm<128, 6>(h, mx, mw, p, st);
+}
+
+// VGGish layer table: H, W are the conv's spatial size (input == un-pooled output)
+struct VggLayer { int H, W, Cin, Cout, taps, relu, pool; };
+const VggLayer kVgg[8] = {
+    {48, 32, 64, 128, 9, 1, 1},     // conv2  -> [24,16,128]
+    {24, 16, 128, 256, 9, 1, 0},    // conv3_1
+    {24, 16, 256, 256, 9, 1, 1},    // conv3_2 -> [12,8,256]
+    {12, 8, 256, 512, 9, 1, 0},     // conv4_1
+    {12, 8, 512, 512, 9, 1, 1},     // conv4_2 -> [6,4,512] == [12288]
+    {1, 1, 12288, 4096, 1, 1, 0},   // fc1
+    {1, 1, 4096, 4096, 1, 1, 0},    // fc2
+    {1, 1, 4096, 128, 1, 0, 0},     // fc3 (no ReLU: fadtk/model_loader.py:102-103)
+};
+// bytes of fp16 activation per example produced by: conv1, conv2, conv3_1, conv3_2, conv4_1, conv4_2, fc1, fc2
+const size_t kActElems[8] = {48 * 32 * 64, 24 * 16 * 128, 24 * 16 * 256, 12 * 8 * 256,
+                             12 * 8 * 512, 6 * 4 * 512, 4096, 4096};
+
+void build_frontend_tables(std::vector<double>& tw, std::vector<double>& hann,
+                           std::vector<double>& melw, std::vector<int>& mstart, std::vector<int>& mcount) {
+    const double PI = 3.14159265358979323846;
+    tw.resize(512); hann.resize(fad::kWin);
+    for (int k = 0; k < 256; ++k) {
+        tw[2 * k] = std::cos(-2.0 * PI * k / 512.0);
+        tw[2 * k + 1] = std::sin(-2.0 * PI * k / 512.0);
+    }
+    for (int n = 0; n < fad::kWin; ++n) hann[n] = 0.5 - 0.5 * std::cos(2.0 * PI / fad::kWin * n);
+    // HTK mel filterbank, 64 bands over 125..7500 Hz on 257 bins of 0..8000 Hz; DC bin zeroed
+    auto mel = [](double f) { return 1127.0 * std::log(1.0 + f / 700.0); };
+    std::vector<double> bins(fad::kBins), edges(fad::kMel + 2);
+    for (int i = 0; i < fad::kBins; ++i) bins[i] = mel(8000.0 * i / (fad::kBins - 1));
+    const double lo = mel(125.0), hi = mel(7500.0);
+    for (int i = 0; i < fad::kMel + 2; ++i) edges[i] = lo + (hi - lo) * i / (fad::kMel + 1);
+    melw.assign(fad::kMel * fad::kMelMaxTaps, 0.0);
+    mstart.assign(fad::kMel, 0); mcount.assign(fad::kMel, 0);
+    for (int b = 0; b < fad::kMel; ++b) {
+        const double l = edges[b], c = edges[b + 1], u = edges[b + 2];
+        int first = -1, cnt = 0;
+        for (int i = 1; i < fad::kBins; ++i) {            // bin 0 (DC) has zero weight
+            const double w = std::fmax(0.0, std::fmin((bins[i] - l) / (c - l), (u - bins[i]) / (u - c)));
+            if (w > 0.0) {
+                if (first < 0) first = i;
+                const int off = i - first;
+                if (off < fad::kMelMaxTaps) { melw[b * fad::kMelMaxTaps + off] = w; cnt = off + 1; }
+            }
+        }
+        mstart[b] = first < 0 ? 0 : first;
+        mcount[b] = cnt;
+    }
+}
+
+int ensure(void** ptr, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    CK(cudaMalloc(ptr, bytes));
+    *cap = bytes;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fad_version(void) { return 1; }
+const char* fad_last_error(void) { return g_err.c_str(); }
+
+int fad_create(int device, int max_examples, fad_handle** out) {
+    if (!out) return fail("null out pointer");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail("no CUDA device: fadtk_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail("bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("fadtk_b200 kernels are built for sm_100a (Blackwell B200) only");
+    fad_handle* h = new fad_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->max_examples = max_examples > 0 ? max_examples : 2048;
+
+    std::vector<double> tw, hann, melw; std::vector<int> ms, mc;
+    build_frontend_tables(tw, hann, melw, ms, mc);
+    CK(cudaMalloc(&h->d_twiddle, tw.size() * 8)); CK(cudaMemcpy(h->d_twiddle, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_hann, hann.size() * 8)); CK(cudaMemcpy(h->d_hann, hann.data(), hann.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_melw, melw.size() * 8)); CK(cudaMemcpy(h->d_melw, melw.data(), melw.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_mel_start, ms.size() * 4)); CK(cudaMemcpy(h->d_mel_start, ms.data(), ms.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_mel_count, mc.size() * 4)); CK(cudaMemcpy(h->d_mel_count, mc.data(), mc.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->fr_scal, 32 * sizeof(double)));
+    CK(cudaFuncSetAttribute(fad::logmel_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fad::logmel_smem_bytes<double>()));
+    CK(cudaFuncSetAttribute(fad::logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fad::logmel_smem_bytes<float>()));
+    CK(cudaFuncSetAttribute(fad::stats_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fad::kStSmemBytes));
+    *out = h;
+    return 0;
+}
+
+int fad_destroy(fad_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
+                    h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 5; ++i) { if (h->conv_w[i]) cudaFree(h->conv_w[i]); if (h->conv_b[i]) cudaFree(h->conv_b[i]); }
+    for (int i = 0; i < 3; ++i) { if (h->fc_w[i]) cudaFree(h->fc_w[i]); if (h->fc_b[i]) cudaFree(h->fc_b[i]); }
+    for (int i = 0; i < 9; ++i) if (h->act[i]) cudaFree(h->act[i]);
+    delete h;
+    return 0;
+}
+
+long long fad_launch_count(fad_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------ VGGish
+int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
+    if (!h || !w) return fail("null argument");
+    CK(cudaSetDevice(h->device));
+    auto up = [&](void** dst, const void* src, size_t bytes) -> int {
+        if (!src) return fail("missing weight pointer");
+        if (!*dst) CK(cudaMalloc(dst, bytes));
+        CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (up((void**)&h->conv1_w, w->conv1_w_host, 64 * 9 * 4)) return 1;
+    if (up((void**)&h->conv1_b, w->conv1_b_host, 64 * 4)) return 1;
+    for (int i = 0; i < 5; ++i) {
+        const VggLayer& L = kVgg[i];
+        if (up((void**)&h->conv_w[i], w->conv_w_host[i], (size_t)L.Cout * 9 * L.Cin * 2)) return 1;
+        if (up((void**)&h->conv_b[i], w->conv_b_host[i], (size_t)L.Cout * 4)) return 1;
+    }
+    for (int i = 0; i < 3; ++i) {
+        const VggLayer& L = kVgg[5 + i];
+        if (up((void**)&h->fc_w[i], w->fc_w_host[i], (size_t)L.Cout * L.Cin * 2)) return 1;
+        if (up((void**)&h->fc_b[i], w->fc_b_host[i], (size_t)L.Cout * 4)) return 1;
+    }
+    const size_t B = (size_t)h->max_examples;
+    if (!h->logmel) CK(cudaMalloc(&h->logmel, B * 96 * 64 * 4));
+    for (int i = 0; i < 8; ++i)
+        if (!h->act[i]) CK(cudaMalloc(&h->act[i], B * kActElems[i] * 2));
+    // descriptors of the fixed pipeline (batch dimension = max_examples; tiles past the live
+    // batch are never scheduled and rows past it are masked in the epilogue)
+    for (int i = 0; i < 8; ++i) {
+        const VggLayer& L = kVgg[i];
+        if (make_geom(h->geom[i], L.H, L.W, L.Cin, L.Cout, L.taps, L.relu, L.pool)) return 1;
+        const void* wptr = i < 5 ? (const void*)h->conv_w[i] : (const void*)h->fc_w[i - 5];
+        if (encode_layer_maps(h->geom[i], h->act[i], (long long)B, wptr, &h->map_x[i], &h->map_w[i])) return 1;
+    }
+    h->vgg_loaded = true;
+    return 0;
+}
+
+long long fad_vggish_num_examples(long long n_samples) {
+    if (n_samples < fad::kWin) return 0;
+    const long long t = 1 + (n_samples - fad::kWin) / fad::kHop;
+    if (t < fad::kExFrames) return 0;
+    return 1 + (t - fad::kExFrames) / fad::kExFrames;
+}
+
+long long fad_vggish_plan(const long long* clip_offsets_host, long long n_clips,
+                          long long* ex_start_host, long long capacity, long long* rows_per_clip_host) {
+    long long n = 0;
+    for (long long c = 0; c < n_clips; ++c) {
+        const long long len = clip_offsets_host[c + 1] - clip_offsets_host[c];
+        const long long k = fad_vggish_num_examples(len);
+        if (rows_per_clip_host) rows_per_clip_host[c] = k;
+        for (long long e = 0; e < k; ++e, ++n)
+            if (ex_start_host && n < capacity)
+                ex_start_host[n] = clip_offsets_host[c] + e * (long long)(fad::kExFrames * fad::kHop);
+    }
+    return n;
+}
+
+static int launch_logmel(fad_handle* h, const int16_t* pcm, const long long* ex_start, long long n,
+                         float* out, int use_double, cudaStream_t st) {
+    fad::FrontendTables tab{h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count};
+    const long long frames = n * fad::kExFrames;
+    long long blocks = (frames + fad::kFeWarps - 1) / fad::kFeWarps;
+    const long long cap = (long long)h->num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return 0;
+    if (use_double)
+        fad::logmel_kernel<double><<<(int)blocks, fad::kFeWarps * 32, fad::logmel_smem_bytes<double>(), st>>>(
+            pcm, ex_start, (int)n, tab, out);
+    else
+        fad::logmel_kernel<float><<<(int)blocks, fad::kFeWarps * 32, fad::logmel_smem_bytes<float>(), st>>>(
+            pcm, ex_start, (int)n, tab, out);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int fad_vggish_logmel(fad_handle* h, const int16_t* pcm, const long long* ex_start,
+                      long long n_examples, float* logmel_out, int use_double, void* stream) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    return launch_logmel(h, pcm, ex_start, n_examples, logmel_out, use_double, (cudaStream_t)stream);
+}
+
+int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_start,
+                       long long n_examples, void* emb_out_f16, void* stream) {
+    if (!h) return fail("null handle");
+    if (!h->vgg_loaded) return fail("fad_vggish_load has not been called");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static const int fe_double = []() { const char* e = getenv("FADTK_FRONTEND_FP32"); return (e && e[0] == '1') ? 0 : 1; }();
+    for (long long base = 0; base < n_examples; base += h->max_examples) {
+        const int nb = (int)((n_examples - base) < h->max_examples ? (n_examples - base) : h->max_examples);
+        if (launch_logmel(h, pcm, ex_start + base, nb, h->logmel, fe_double, st)) return 1;
+        fad::conv1_kernel<<<dim3(6, nb), 256, 0, st>>>(h->logmel, h->conv1_w, h->conv1_b, h->act[0]);
+        CK(cudaGetLastError());
+        h->launches++;
+        for (int i = 0; i < 8; ++i) {
+            const float* bias = i < 5 ? h->conv_b[i] : h->fc_b[i - 5];
+            void* out = (i == 7) ? (void*)((__half*)emb_out_f16 + (size_t)base * 128) : (void*)h->act[i + 1];
+            if (run_layer(h, h->geom[i], h->map_x[i], h->map_w[i], nb, bias, out, nullptr, st)) return 1;
+        }
+    }
+    return 0;
+}
+
+int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int Cin,
+                   const void* w_f16, const float* bias, int Cout, int taps, int relu, int pool,
+                   void* out_f16, float* out_f32_or_null, void* stream) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    LayerGeom g;
+    if (make_geom(g, H, W, Cin, Cout, taps, relu, pool)) return 1;
+    if (pool && out_f32_or_null) return fail("fp32 copy is only available for un-pooled layers");
+    CUtensorMap mx, mw;
+    if (encode_layer_maps(g, x_f16, NB, w_f16, &mx, &mw)) return 1;
+    return run_layer(h, g, mx, mw, NB, bias, out_f16, out_f32_or_null, (cudaStream_t)stream);
+}
+
+// -------------------------------------------------------------------------- statistics
+size_t fad_stats_acc_len(int d) { return 1 + 2 * (size_t)d + (size_t)d * d; }
+
+int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, int d,
+                         const void* shift_f16, double* acc, int use_simt, void* stream) {
+    if (!h) return fail("null handle");
+    if (n_rows <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const __half* E = reinterpret_cast<const __half*>(emb_f16);
+    const __half* shift = reinterpret_cast<const __half*>(shift_f16);
+    if (use_simt) {
+        if (d % 64 != 0) return fail("d must be a multiple of 64");
+        dim3 grid((unsigned)((n_rows + fad::kSimtRows - 1) / fad::kSimtRows), d / 64, d / 64);
+        fad::stats_simt_kernel<<<grid, 256, 0, st>>>(E, n_rows, d, shift, acc);
+        CK(cudaGetLastError());
+        h->launches++;
+        return 0;
+    }
+    if (d % 128 != 0) return fail("d must be a multiple of 128 for the tensor-core statistics kernel");
+    fad::StatsJobParams p;
+    p.n_rows = n_rows; p.d = d; p.n_tiles = d / 128;
+    p.n_pairs = p.n_tiles * (p.n_tiles + 1) / 2;
+    const long long stages = (n_rows + 63) / 64;
+    long long want = (2LL * h->num_sms) / p.n_pairs;          // ~2 waves of jobs
+    if (p.n_pairs == 1) want = h->num_sms;
+    if (want < 1) want = 1;
+    long long per = (stages + want - 1) / want;                // 64-row stages per split
+    if (per < 4) per = 4;                                      // at least one 256-row chunk
+    p.n_splits = (int)((stages + per - 1) / per);
+    p.rows_per_split = per * 64;
+    p.shift = shift;
+    const size_t jobs = (size_t)p.n_pairs * p.n_splits;
+    if (ensure((void**)&h->ws_tiles, &h->ws_tiles_cap, jobs * 128 * 128 * 8)) return 1;
+    if (ensure((void**)&h->ws_sums, &h->ws_sums_cap, (size_t)p.n_tiles * p.n_splits * 2 * 128 * 8)) return 1;
+    p.ws_tiles = h->ws_tiles; p.ws_sums = h->ws_sums;
+    CUtensorMap me;
+    const uint64_t ed[2] = {(uint64_t)d, (uint64_t)n_rows};
+    const uint64_t es[1] = {(uint64_t)d * 2};
+    const uint32_t eb[2] = {64, 64};
+    if (encode_f16_map(&me, E, 2, ed, es, eb)) return 1;
+    fad::stats_umma_kernel<<<(unsigned)jobs, fad::kStThreads, fad::kStSmemBytes, st>>>(me, p);
+    CK(cudaGetLastError());
+    fad::stats_reduce_kernel<<<p.n_pairs, 256, 0, st>>>(p, acc);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return 0;
+}
+
+int fad_stats_accumulate_gather(fad_handle* h, const void* emb_f16, long long n_src_rows,
+                                const long long* idx, long long n_idx, int d,
+                                const void* shift_f16, double* acc, void* stream) {
+    if (!h) return fail("null handle");
+    (void)n_src_rows;
+    if (n_idx <= 0) return 0;
+    if (d % 8 != 0) return fail("d must be a multiple of 8");
+    CK(cudaSetDevice(h->device));
+    if (ensure((void**)&h->gather_buf, &h->gather_cap, (size_t)n_idx * d * 2)) return 1;
+    const long long vecs = n_idx * (d / 8);
+    long long blocks = (vecs + 255) / 256;
+    if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+    fad::gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(emb_f16), idx, n_idx, d, h->gather_buf);
+    CK(cudaGetLastError());
+    h->launches++;
+    return fad_stats_accumulate(h, h->gather_buf, n_idx, d, shift_f16, acc, 0, stream);
+}
+
+int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, int d,
+                       double* mu_out, double* cov_out, void* stream) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    const size_t total = (size_t)d * d;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (blocks > (unsigned)h->num_sms * 8) blocks = h->num_sms * 8;
+    fad::stats_finalize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        acc, reinterpret_cast<const __half*>(shift_f16), d, mu_out, cov_out);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- Frechet
+namespace {
+int launch_dgemm(fad_handle* h, const double* A, const double* B, double* C, int d, double alpha,
+                 double beta_diag, double* trace, cudaStream_t st) {
+    dim3 grid((d + 63) / 64, (d + 63) / 64);
+    fad::dgemm_kernel<<<grid, 256, 0, st>>>(A, B, C, d, alpha, beta_diag, trace);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// Coupled Newton-Schulz: on return Y ~ sqrt(sym(A)/|A|_F); scal[0..1] = |A|_F, tr A; trY set.
+int newton_schulz(fad_handle* h, const double* A, int d, int iters, double* Y, double* Z, double* W,
+                  double* T, double* scal, double* trY, double* trZ, cudaStream_t st) {
+    const size_t total = (size_t)d * d;
+    unsigned eb = (unsigned)((total + 255) / 256);
+    if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
+    fad::norm_trace_kernel<<<1, 256, 0, st>>>(A, d, scal);
+    fad::ns_init_kernel<<<eb, 256, 0, st>>>(A, d, scal, Y, Z);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    double* Yc = Y; double* Zc = Z; double* Yn = T; double* Zn = T + total;
+    for (int it = 0; it < iters; ++it) {
+        if (launch_dgemm(h, Zc, Yc, W, d, -0.5, 1.5, nullptr, st)) return 1;      // W = 1.5 I - 0.5 Z Y
+        const bool last = (it == iters - 1);
+        if (last) { CK(cudaMemsetAsync(trY, 0, sizeof(double), st)); CK(cudaMemsetAsync(trZ, 0, sizeof(double), st)); }
+        if (launch_dgemm(h, Yc, W, Yn, d, 1.0, 0.0, last ? trY : nullptr, st)) return 1;   // Y <- Y W
+        if (launch_dgemm(h, W, Zc, Zn, d, 1.0, 0.0, last ? trZ : nullptr, st)) return 1;   // Z <- W Z
+        double* t = Yc; Yc = Yn; Yn = t;
+        t = Zc; Zc = Zn; Zn = t;
+    }
+    if (Yc != Y) {
+        CK(cudaMemcpyAsync(Y, Yc, total * 8, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(Z, Zc, total * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+}  // namespace
+
+int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const double* mu2,
+                const double* cov2, int d, int iters, double* out, void* stream) {
+    if (!h) return fail("null handle");
+    if (d <= 0) return fail("bad dimension");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iters <= 0) iters = 60;
+    const size_t total = (size_t)d * d;
+    // buffers: Y Z W T(2) S M P  -> 8 matrices
+    if (ensure((void**)&h->fr_buf, &h->fr_cap, 8 * total * 8)) return 1;
+    double* Y = h->fr_buf;           double* Z = Y + total;   double* W = Z + total;
+    double* T = W + total;           /* T uses 2 matrices */  double* S = T + 2 * total;
+    double* M = S + total;           double* P = M + total;
+    double* scalA = h->fr_scal;      double* scalB = scalA + 2;  double* scalM = scalA + 4;
+    double* trY = scalA + 6;         double* resid = scalA + 7;  double* trS = scalA + 8;
+    double* trZ = scalA + 9;         double* trZs = scalA + 10;
+    unsigned eb = (unsigned)((total + 255) / 256);
+    if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
+
+    // S = C1^(1/2)
+    if (newton_schulz(h, cov1, d, iters, Y, Z, W, T, scalA, trS, trZs, st)) return 1;
+    fad::ns_unscale_kernel<<<eb, 256, 0, st>>>(Y, d, scalA, S);
+    // M = S C2 S
+    fad::norm_trace_kernel<<<1, 256, 0, st>>>(cov2, d, scalB);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    if (launch_dgemm(h, S, cov2, P, d, 1.0, 0.0, nullptr, st)) return 1;
+    if (launch_dgemm(h, P, S, M, d, 1.0, 0.0, nullptr, st)) return 1;
+    // tr sqrt(M)
+    if (newton_schulz(h, M, d, iters, Y, Z, W, T, scalM, trY, trZ, st)) return 1;
+    // residual | Y^2 - sym(M)/|M|_F |_F
+    CK(cudaMemsetAsync(resid, 0, sizeof(double), st));
+    if (launch_dgemm(h, Y, Y, P, d, 1.0, 0.0, nullptr, st)) return 1;
+    fad::resid_kernel<<<eb, 256, 0, st>>>(P, M, d, scalM, resid);
+    fad::frechet_assemble_kernel<<<1, 256, 0, st>>>(mu1, mu2, d, scalA, scalB, scalM, trY, trZ, resid, iters, out);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+// Sufficient statistics of an embedding matrix E[N, d] (fp16):   n,  sum(y),  sum(y y^T)
+// with y = fp16(x - shift).  Replaces np.mean / np.cov in fadtk/fad.py:42-48 and the per-file
+// scatter + Chan merge in fadtk/utils.py:13-46 with one shifted E^T E contraction.
+//
+// stats_umma_kernel   tcgen05 path.  E is row-major, so both operands of E^T E are "MN-major":
+//   a TMA box [64 rows x 64 cols] with 128-B swizzle IS the canonical MN-major SWIZZLE_128B
+//   UMMA layout (K = row index).  One CTA = one job = (128x128 output tile (ti<=tj), row range).
+//     warp 0      TMA producer: per 64-row stage, two 64-column boxes per panel
+//     warps 4-7   transform: subtract the shift IN PLACE in smem (fp16, exact when x ~ shift),
+//                 zero rows past the end, accumulate column sums in fp64 registers
+//     warp 1      MMA issuer: 4 x tcgen05.mma (K=16) per stage, fp32 accumulate in TMEM;
+//                 products of fp16 values are exact in fp32
+//     warps 8-11  drain: every 256 rows the TMEM tile is added into an fp64 tile in shared
+//                 memory, which bounds the fp32 accumulation length (tensor-core adds truncate)
+//   Each job stores its fp64 tile to a workspace; stats_reduce_kernel sums jobs in a fixed
+//   order (deterministic) into the caller's packed accumulator.
+// stats_simt_kernel    plain fp64 CUDA-core version of the same contraction (verification).
+//
+// Packed accumulator (fp64, caller-owned, all-reduced across GPUs as-is):
+//   acc[0] = n,  acc[1 .. d] = sum(x - shift) (exact, fp64),  acc[1+d .. 1+d+d*d) = sum(y y^T)
+//   (d x d, full, row-major),  acc[1+d+d*d ..] = sum(y)  (the fp16-rounded rows, for centring)
+#pragma once
+#include "sm100.cuh"
+
+namespace fad {
+
+constexpr int kStTile = 128;
+constexpr int kStStageRows = 64;
+constexpr int kStChunkRows = 256;                  // rows per fp32 TMEM accumulation
+constexpr int kStStages = 3;
+constexpr uint32_t kStPanelBytes = kStStageRows * kStTile * 2;   // 16 KiB: two 64x64 boxes
+constexpr uint32_t kStStageBytes = 2 * kStPanelBytes;            // A panel + B panel
+constexpr int kStThreads = 384;
+constexpr uint32_t kStSmemBytes = kStStages * kStStageBytes + kStTile * kStTile * 8 + 1024 + 256;
+
+struct StatsJobParams {
+    long long n_rows;          // valid rows in E
+    int d;
+    int n_tiles;               // d / 128
+    int n_pairs;               // n_tiles (n_tiles + 1) / 2
+    int n_splits;              // row splits per tile pair
+    long long rows_per_split;  // multiple of 64
+    const __half* shift;       // [d]
+    double* ws_tiles;          // [n_pairs * n_splits][128 (col)][128 (row)]
+    double* ws_sums;           // [n_tiles * n_splits][2][128]  (exact x-shift sums | rounded y sums)
+};
+
+__device__ __forceinline__ void pair_to_tiles(int pair, int n_tiles, int& ti, int& tj) {
+    ti = 0;
+    int rem = pair;
+    while (rem >= n_tiles - ti) { rem -= n_tiles - ti; ++ti; }
+    tj = ti + rem;
+}
+
+__global__ void __launch_bounds__(kStThreads, 1)
+stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParams p)
+{
+    using namespace sm100;
+    constexpr uint32_t kIdesc = make_idesc(FMT_F16, kStTile, kStTile, /*a MN-major*/1, /*b MN-major*/1);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    double* acc64 = reinterpret_cast<double*>(smem + kStStages * kStStageBytes);     // [col][row]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStStages * kStStageBytes + kStTile * kStTile * 8);
+    uint64_t* full = bars;                       // TMA landed
+    uint64_t* ready = bars + kStStages;          // transform done
+    uint64_t* empty = bars + 2 * kStStages;      // MMAs retired
+    uint64_t* tmem_full = bars + 3 * kStStages;
+    uint64_t* tmem_empty = bars + 3 * kStStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.x;
+    const int pair = job / p.n_splits, split = job % p.n_splits;
+    int ti, tj;
+    pair_to_tiles(pair, p.n_tiles, ti, tj);
+    const bool diag = (ti == tj);
+    const long long row_begin = (long long)split * p.rows_per_split;
+    long long row_end = row_begin + p.rows_per_split;
+    if (row_end > p.n_rows) row_end = p.n_rows;
+    const long long span = row_end > row_begin ? row_end - row_begin : 0;
+    const int n_stages_total = (int)((span + kStStageRows - 1) / kStStageRows);
+    const int n_chunks = (n_stages_total + 3) / 4;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&map_e);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<256>(tmem_slot);
+    for (int i = threadIdx.x; i < kStTile * kStTile; i += kStThreads) acc64[i] = 0.0;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < n_stages_total; ++it) {
+                const int r0 = (int)(row_begin + (long long)it * kStStageRows);
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], diag ? kStPanelBytes : kStStageBytes);
+                uint8_t* st = smem + s * kStStageBytes;
+                tma_load_2d(st, &map_e, &full[s], ti * kStTile, r0);
+                tma_load_2d(st + 8192, &map_e, &full[s], ti * kStTile + 64, r0);
+                if (!diag) {
+                    tma_load_2d(st + kStPanelBytes, &map_e, &full[s], tj * kStTile, r0);
+                    tma_load_2d(st + kStPanelBytes + 8192, &map_e, &full[s], tj * kStTile + 64, r0);
+                }
+                if (++s == kStStages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            int s = 0; uint32_t ph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            int it = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * kStTile;
+                const int n_st = min(4, n_stages_total - it);
+                for (int q = 0; q < n_st; ++q, ++it) {
+                    mbar_wait(&ready[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + s * kStStageBytes);
+                    const uint32_t b_addr = diag ? a_addr : a_addr + kStPanelBytes;
+                    // MN-major SW128: 64-col blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO)
+                    const uint64_t a_desc = mnmajor_sw128_desc(a_addr, 8192, 1024);
+                    const uint64_t b_desc = mnmajor_sw128_desc(b_addr, 8192, 1024);
+#pragma unroll
+                    for (int k = 0; k < kStStageRows / 16; ++k) {
+                        // 16 K-rows = 2048 B -> +128 in the 16-B address field
+                        umma_f16(d_tmem, a_desc + 128 * k, b_desc + 128 * k, kIdesc, (q | k) != 0);
+                    }
+                    umma_commit(&empty[s]);
+                    if (++s == kStStages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---------------------------------------------------------- shift transform
+        const int t = threadIdx.x - 128;             // 0..127
+        const int cg = t & 15;                        // 16-B column group inside the 128-col panel
+        const int rl = t >> 4;                        // row lane 0..7
+        const int cb = cg >> 3, lc = cg & 7;
+        const uint32_t chunk_off = cb * 8192 + ((lc ^ rl) << 4);   // swizzled position of (row%8==rl, lc)
+        __half2 shA[4], shB[4];
+        {
+            const uint4 a = *reinterpret_cast<const uint4*>(p.shift + ti * kStTile + cg * 8);
+            const uint4 b = *reinterpret_cast<const uint4*>(p.shift + tj * kStTile + cg * 8);
+            shA[0] = *reinterpret_cast<const __half2*>(&a.x); shA[1] = *reinterpret_cast<const __half2*>(&a.y);
+            shA[2] = *reinterpret_cast<const __half2*>(&a.z); shA[3] = *reinterpret_cast<const __half2*>(&a.w);
+            shB[0] = *reinterpret_cast<const __half2*>(&b.x); shB[1] = *reinterpret_cast<const __half2*>(&b.y);
+            shB[2] = *reinterpret_cast<const __half2*>(&b.z); shB[3] = *reinterpret_cast<const __half2*>(&b.w);
+        }
+        double colsum[8], colsum_x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { colsum[j] = 0.0; colsum_x[j] = 0.0; }
+        int s = 0; uint32_t ph = 0;
+        for (int it = 0; it < n_stages_total; ++it) {
+            const long long r0 = row_begin + (long long)it * kStStageRows;
+            mbar_wait(&full[s], ph);
+            uint8_t* st = smem + s * kStStageBytes;
+#pragma unroll
+            for (int panel = 0; panel < 2; ++panel) {
+                if (panel == 1 && diag) break;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rl + 8 * i;
+                    uint4* ptr = reinterpret_cast<uint4*>(st + panel * kStPanelBytes + chunk_off + r * 128);
+                    uint4 v = *ptr;
+                    __half2* h = reinterpret_cast<__half2*>(&v);
+                    if (r0 + r < row_end) {
+                        if (panel == 0 && diag) {
+                            // x - shift is exact in fp32 (two fp16 values): exact column sums for the mean
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 fx = __half22float2(h[j]), fs = __half22float2(shA[j]);
+                                colsum_x[2 * j] += (double)(fx.x - fs.x); colsum_x[2 * j + 1] += (double)(fx.y - fs.y);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) h[j] = __hsub2(h[j], panel ? shB[j] : shA[j]);
+                        if (panel == 0 && diag) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __half22float2(h[j]);
+                                colsum[2 * j] += (double)f.x; colsum[2 * j + 1] += (double)f.y;
+                            }
+                        }
+                    } else {
+                        v = make_uint4(0, 0, 0, 0);
+                    }
+                    *ptr = v;
+                }
+            }
+            fence_proxy_async_smem();                 // generic-proxy stores -> visible to UMMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);
+            if (++s == kStStages) { s = 0; ph ^= 1; }
+        }
+        // column sums: reduce the 8 row lanes through the (now idle) stage-0 buffer
+        if (diag) {
+            if (n_chunks > 0) {
+                // every MMA of this job has retired once the last accumulator is committed
+                const int last = n_chunks - 1;
+                mbar_wait(&tmem_full[last & 1], (uint32_t)((last >> 1) & 1));
+            }
+            __syncwarp();
+            asm volatile("bar.sync 1, 128;");
+            double* red = reinterpret_cast<double*>(smem);       // [2][8 row lanes][128 cols]
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                red[rl * 128 + cg * 8 + j] = colsum_x[j];
+                red[1024 + rl * 128 + cg * 8 + j] = colsum[j];
+            }
+            asm volatile("bar.sync 1, 128;");
+            double tot_x = 0.0, tot_y = 0.0;
+            for (int k = 0; k < 8; ++k) { tot_x += red[k * 128 + t]; tot_y += red[1024 + k * 128 + t]; }
+            double* wsum = p.ws_sums + ((size_t)ti * p.n_splits + split) * 2 * kStTile;
+            wsum[t] = tot_x;
+            wsum[kStTile + t] = tot_y;
+        }
+    } else if (warp >= 8) {
+        // -------------------------------------------------- drain TMEM -> fp64 smem
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tc_fence_after_sync();
+            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * kStTile;
+#pragma unroll 1
+            for (int cc = 0; cc < kStTile / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + cc * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    acc64[(cc * 32 + j) * kStTile + row] += (double)__uint_as_float(v[j]);
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+        double* dst = p.ws_tiles + (size_t)job * kStTile * kStTile;
+        for (int col = 0; col < kStTile; ++col) dst[col * kStTile + row] = acc64[col * kStTile + row];
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<256>(tmem_base);
+}
+
+// acc += sum over row splits of the job tiles (fixed order => deterministic).
+// grid = (n_pairs), block = 256
+__global__ void stats_reduce_kernel(StatsJobParams p, double* __restrict__ acc)
+{
+    const int pair = blockIdx.x;
+    int ti, tj;
+    pair_to_tiles(pair, p.n_tiles, ti, tj);
+    const int d = p.d;
+    double* outer = acc + 1 + d;
+    for (int e = threadIdx.x; e < kStTile * kStTile; e += blockDim.x) {
+        const int col = e / kStTile, row = e % kStTile;        // workspace layout is [col][row]
+        double v = 0.0;
+        for (int s = 0; s < p.n_splits; ++s)
+            v += p.ws_tiles[((size_t)pair * p.n_splits + s) * kStTile * kStTile + e];
+        const int I = ti * kStTile + row, J = tj * kStTile + col;
+        outer[(size_t)I * d + J] += v;
+        if (ti != tj) outer[(size_t)J * d + I] += v;
+    }
+    if (ti == tj) {
+        for (int c = threadIdx.x; c < kStTile; c += blockDim.x) {
+            double vx = 0.0, vy = 0.0;
+            for (int s = 0; s < p.n_splits; ++s) {
+                const double* wsum = p.ws_sums + ((size_t)ti * p.n_splits + s) * 2 * kStTile;
+                vx += wsum[c]; vy += wsum[kStTile + c];
+            }
+            acc[1 + ti * kStTile + c] += vx;
+            acc[1 + (size_t)d + (size_t)d * d + ti * kStTile + c] += vy;
+        }
+    }
+    if (pair == 0 && threadIdx.x == 0) acc[0] += (double)p.n_rows;
+}
+
+// --------------------------------------------------------------------------------------
+// fp64 CUDA-core version (verification path).  grid = (row chunks, d/64, d/64) upper tiles only.
+constexpr int kSimtRows = 1024;
+__global__ void __launch_bounds__(256)
+stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
+                  const __half* __restrict__ shift, double* __restrict__ acc)
+{
+    const int ti = blockIdx.y, tj = blockIdx.z;
+    if (tj < ti) return;
+    __shared__ double yi[32][65], yj[32][65];
+    const long long r_begin = (long long)blockIdx.x * kSimtRows;
+    const long long r_end = min(n_rows, r_begin + kSimtRows);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 4x4 outputs per thread
+    double c[4][4] = {};
+    double csum = 0.0, csum_x = 0.0;
+    __shared__ float xi[32][65];        // x - shift is exact in fp32
+    for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
+        for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+            const int r = i >> 6, cc = i & 63;
+            double a = 0.0, b = 0.0; float ax = 0.0f;
+            if (r0 + r < r_end) {
+                const __half* rowp = E + (size_t)(r0 + r) * d;
+                a = (double)__half2float(__hsub(rowp[ti * 64 + cc], shift[ti * 64 + cc]));
+                b = (double)__half2float(__hsub(rowp[tj * 64 + cc], shift[tj * 64 + cc]));
+                ax = __half2float(rowp[ti * 64 + cc]) - __half2float(shift[ti * 64 + cc]);
+            }
+            yi[r][cc] = a; yj[r][cc] = b; xi[r][cc] = ax;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = yi[r][ty * 4 + u]; b[u] = yj[r][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) c[u][v] = fma(a[u], b[v], c[u][v]);
+        }
+        if (ti == tj && threadIdx.x < 64)
+            for (int r = 0; r < 32; ++r) { csum += yi[r][threadIdx.x]; csum_x += (double)xi[r][threadIdx.x]; }
+        __syncthreads();
+    }
+    double* outer = acc + 1 + d;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int I = ti * 64 + ty * 4 + u, J = tj * 64 + tx * 4 + v;
+            atomicAdd(&outer[(size_t)I * d + J], c[u][v]);
+            if (ti != tj) atomicAdd(&outer[(size_t)J * d + I], c[u][v]);
+        }
+    if (ti == tj && threadIdx.x < 64) {
+        atomicAdd(&acc[1 + ti * 64 + threadIdx.x], csum_x);
+        atomicAdd(&acc[1 + (size_t)d + (size_t)d * d + ti * 64 + threadIdx.x], csum);
+    }
+    if (blockIdx.x == 0 && ti == 0 && tj == 0 && threadIdx.x == 0) atomicAdd(&acc[0], (double)n_rows);
+}
+
+// mu = shift + sum(x-shift)/n ; cov = (outer - sum(y) sum(y)^T / n) / (n - 1)   (cov = 0 when n < 2,
+// fadtk/utils.py:42-43).  grid-stride over d*d.
+__global__ void stats_finalize_kernel(const double* __restrict__ acc, const __half* __restrict__ shift,
+                                      int d, double* __restrict__ mu, double* __restrict__ cov)
+{
+    const double n = acc[0];
+    const double* sum_x = acc + 1;
+    const double* outer = acc + 1 + d;
+    const double* sum = acc + 1 + (size_t)d + (size_t)d * d;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)d * d;
+         e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / d), j = (int)(e % d);
+        cov[e] = n < 2.0 ? 0.0 : (outer[e] - sum[i] * sum[j] / n) / (n - 1.0);
+        if (j == 0) mu[i] = (double)__half2float(shift[i]) + (n > 0.0 ? sum_x[i] / n : 0.0);
+    }
+}
+
+// out[i, :] = src[idx[i], :]  (FAD-inf bootstrap gather, fadtk/fad.py:333-334); 16-B vectors.
+__global__ void gather_rows_kernel(const __half* __restrict__ src, const long long* __restrict__ idx,
+                                   long long n_out, int d, __half* __restrict__ out)
+{
+    const int vec_per_row = d / 8;
+    const long long total = n_out * vec_per_row;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / vec_per_row;
+        const int v = (int)(e % vec_per_row);
+        reinterpret_cast<uint4*>(out)[e] = reinterpret_cast<const uint4*>(src + (size_t)idx[i] * d)[v];
+    }
+}
+
+}  // namespace fad

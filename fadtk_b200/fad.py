@@ -1,0 +1,306 @@
+"""FAD engine (mirror of fadtk/fad.py): same functions, class, methods, on-disk layout and
+error behaviour; the arithmetic runs on the B200 through the C ABI.
+
+    calc_embd_statistics      fad.py:42-48   -> shifted E^T E tensor-core kernel (csrc/stats.cuh)
+    calc_frechet_distance     fad.py:51-120  -> Newton-Schulz GEMM chain on the PSD form (csrc/frechet.cuh)
+    FrechetAudioDistance      fad.py:123-395 -> same methods; file <-> GPU staging is batched
+"""
+from __future__ import annotations
+
+import logging
+import os
+import traceback
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from typing import NamedTuple, Union
+
+import numpy as np
+import torch
+
+from . import synth
+from .model_loader import ModelLoader
+from .utils import *  # noqa: F401,F403  (the reference re-exports utils from fad)
+from .utils import DeviceStatistics, PathLike, calculate_embd_statistics_online, find_sox_formats, \
+    get_cache_embedding_path, statistics_of_arrays
+
+log = logging.getLogger("fadtk_b200")
+if not log.handlers:
+    _h = logging.StreamHandler()
+    _h.setFormatter(logging.Formatter("%(asctime)s %(levelname)s %(message)s", "%H:%M:%S"))
+    log.addHandler(_h)
+    log.setLevel(os.environ.get("FADTK_LOGLEVEL", "INFO"))
+
+sox_path = os.environ.get('SOX_PATH', 'sox')
+
+
+class FADInfResults(NamedTuple):
+    score: float
+    slope: float
+    r2: float
+    points: list[tuple[int, float]]
+
+
+def calc_embd_statistics(embd_lst: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Mean and covariance matrix of an [n, d] embedding array (fadtk/fad.py:42-48).
+
+    Like numpy in the reference, the mean comes back in the dtype of the input (fp16 embeddings
+    give an fp16 mean) and the covariance in float64.
+    """
+    assert embd_lst.shape[0] >= 2, (f"FAD requires at least two embedding window frames, you have {embd_lst.shape}."
+        " (This probably means that your audio is too short)")
+    mu, cov = statistics_of_arrays([embd_lst])
+    if np.issubdtype(embd_lst.dtype, np.floating):
+        mu = mu.astype(embd_lst.dtype)
+    return mu, cov
+
+
+def _frechet_parts(cov1, cov2):
+    """-> (tr C1, tr C2, tr sqrt(C1 C2), residual) from the GPU chain."""
+    from . import _native
+    eng = _native.engine()
+    dev = eng.torch_device
+    d = cov1.shape[0]
+    c1 = torch.from_numpy(np.ascontiguousarray(cov1, dtype=np.float64)).to(dev)
+    c2 = torch.from_numpy(np.ascontiguousarray(cov2, dtype=np.float64)).to(dev)
+    z = torch.zeros(d, dtype=torch.float64, device=dev)
+    out = eng.frechet(z, c1, z, c2).cpu().numpy()
+    return out[5], out[6], out[1], out[2]
+
+
+def calc_frechet_distance(mu1, cov1, mu2, cov2, eps=1e-6):
+    """Frechet distance between N(mu1, cov1) and N(mu2, cov2) (fadtk/fad.py:51-120):
+
+        d^2 = ||mu1 - mu2||^2 + Tr(cov1 + cov2 - 2 sqrt(cov1 cov2))
+
+    The reference takes Tr sqrt(cov1 cov2) from an eigen-decomposition of the non-symmetric
+    product; here it is the trace of the square root of the similar PSD matrix
+    cov1^(1/2) cov2 cov1^(1/2) (same eigenvalues), computed on the GPU.  ``eps`` is accepted for
+    signature compatibility: the PSD form has no singular-product failure mode to regularise.
+    """
+    mu1 = np.atleast_1d(mu1)
+    mu2 = np.atleast_1d(mu2)
+    cov1 = np.atleast_2d(cov1)
+    cov2 = np.atleast_2d(cov2)
+
+    assert mu1.shape == mu2.shape, \
+        f'Training and test mean vectors have different lengths ({mu1.shape} vs {mu2.shape})'
+    assert cov1.shape == cov2.shape, \
+        f'Training and test covariances have different dimensions ({cov1.shape} vs {cov2.shape})'
+
+    diff = mu1 - mu2            # numpy dtype rules as in the reference (fp16 - fp16 stays fp16)
+    tr1, tr2, tr_covmean, resid = _frechet_parts(cov1, cov2)
+    if not np.isfinite(tr_covmean):
+        raise ValueError("non-finite covariance statistics (NaN/Inf input)")
+    if resid > 1e-3:
+        log.warning(f'Detected high error in matrix square root: residual {resid}')
+    return (diff.dot(diff) + tr1 + tr2 - 2 * tr_covmean)
+
+
+class FrechetAudioDistance:
+    """Same constructor and methods as fadtk.fad.FrechetAudioDistance (fad.py:123-395)."""
+    loaded = False
+
+    def __init__(self, ml: ModelLoader, audio_load_worker=8, load_model=True):
+        self.ml = ml
+        self.audio_load_worker = audio_load_worker
+        self.sox_formats = find_sox_formats(sox_path)
+        self.device = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
+        if load_model:
+            self.ml.load_model()
+            self.loaded = True
+        torch.autograd.set_grad_enabled(False)
+
+    # ------------------------------------------------------------------ audio
+    def _converted_path(self, f: Path) -> Path:
+        return (f.parent / "convert" / str(self.ml.sr) / f.name).with_suffix(".wav")
+
+    def convert_audio(self, f: Union[str, Path]) -> np.ndarray:
+        """Decode -> mono -> model sample rate -> PCM16; cached under <dir>/convert/<sr>/ like
+        the reference (fad.py:143-160).  Returns the int16 samples."""
+        f = Path(f)
+        new = self._converted_path(f)
+        if new.exists():
+            return synth.read_wav(new)[0]
+        new.parent.mkdir(parents=True, exist_ok=True)
+        if f.suffix.lower() == ".wav":
+            pcm, sr = synth.read_wav(f)
+            x = None
+        else:
+            import torchaudio                    # needs a decoding backend (absent in this image)
+            x, sr = torchaudio.load(str(f))
+            pcm = None
+        if pcm is not None and pcm.ndim == 1 and sr == self.ml.sr:
+            out = pcm                            # already mono PCM16 at the model rate: bit-exact copy
+        else:
+            if x is None:
+                x = torch.from_numpy((pcm if pcm.ndim > 1 else pcm[:, None]).T.astype(np.float32) / 32768.0)
+            x = torch.mean(x, 0).unsqueeze(0)
+            if sr != self.ml.sr:
+                import torchaudio
+                resampler = torchaudio.transforms.Resample(
+                    sr, self.ml.sr, lowpass_filter_width=64, rolloff=0.9475937167399596,
+                    resampling_method="sinc_interp_kaiser", beta=14.769656459379492)
+                x = resampler(x)
+            out = torch.clamp(torch.round(x[0] * 32768.0), -32768, 32767).to(torch.int16).numpy()
+        synth.write_wav(new, out, self.ml.sr)
+        return out
+
+    def load_audio(self, f: Union[str, Path]):
+        self.convert_audio(f)
+        return self.ml.load_wav(self._converted_path(Path(f)))
+
+    # ------------------------------------------------------------- embeddings
+    def cache_embedding_file(self, audio_dir: Union[str, Path]):
+        """Compute the embedding of one audio file and cache it (fad.py:188-201)."""
+        cache = get_cache_embedding_path(self.ml.name, audio_dir)
+        if cache.exists():
+            return
+        wav_data = self.load_audio(audio_dir)
+        embd = self.ml.get_embedding(wav_data)
+        cache.parent.mkdir(parents=True, exist_ok=True)
+        np.save(cache, embd)
+
+    def read_embedding_file(self, audio_dir: Union[str, Path]):
+        cache = get_cache_embedding_path(self.ml.name, audio_dir)
+        assert cache.exists(), f"Embedding file {cache} does not exist, please run cache_embedding_file first."
+        return np.load(cache)
+
+    def load_embeddings(self, dir: Union[str, Path], max_count: int = -1, concat: bool = True):
+        files = list(Path(dir).glob("*.*"))
+        log.info(f"Loading {len(files)} audio files from {dir}...")
+        return self._load_embeddings(files, max_count=max_count, concat=concat)
+
+    def _load_embeddings(self, files: list[Path], max_count: int = -1, concat: bool = True):
+        if len(files) == 0:
+            raise ValueError("No files provided")
+        if max_count == -1:
+            with ThreadPoolExecutor(max(1, self.audio_load_worker)) as ex:
+                embd_lst = list(ex.map(self.read_embedding_file, files))
+        else:
+            total_len = 0
+            embd_lst = []
+            for f in files:
+                embd_lst.append(self.read_embedding_file(f))
+                total_len += embd_lst[-1].shape[0]
+                if total_len > max_count:
+                    break
+        if concat:
+            return np.concatenate(embd_lst, axis=0)
+        return embd_lst, files
+
+    # ------------------------------------------------------------- statistics
+    def load_stats(self, path: PathLike):
+        """Embedding statistics of a named set, an .npz file or a directory (fad.py:245-290)."""
+        if isinstance(path, str):
+            for bp in (Path(os.environ.get("FADTK_STATS_DIR", "")), Path(__file__).parent / "stats"):
+                stats = bp / (path.lower() + ".npz")
+                if str(bp) != "." and stats.exists():
+                    path = stats
+                    break
+        path = Path(path)
+
+        if path.is_file():
+            log.info(f"Loading embedding statistics from {path}...")
+            with np.load(path) as data:
+                if f'{self.ml.name}.mu' not in data or f'{self.ml.name}.cov' not in data:
+                    raise ValueError(f"FAD statistics file {path} doesn't contain data for model {self.ml.name}")
+                return data[f'{self.ml.name}.mu'], data[f'{self.ml.name}.cov']
+
+        cache_dir = path / "stats" / self.ml.name
+        emb_dir = path / "embeddings" / self.ml.name
+        if cache_dir.exists():
+            log.info(f"Embedding statistics is already cached for {path}, loading...")
+            return np.load(cache_dir / "mu.npy"), np.load(cache_dir / "cov.npy")
+
+        if not path.is_dir():
+            log.error(f"The dataset you want to use ({path}) is not a directory nor a file.")
+            exit(1)
+
+        log.info(f"Loading embedding files from {path}...")
+        mu, cov = calculate_embd_statistics_online(sorted(emb_dir.glob("*.npy")))
+        log.info("> Embeddings statistics calculated.")
+
+        cache_dir.mkdir(parents=True, exist_ok=True)
+        np.save(cache_dir / "mu.npy", mu)
+        np.save(cache_dir / "cov.npy", cov)
+        return mu, cov
+
+    # ------------------------------------------------------------------ scores
+    def score(self, baseline: PathLike, eval: PathLike):
+        """A single FAD score between a baseline and an eval set (fad.py:292-302)."""
+        mu_bg, cov_bg = self.load_stats(baseline)
+        mu_eval, cov_eval = self.load_stats(eval)
+        return calc_frechet_distance(mu_bg, cov_bg, mu_eval, cov_eval)
+
+    def score_inf(self, baseline: PathLike, eval_files: list[Path], steps: int = 25, min_n=500, raw: bool = False):
+        """FAD for growing sample counts and the FAD-inf extrapolation (fad.py:304-351).
+
+        The bootstrap indices come from the host's global numpy RNG exactly as in the reference
+        (``np.random.choice(N, n, replace=True)``, fad.py:333) so a seeded run reproduces it; the
+        gather, statistics and Frechet chain of every step run on the GPU.
+        """
+        log.info(f"Calculating FAD-inf for {self.ml.name}...")
+        mu_base, cov_base = self.load_stats(baseline)
+        if all([Path(f).suffix == '.npy' for f in eval_files]):
+            embeds = np.concatenate([np.load(f) for f in eval_files], axis=0)
+        else:
+            embeds = self._load_embeddings(eval_files, concat=True)
+
+        max_n = len(embeds)
+        ns = [int(n) for n in np.linspace(min_n, max_n, steps)]
+
+        from . import _native
+        eng = _native.engine()
+        fp16_rows = embeds.dtype == np.float16
+        emb_dev = torch.from_numpy(np.ascontiguousarray(embeds)).to(eng.torch_device) if fp16_rows else None
+
+        results = []
+        for n in ns:
+            indices = np.random.choice(embeds.shape[0], size=n, replace=True)
+            if fp16_rows:
+                st = DeviceStatistics(embeds.shape[1], eng)
+                st.add_gather(emb_dev, torch.from_numpy(indices).to(eng.torch_device))
+                mu_d, cov_d = st.finalize()
+                mu_eval = mu_d.cpu().numpy().astype(np.float16)      # np.mean dtype quirk, fad.py:48
+                cov_eval = cov_d.cpu().numpy()
+            else:
+                mu_eval, cov_eval = calc_embd_statistics(embeds[indices])
+            fad_score = calc_frechet_distance(mu_base, cov_base, mu_eval, cov_eval)
+            results.append([n, fad_score])
+
+        ys = np.array(results)
+        xs = 1 / np.array(ns)
+        slope, intercept = np.polyfit(xs, ys[:, 1], 1)
+        r2 = 1 - np.sum((ys[:, 1] - (slope * xs + intercept)) ** 2) / np.sum((ys[:, 1] - np.mean(ys[:, 1])) ** 2)
+        return FADInfResults(score=intercept, slope=slope, r2=r2, points=results)
+
+    def score_individual(self, baseline: PathLike, eval_dir: PathLike, csv_name: Union[Path, str]) -> Path:
+        """FAD of every file in eval_dir against the baseline, written to a csv sorted by |score|
+        (fad.py:353-395).  Files whose statistics fail are logged and dropped, as in the reference."""
+        csv = Path(csv_name)
+        if isinstance(csv_name, str):
+            csv = Path('data') / f'fad-individual' / self.ml.name / csv_name
+        if csv.exists():
+            log.info(f"CSV file {csv} already exists, exiting...")
+            return csv
+
+        mu, cov = self.load_stats(baseline)
+
+        def _find_z_helper(f):
+            try:
+                embd = self.read_embedding_file(f)
+                mu_eval, cov_eval = calc_embd_statistics(embd)
+                return calc_frechet_distance(mu, cov, mu_eval, cov_eval)
+            except Exception as e:
+                traceback.print_exc()
+                log.error(f"An error occurred calculating individual FAD using model {self.ml.name} on file {f}")
+                log.error(e)
+
+        _files = list(Path(eval_dir).glob("*.*"))
+        scores = [_find_z_helper(f) for f in _files]      # one GPU, one stream: no thread fan-out
+
+        pairs = [p for p in zip(_files, scores) if p[1] is not None]
+        pairs = sorted(pairs, key=lambda x: np.abs(x[1]))
+        csv.parent.mkdir(parents=True, exist_ok=True)
+        csv.write_text("\n".join([",".join([str(x).replace(',', '_') for x in row]) for row in pairs]))
+        return csv

@@ -1,0 +1,193 @@
+"""Embedding-model plugin surface (mirror of fadtk/model_loader.py:21-86, :89-108, :676-701).
+
+``ModelLoader`` keeps the reference's contract verbatim - constructor arguments and attributes,
+``load_model`` / ``_get_embedding`` / ``get_embedding`` / ``load_wav`` / ``enforce_min_len``,
+picklable before ``load_model`` - so third-party plugins written against fadtk (README plugin
+template, README.md:113-138) keep working.  ``VGGishModel`` is the B200-native implementation:
+its forward is hand-written sm_100a CUDA behind the C ABI (include/fadtk_b200.h), not torchvggish.
+
+One addition: ``embed_pcm_batch(list_of_int16_arrays)`` lets the batch driver push many clips
+through the GPU in one launch sequence; the default implementation falls back to the per-clip
+``get_embedding`` so plain plugins need not implement it.
+"""
+from __future__ import annotations
+
+import logging
+from abc import ABC, abstractmethod
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import synth, weights
+
+log = logging.getLogger(__name__)
+
+
+class ModelLoader(ABC):
+    """Load a model and get embeddings from it (fadtk/model_loader.py:21-86)."""
+
+    def __init__(self, name: str, num_features: int, sr: int, min_len: int = -1):
+        self.model = None
+        self.sr = sr
+        self.num_features = num_features
+        self.name = name
+        self.min_len = min_len
+        self.device = torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
+
+    def get_embedding(self, audio: np.ndarray):
+        embd = self._get_embedding(audio)
+        if isinstance(embd, torch.Tensor):
+            embd = embd.detach().cpu().numpy()
+        # float32 embeddings are stored as float16, like the reference (model_loader.py:47-48)
+        if embd.dtype == np.float32:
+            embd = embd.astype(np.float16)
+        return embd
+
+    @abstractmethod
+    def load_model(self):
+        pass
+
+    @abstractmethod
+    def _get_embedding(self, audio: np.ndarray):
+        """(n_frames, n_features) embedding of one clip."""
+
+    def load_wav(self, wav_file: Path):
+        pcm, sr = synth.read_wav(wav_file)              # PCM16 RIFF written by load_audio
+        if pcm.ndim > 1:
+            pcm = pcm[:, 0]
+        wav_data = pcm / 32768.0                        # [-1.0, +1.0), float64 (model_loader.py:64-65)
+        return self.enforce_min_len(wav_data)
+
+    def enforce_min_len(self, audio: np.ndarray) -> np.ndarray:
+        if self.min_len < 0:
+            return audio
+        need = self.min_len * self.sr
+        if audio.shape[0] < need:
+            log.warning(
+                f"Audio is too short for {self.name}.\n"
+                f"The model requires a minimum length of {self.min_len}s, audio is {audio.shape[0] / self.sr:.2f}s.\n"
+                f"Padding with zeros.")
+            audio = np.pad(audio, (0, int(np.ceil(need - audio.shape[0]))))
+        return audio
+
+    # ---- batched extension (not in the reference) -------------------------------------
+    def embed_pcm_batch(self, clips):
+        """list of int16 mono arrays at ``self.sr`` -> list of fp16 [n_i, d] arrays."""
+        out = []
+        for pcm in clips:
+            wav = self.enforce_min_len(np.asarray(pcm).astype(np.int16) / 32768.0)
+            out.append(self.get_embedding(wav))
+        return out
+
+
+def _as_pcm16(audio: np.ndarray) -> np.ndarray:
+    """The reference feeds ``int16 / 32768.0`` (load_wav); recover the integers exactly."""
+    audio = np.asarray(audio)
+    if audio.dtype == np.int16:
+        return audio
+    scaled = audio * 32768.0
+    pcm = np.rint(scaled)
+    if not np.array_equal(pcm, scaled) or pcm.min(initial=0) < -32768 or pcm.max(initial=0) > 32767:
+        # arbitrary float waveforms: quantise like torchaudio.save(..., PCM_S16) would (fad.py:160)
+        pcm = np.clip(np.rint(np.clip(audio, -1.0, 1.0) * 32768.0), -32768, 32767)
+    return pcm.astype(np.int16)
+
+
+class VGGishModel(ModelLoader):
+    """S. Hershey et al., "CNN Architectures for Large-Scale Audio Classification", ICASSP 2017.
+
+    Same registry name, dimensionality, sample rate and minimum length as the reference
+    (fadtk/model_loader.py:93-97).  PCA post-processing and the final ReLU are disabled as the
+    reference does (:100-103); enabling either is not supported by the native path.
+    """
+
+    def __init__(self, use_pca=False, use_activation=False, checkpoint=None, seed: int = 0):
+        super().__init__("vggish", 128, 16000, min_len=1)
+        if use_pca or use_activation:
+            raise NotImplementedError("the B200 path implements the reference's default (no PCA, no final ReLU)")
+        self.use_pca = use_pca
+        self.use_activation = use_activation
+        self.checkpoint = checkpoint
+        self.seed = seed
+        self._engine = None
+
+    def __getstate__(self):                             # stay picklable after load_model()
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st["model"] = None
+        return st
+
+    def load_model(self):
+        from . import _native
+        self._engine = _native.engine()
+        state = weights.load_vggish_state(self.checkpoint, self.seed)
+        self._engine.vggish_load(weights.pack_vggish(state))
+        self.model = self._engine
+        self.device = self._engine.torch_device
+
+    def _get_embedding(self, audio: np.ndarray):
+        return self._embed_flat([_as_pcm16(audio)])[0]
+
+    def embed_pcm_batch(self, clips):
+        padded = []
+        need = self.min_len * self.sr
+        for c in clips:
+            c = np.asarray(c, dtype=np.int16)
+            if c.shape[0] < need:
+                c = np.pad(c, (0, need - c.shape[0]))
+            padded.append(c)
+        return [t.cpu().numpy() for t in self._embed_flat(padded)]
+
+    def _embed_flat(self, clips):
+        """list of int16 arrays -> list of fp16 cuda tensors [n_i, 128]."""
+        if self._engine is None:
+            raise RuntimeError("load_model() has not been called")
+        eng = self._engine
+        offsets = np.zeros(len(clips) + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum([len(c) for c in clips])
+        ex_start, rows = eng.vggish_plan(offsets)
+        flat = torch.from_numpy(np.concatenate(clips)) if len(clips) > 1 else torch.from_numpy(np.ascontiguousarray(clips[0]))
+        pcm = flat.pin_memory().to(eng.torch_device, non_blocking=True)
+        ex = torch.from_numpy(ex_start).to(eng.torch_device)
+        emb = eng.vggish_forward(pcm, ex)
+        return list(torch.split(emb, [int(r) for r in rows]))
+
+
+class UnbuiltModel(ModelLoader):
+    """Registry entry whose forward pass has no B200-native implementation yet.
+
+    The names stay valid ``choices`` for the CLI (fadtk/__main__.py:13,17); statistics / Frechet
+    scoring from cached ``.npy`` embeddings or ``.npz`` statistics works for every name, only
+    ``load_model`` (i.e. embedding raw audio) is unavailable.
+    """
+
+    def load_model(self):
+        raise NotImplementedError(
+            f"{self.name}: no sm_100a forward pass in fadtk_b200 yet (see DESIGN.md, scope table)")
+
+    def _get_embedding(self, audio):
+        raise NotImplementedError(self.name)
+
+
+def _layered(prefix, dim, layers, default_layer):
+    return [UnbuiltModel(prefix + ("" if v == default_layer else f"-{v}"), dim, 16000) for v in range(1, layers + 1)]
+
+
+def get_all_models() -> list[ModelLoader]:
+    """Same names, order and (num_features, sr) as fadtk/model_loader.py:676-701."""
+    ms = [
+        UnbuiltModel("clap-2023", 1024, 44100),
+        UnbuiltModel("clap-laion-audio", 512, 48000), UnbuiltModel("clap-laion-music", 512, 48000),
+        VGGishModel(),
+        *[UnbuiltModel("MERT-v1-95M" + ("" if v == 12 else f"-{v}"), 768, 24000) for v in range(1, 13)],
+        UnbuiltModel("encodec-emb", 128, 24000), UnbuiltModel("encodec-emb-48k", 128, 48000),
+        *_layered("w2v2-base", 768, 12, 12), *_layered("w2v2-large", 1024, 24, 24),
+        *_layered("hubert-base", 768, 12, 12), *_layered("hubert-large", 1024, 24, 24),
+        *_layered("wavlm-base", 768, 12, 12), *_layered("wavlm-base-plus", 768, 12, 12),
+        *_layered("wavlm-large", 1024, 24, 24),
+        UnbuiltModel("whisper-tiny", 384, 16000), UnbuiltModel("whisper-small", 768, 16000),
+        UnbuiltModel("whisper-base", 512, 16000), UnbuiltModel("whisper-medium", 1024, 16000),
+        UnbuiltModel("whisper-large", 1280, 16000),
+    ]
+    return ms

@@ -1,0 +1,140 @@
+"""Statistics + cache-path helpers (mirror of fadtk/utils.py).
+
+``calculate_embd_statistics_online`` keeps the reference's name and return value but not its
+mechanism: instead of one process per file pickling a d x d fp64 scatter matrix back to a
+sequential Chan merge (utils.py:13-46), all rows go through one shifted E^T E tensor-core
+contraction on the GPU (csrc/stats.cuh) whose packed fp64 result is additive - across batches
+and, with one all-reduce, across GPUs.
+"""
+from __future__ import annotations
+
+import subprocess
+from pathlib import Path
+from typing import Iterable, Union
+
+import numpy as np
+import torch
+
+PathLike = Union[str, Path]
+
+_ROWS_PER_UPLOAD = 1 << 20
+
+
+def _split_hi_lo(x: torch.Tensor) -> torch.Tensor:
+    """fp32/fp64 rows -> fp16 [n, 2d] = [hi | lo] with hi + lo == x to ~2^-22 relative."""
+    hi = x.to(torch.float16)
+    lo = (x - hi.to(x.dtype)).to(torch.float16)
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+class DeviceStatistics:
+    """Running (n, sum, outer-product-sum) of embedding rows on one GPU.
+
+    ``add`` accepts numpy or torch arrays of shape [n, d].  fp16 rows (what the reference caches,
+    model_loader.py:47-48) go straight to the tensor-core kernel; wider dtypes are split into
+    fp16 hi/lo halves and contracted as a [n, 2d] matrix so nothing is rounded away.
+    """
+
+    def __init__(self, d: int, engine=None):
+        from . import _native
+        self.eng = engine or _native.engine()
+        self.d = d
+        self.wide = None
+        self.shift = None
+        self.acc = None
+
+    def _setup(self, first: torch.Tensor):
+        self.wide = first.dtype != torch.float16
+        dd = 2 * self.d if self.wide else self.d
+        head = first[: min(first.shape[0], 4096)].to(self.eng.torch_device)
+        if self.wide:
+            s = torch.zeros(dd, dtype=torch.float16, device=self.eng.torch_device)
+            s[: self.d] = head.double().mean(0).to(torch.float16)
+            self.shift = s
+        else:
+            self.shift = head.float().mean(0).to(torch.float16)
+        self.acc = self.eng.stats_new(dd)
+
+    def add(self, rows):
+        t = torch.from_numpy(np.ascontiguousarray(rows)) if isinstance(rows, np.ndarray) else rows
+        if t.shape[0] == 0:
+            return
+        if self.acc is None:
+            self._setup(t)
+        for s in range(0, t.shape[0], _ROWS_PER_UPLOAD):
+            part = t[s:s + _ROWS_PER_UPLOAD]
+            if not part.is_cuda:
+                part = part.pin_memory().to(self.eng.torch_device, non_blocking=True)
+            part = _split_hi_lo(part) if self.wide else part.contiguous()
+            self.eng.stats_accumulate(part, self.shift, self.acc)
+
+    def add_gather(self, emb_dev: torch.Tensor, idx_dev: torch.Tensor):
+        if self.acc is None:
+            self._setup(emb_dev)
+        assert not self.wide
+        self.eng.stats_accumulate_gather(emb_dev, idx_dev, self.shift, self.acc)
+
+    def allreduce(self):
+        """Sum the packed accumulator over all ranks (NCCL over NVLink); no-op single-process."""
+        from . import dist
+        dist.allreduce_sum_(self.acc)
+
+    def count(self) -> int:
+        return 0 if self.acc is None else int(self.acc[0].item())
+
+    def finalize(self):
+        """-> (mu fp64 [d], cov fp64 [d, d]) cuda tensors; cov is zero when n < 2 (utils.py:42-43)."""
+        if self.acc is None:
+            raise AssertionError("No files provided")
+        if not self.wide:
+            return self.eng.stats_finalize(self.acc, self.shift, self.d)
+        d = self.d
+        mu2, cov2 = self.eng.stats_finalize(self.acc, self.shift, 2 * d)
+        mu = mu2[:d] + mu2[d:]
+        cov = cov2[:d, :d] + cov2[:d, d:] + cov2[d:, :d] + cov2[d:, d:]
+        return mu.contiguous(), cov.contiguous()
+
+
+def statistics_of_arrays(arrays: Iterable[np.ndarray], d: int | None = None, reduce_ranks: bool = False):
+    """mean / covariance of the concatenation of ``arrays`` -> numpy fp64 (mu [d], cov [d, d])."""
+    st = None
+    for a in arrays:
+        if st is None:
+            st = DeviceStatistics(d or a.shape[-1])
+        st.add(a)
+    if st is None:
+        raise AssertionError("No files provided")
+    if reduce_ranks:
+        st.allreduce()
+    mu, cov = st.finalize()
+    return mu.cpu().numpy(), cov.cpu().numpy()
+
+
+def calculate_embd_statistics_online(files: list[PathLike]) -> tuple[np.ndarray, np.ndarray]:
+    """Mean and covariance of the embeddings stored in ``files`` (fadtk/utils.py:19-46).
+
+    :param files: npy files holding ndarrays of shape (n_frames, n_features)
+
+    Deliberate difference from the reference: a single-frame file contributes its one row
+    instead of turning the whole covariance into NaN (utils.py:16 / SURVEY.md section 7), and
+    per-file means are not rounded to fp16 before merging (2-4e-5 relative on FAD).
+    """
+    assert len(files) > 0, "No files provided"
+    return statistics_of_arrays(np.load(f) for f in files)
+
+
+def find_sox_formats(sox_path: str) -> list[str]:
+    """File formats supported by SoX (fadtk/utils.py:49-57); empty when SoX is absent."""
+    try:
+        out = subprocess.check_output((sox_path, "-h")).decode()
+        head = "AUDIO FILE FORMATS: "
+        i = out.index(head) + len(head)
+        return out[i:out.index("\n", i)].split()
+    except Exception:
+        return []
+
+
+def get_cache_embedding_path(model: str, audio_dir: PathLike) -> Path:
+    """<dir>/embeddings/<model>/<stem>.npy for an audio file (fadtk/utils.py:60-68)."""
+    audio_dir = Path(audio_dir)
+    return audio_dir.parent / "embeddings" / model / audio_dir.with_suffix(".npy").name

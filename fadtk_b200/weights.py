@@ -1,0 +1,91 @@
+"""VGGish parameters: seeded synthetic set, checkpoint loading, device packing.
+
+There is no network in the build or GPU containers, so unless a real
+``vggish-10086976.pth`` (torchvggish release file, model_loader.py:99) is supplied
+the engine runs on *seeded synthetic* parameters with the real architecture.  The
+state-dict uses torchvggish's key names, so the same dict feeds the CUDA path
+(packed by ``pack_vggish``) and the CPU oracle byte-for-byte.
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+
+import numpy as np
+import torch
+
+# (state-dict key, Cin, Cout, maxpool after?)
+VGGISH_CONVS = (
+    ("features.0", 1, 64, True),
+    ("features.3", 64, 128, True),
+    ("features.6", 128, 256, False),
+    ("features.8", 256, 256, True),
+    ("features.11", 256, 512, False),
+    ("features.13", 512, 512, True),
+)
+# (state-dict key, in, out, relu after?) - the ReLU after the last Linear is removed
+# by the reference (model_loader.py:102-103)
+VGGISH_FCS = (
+    ("embeddings.0", 512 * 6 * 4, 4096, True),
+    ("embeddings.2", 4096, 4096, True),
+    ("embeddings.4", 4096, 128, False),
+)
+
+
+def synthetic_vggish_state(seed: int = 0) -> dict:
+    """He-normal convolutions / linears with small random biases, float32, on CPU."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, cin, cout, _ in VGGISH_CONVS:
+        std = math.sqrt(2.0 / (9 * cin))
+        sd[key + ".weight"] = torch.randn((cout, cin, 3, 3), generator=g) * std
+        sd[key + ".bias"] = torch.randn((cout,), generator=g) * 0.05
+    for key, fin, fout, relu in VGGISH_FCS:
+        std = math.sqrt((2.0 if relu else 1.0) / fin)
+        sd[key + ".weight"] = torch.randn((fout, fin), generator=g) * std
+        sd[key + ".bias"] = torch.randn((fout,), generator=g) * 0.05
+    return sd
+
+
+def load_vggish_state(path=None, seed: int = 0) -> dict:
+    """Real checkpoint if ``path`` (or $FADTK_VGGISH_CKPT) exists, else synthetic."""
+    import os
+    path = path or os.environ.get("FADTK_VGGISH_CKPT")
+    if path and Path(path).exists():
+        sd = torch.load(path, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+        return {k: v.float().contiguous() for k, v in sd.items()
+                if k.startswith(("features.", "embeddings."))}
+    return synthetic_vggish_state(seed)
+
+
+def pack_vggish(sd: dict) -> dict:
+    """Re-lay the state-dict for the sm_100a kernels (all on CPU, contiguous).
+
+    conv1   : float32 [64, 9]                     (CUDA-core stencil, fp32 input)
+    conv2-6 : float16 [Cout, 9*Cin], k = (kh*3+kw)*Cin + cin   (UMMA B operand, K-major)
+    fc1-3   : float16 [out, in]                   (already K-major; fc1's input order is
+                                                   the NHWC flatten the upstream uses)
+    biases  : float32
+    """
+    out = {}
+    key, _, cout, _ = VGGISH_CONVS[0]
+    out["conv1.w"] = sd[key + ".weight"].reshape(cout, 9).float().contiguous()
+    out["conv1.b"] = sd[key + ".bias"].float().contiguous()
+    for i, (key, cin, cout, _) in enumerate(VGGISH_CONVS[1:], start=2):
+        w = sd[key + ".weight"].permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+        out[f"conv{i}.w"] = w.to(torch.float16).contiguous()
+        out[f"conv{i}.b"] = sd[key + ".bias"].float().contiguous()
+    for i, (key, fin, fout, _) in enumerate(VGGISH_FCS, start=1):
+        out[f"fc{i}.w"] = sd[key + ".weight"].to(torch.float16).contiguous()
+        out[f"fc{i}.b"] = sd[key + ".bias"].float().contiguous()
+    return out
+
+
+def state_fingerprint(sd: dict) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].numpy()).tobytes()[:4096])
+    return h.hexdigest()[:16]

@@ -1,0 +1,109 @@
+/* fadtk_b200 - C ABI of the B200-native Frechet-Audio-Distance hot path.
+ *
+ * The reference (microsoft/fadtk) has no native layer: its hot path is Python calling
+ * third-party PyTorch models and numpy/scipy.  This header is the boundary a maintainer
+ * binds instead (ctypes stub in INTEGRATION.md); every entry point names the reference code
+ * it replaces.  Conventions:
+ *   - extern "C", plain C types, no C++ exceptions cross the boundary;
+ *   - every function returns 0 on success, non-zero on failure with a message available from
+ *     fad_last_error() (thread-local);
+ *   - all data buffers are CALLER-OWNED DEVICE pointers (e.g. torch.Tensor.data_ptr()) unless
+ *     the parameter name ends in _host; `stream` is a cudaStream_t passed as void*;
+ *   - a fad_handle belongs to one device and must not be used from two threads at once;
+ *     distinct handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef FADTK_B200_H
+#define FADTK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fad_handle fad_handle;
+
+/* ---- library ------------------------------------------------------------------------ */
+int         fad_version(void);
+const char* fad_last_error(void);
+
+/* One handle per (process, device).  max_examples bounds the number of 0.96-s VGGish examples
+ * processed per internal batch (workspace ~0.7 MB per example). */
+int  fad_create(int device, int max_examples, fad_handle** out);
+int  fad_destroy(fad_handle* h);
+
+/* ---- VGGish embedder: replaces VGGishModel.load_model/_get_embedding ------------------
+ * (fadtk/model_loader.py:89-108 -> torchvggish front-end + VGG stack) and the float32 ->
+ * float16 conversion of ModelLoader.get_embedding (fadtk/model_loader.py:40-50). */
+typedef struct {
+    const float*    conv1_w_host;   /* [64, 9]  fp32                                      */
+    const float*    conv1_b_host;   /* [64]                                               */
+    const uint16_t* conv_w_host[5]; /* conv2..conv6: fp16 [Cout, 9*Cin], k=(kh*3+kw)*Cin+c */
+    const float*    conv_b_host[5];
+    const uint16_t* fc_w_host[3];   /* fc1..fc3: fp16 [out, in]                           */
+    const float*    fc_b_host[3];
+} fad_vggish_weights;
+
+int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w);
+
+/* Examples (rows of the embedding) produced by a clip of n_samples at 16 kHz:
+ * 1 + floor((T - 96) / 96) with T = 1 + floor((n_samples - 400) / 160); 0 if too short. */
+long long fad_vggish_num_examples(long long n_samples);
+
+/* Host-side planning: clip_offsets_host[n_clips + 1] (sample offsets into one flat PCM
+ * buffer) -> start sample of every example.  Returns the number of examples; writes at most
+ * `capacity` entries to ex_start_host (pass NULL/0 to only count).  rows_per_clip_host (may be
+ * NULL) receives the per-clip example counts. */
+long long fad_vggish_plan(const long long* clip_offsets_host, long long n_clips,
+                          long long* ex_start_host, long long capacity,
+                          long long* rows_per_clip_host);
+
+/* pcm: int16 mono 16 kHz (device).  ex_start: int64 [n_examples] (device).
+ * emb_out: fp16 [n_examples, 128] (device) - exactly what the reference caches as .npy. */
+int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_start,
+                       long long n_examples, void* emb_out_f16, void* stream);
+
+/* Stage-level entry points (used by the parity tests and profiling). */
+int fad_vggish_logmel(fad_handle* h, const int16_t* pcm, const long long* ex_start,
+                      long long n_examples, float* logmel_out /* [n,96,64] */, int use_double,
+                      void* stream);
+/* One tensor-core layer: 3x3 conv pad 1 (taps = 9) or fully connected (taps = 1, H = W = 1) on
+ * NHWC fp16 input x[NB,H,W,Cin] with fp16 weights w[Cout, taps*Cin]; fused bias, optional ReLU,
+ * optional 2x2 max-pool; fp16 NHWC output (and optional fp32 copy of the un-pooled output). */
+int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int Cin,
+                   const void* w_f16, const float* bias, int Cout, int taps, int relu, int pool,
+                   void* out_f16, float* out_f32_or_null, void* stream);
+
+/* ---- statistics: replaces calc_embd_statistics (fadtk/fad.py:42-48) and
+ * _process_file / calculate_embd_statistics_online (fadtk/utils.py:13-46) ----------------
+ * Packed fp64 accumulator of length fad_stats_acc_len(d):
+ *   acc[0] = n, acc[1..d] = sum(x - shift) (exact), acc[1+d..1+d+d*d) = sum y y^T (d x d),
+ *   acc[1+d+d*d..] = sum y,   y = fp16(x - shift)
+ * It is additive: accumulate batches into it, all-reduce (sum) it across GPUs, then finalize.
+ * `shift` (fp16 [d], device) must be identical for every contribution to one accumulator. */
+size_t fad_stats_acc_len(int d);
+int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, int d,
+                         const void* shift_f16, double* acc, int use_simt, void* stream);
+/* rows emb[idx[i]] for i < n_idx (FAD-inf bootstrap, fadtk/fad.py:333-336) */
+int fad_stats_accumulate_gather(fad_handle* h, const void* emb_f16, long long n_src_rows,
+                                const long long* idx, long long n_idx, int d,
+                                const void* shift_f16, double* acc, void* stream);
+int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, int d,
+                       double* mu_out, double* cov_out, void* stream);
+
+/* ---- Frechet distance: replaces calc_frechet_distance (fadtk/fad.py:51-120) ------------
+ * mu/cov fp64 device arrays.  out (device, 8 doubles): [0] FAD, [1] tr sqrt(C1 C2),
+ * [2] relative residual of the final square root, [3] iterations, [4] |mu1-mu2|^2,
+ * [5] tr C1, [6] tr C2, [7] reserved.  iters <= 0 selects the default. */
+int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const double* mu2,
+                const double* cov2, int d, int iters, double* out, void* stream);
+
+/* Number of CUDA kernels this library has launched through `h` (bench.py's gpu_launches). */
+long long fad_launch_count(fad_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FADTK_B200_H */
