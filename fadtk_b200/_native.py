@@ -49,7 +49,13 @@ SIGNATURES = {
     "fad_stats_finalize": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_launch_count": (c_ll, [c_vp]),
+    "fad_profile_enable": (C.c_int, [c_vp, C.c_int]),
+    "fad_profile_collect": (C.c_int, [c_vp, c_vp, c_vp, C.c_int]),
 }
+
+PROF_CATEGORIES = 16
+PROF_NAMES = {0: "logmel", 1: "conv1", 2: "conv2", 3: "conv3_1", 4: "conv3_2", 5: "conv4_1", 6: "conv4_2",
+              7: "fc1", 8: "fc2", 9: "fc3", 10: "stats_umma", 11: "stats_reduce", 12: "frechet"}
 
 
 def library_path() -> Path:
@@ -116,6 +122,16 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(lib().fad_launch_count(self._h))
+
+    def profile(self, on: bool):
+        _check(lib().fad_profile_enable(self._h, int(on)))
+
+    def profile_collect(self, reset: bool = True) -> dict:
+        """-> {category: (milliseconds, launches)} measured with CUDA events on the launch stream."""
+        ms = (C.c_double * PROF_CATEGORIES)()
+        cnt = (c_ll * PROF_CATEGORIES)()
+        _check(lib().fad_profile_collect(self._h, ms, cnt, int(reset)))
+        return {PROF_NAMES[i]: (ms[i], int(cnt[i])) for i in PROF_NAMES if cnt[i]}
 
     # ------------------------------------------------------------------ VGGish
     def vggish_load(self, packed: dict):

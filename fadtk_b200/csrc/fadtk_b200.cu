@@ -131,6 +131,15 @@ struct fad_handle {
     double* fr_buf = nullptr;
     size_t fr_cap = 0;
     double* fr_scal = nullptr;   // 32 doubles
+
+    // optional per-category timing with CUDA events recorded on the launching stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int cat; size_t e0, e1; };
+    std::vector<Span> spans;
+    double prof_ms[FAD_PROF_CATEGORIES] = {};
+    long long prof_count[FAD_PROF_CATEGORIES] = {};
 };
 
 namespace {
@@ -240,11 +249,48 @@ int ensure(void** ptr, size_t* cap, size_t bytes) {
     return 0;
 }
 
+size_t prof_begin(fad_handle* h, cudaStream_t st) {
+    if (!h->prof_on) return 0;
+    if (h->ev_used == h->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+    cudaEventRecord(h->ev_pool[h->ev_used], st);
+    return h->ev_used++;
+}
+void prof_end(fad_handle* h, int cat, size_t e0, cudaStream_t st) {
+    if (!h->prof_on) return;
+    const size_t e1 = prof_begin(h, st);
+    h->spans.push_back({cat, e0, e1});
+}
+
 }  // namespace
 
 extern "C" {
 
 int fad_version(void) { return 1; }
+
+int fad_profile_enable(fad_handle* h, int on) {
+    if (!h) return fail("null handle");
+    h->prof_on = on != 0;
+    return 0;
+}
+
+int fad_profile_collect(fad_handle* h, double* ms_out, long long* count_out, int reset) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (const auto& sp : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[sp.e0], h->ev_pool[sp.e1]) == cudaSuccess) {
+            h->prof_ms[sp.cat] += ms; h->prof_count[sp.cat]++;
+        }
+    }
+    h->spans.clear(); h->ev_used = 0;
+    for (int i = 0; i < FAD_PROF_CATEGORIES; ++i) {
+        if (ms_out) ms_out[i] = h->prof_ms[i];
+        if (count_out) count_out[i] = h->prof_count[i];
+        if (reset) { h->prof_ms[i] = 0.0; h->prof_count[i] = 0; }
+    }
+    return 0;
+}
 const char* fad_last_error(void) { return g_err.c_str(); }
 
 int fad_create(int device, int max_examples, fad_handle** out) {
@@ -389,14 +435,20 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
     static const int fe_double = []() { const char* e = getenv("FADTK_FRONTEND_FP32"); return (e && e[0] == '1') ? 0 : 1; }();
     for (long long base = 0; base < n_examples; base += h->max_examples) {
         const int nb = (int)((n_examples - base) < h->max_examples ? (n_examples - base) : h->max_examples);
+        size_t ev = prof_begin(h, st);
         if (launch_logmel(h, pcm, ex_start + base, nb, h->logmel, fe_double, st)) return 1;
+        prof_end(h, FAD_PROF_LOGMEL, ev, st);
+        ev = prof_begin(h, st);
         fad::conv1_kernel<<<dim3(6, nb), 256, 0, st>>>(h->logmel, h->conv1_w, h->conv1_b, h->act[0]);
         CK(cudaGetLastError());
         h->launches++;
+        prof_end(h, FAD_PROF_CONV1, ev, st);
         for (int i = 0; i < 8; ++i) {
             const float* bias = i < 5 ? h->conv_b[i] : h->fc_b[i - 5];
             void* out = (i == 7) ? (void*)((__half*)emb_out_f16 + (size_t)base * 128) : (void*)h->act[i + 1];
+            ev = prof_begin(h, st);
             if (run_layer(h, h->geom[i], h->map_x[i], h->map_w[i], nb, bias, out, nullptr, st)) return 1;
+            prof_end(h, FAD_PROF_LAYER0 + i, ev, st);
         }
     }
     return 0;
@@ -438,14 +490,14 @@ int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, i
     fad::StatsJobParams p;
     p.n_rows = n_rows; p.d = d; p.n_tiles = d / 128;
     p.n_pairs = p.n_tiles * (p.n_tiles + 1) / 2;
-    const long long stages = (n_rows + 63) / 64;
+    const long long stages = (n_rows + fad::kStStageRows - 1) / fad::kStStageRows;
     long long want = (2LL * h->num_sms) / p.n_pairs;          // ~2 waves of jobs
     if (p.n_pairs == 1) want = h->num_sms;
     if (want < 1) want = 1;
-    long long per = (stages + want - 1) / want;                // 64-row stages per split
-    if (per < 4) per = 4;                                      // at least one 256-row chunk
+    long long per = (stages + want - 1) / want;                // 32-row stages per split
+    if (per < fad::kStStagesPerChunk) per = fad::kStStagesPerChunk;   // at least one 256-row chunk
     p.n_splits = (int)((stages + per - 1) / per);
-    p.rows_per_split = per * 64;
+    p.rows_per_split = per * fad::kStStageRows;
     p.shift = shift;
     const size_t jobs = (size_t)p.n_pairs * p.n_splits;
     if (ensure((void**)&h->ws_tiles, &h->ws_tiles_cap, jobs * 128 * 128 * 8)) return 1;
@@ -454,12 +506,16 @@ int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, i
     CUtensorMap me;
     const uint64_t ed[2] = {(uint64_t)d, (uint64_t)n_rows};
     const uint64_t es[1] = {(uint64_t)d * 2};
-    const uint32_t eb[2] = {64, 64};
+    const uint32_t eb[2] = {64, (uint32_t)fad::kStStageRows};
     if (encode_f16_map(&me, E, 2, ed, es, eb)) return 1;
+    size_t ev = prof_begin(h, st);
     fad::stats_umma_kernel<<<(unsigned)jobs, fad::kStThreads, fad::kStSmemBytes, st>>>(me, p);
     CK(cudaGetLastError());
+    prof_end(h, FAD_PROF_STATS, ev, st);
+    ev = prof_begin(h, st);
     fad::stats_reduce_kernel<<<p.n_pairs, 256, 0, st>>>(p, acc);
     CK(cudaGetLastError());
+    prof_end(h, FAD_PROF_STATS_REDUCE, ev, st);
     h->launches += 2;
     return 0;
 }
@@ -555,6 +611,7 @@ int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const doub
     unsigned eb = (unsigned)((total + 255) / 256);
     if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
 
+    const size_t ev_fr = prof_begin(h, st);
     // S = C1^(1/2)
     if (newton_schulz(h, cov1, d, iters, Y, Z, W, T, scalA, trS, trZs, st)) return 1;
     fad::ns_unscale_kernel<<<eb, 256, 0, st>>>(Y, d, scalA, S);
@@ -573,6 +630,7 @@ int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const doub
     fad::frechet_assemble_kernel<<<1, 256, 0, st>>>(mu1, mu2, d, scalA, scalB, scalM, trY, trZ, resid, iters, out);
     CK(cudaGetLastError());
     h->launches += 2;
+    prof_end(h, FAD_PROF_FRECHET, ev_fr, st);
     return 0;
 }
 

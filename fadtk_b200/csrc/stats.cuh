@@ -1,36 +1,44 @@
-// Sufficient statistics of an embedding matrix E[N, d] (fp16):   n,  sum(y),  sum(y y^T)
-// with y = fp16(x - shift).  Replaces np.mean / np.cov in fadtk/fad.py:42-48 and the per-file
-// scatter + Chan merge in fadtk/utils.py:13-46 with one shifted E^T E contraction.
+// Sufficient statistics of an embedding matrix E[N, d] (fp16):   n,  sum(x - s),  sum(y y^T)
+// with s a shared fp16 shift vector and y = x - s carried as an fp16 hi/lo pair (22 bits).
+// Replaces np.mean / np.cov in fadtk/fad.py:42-48 and the per-file scatter + Chan merge in
+// fadtk/utils.py:13-46 with one shifted E^T E contraction on the tensor cores.
 //
-// stats_umma_kernel   tcgen05 path.  E is row-major, so both operands of E^T E are "MN-major":
-//   a TMA box [64 rows x 64 cols] with 128-B swizzle IS the canonical MN-major SWIZZLE_128B
-//   UMMA layout (K = row index).  One CTA = one job = (128x128 output tile (ti<=tj), row range).
-//     warp 0      TMA producer: per 64-row stage, two 64-column boxes per panel
-//     warps 4-7   transform: subtract the shift IN PLACE in smem (fp16, exact when x ~ shift),
-//                 zero rows past the end, accumulate column sums in fp64 registers
-//     warp 1      MMA issuer: 4 x tcgen05.mma (K=16) per stage, fp32 accumulate in TMEM;
-//                 products of fp16 values are exact in fp32
-//     warps 8-11  drain: every 256 rows the TMEM tile is added into an fp64 tile in shared
-//                 memory, which bounds the fp32 accumulation length (tensor-core adds truncate)
+// Numerics.  x and s are fp16, so x - s is exact in fp32.  Rounding it to ONE fp16 costs
+// 2^-12 |y| per element, i.e. ~2^-11/sqrt(n) relative on a covariance entry (1.5e-4 at n = 1000):
+// not good enough.  Instead yh = fp16(x - s), yl = fp16((x - s) - yh) and
+//     sum y y^T  ~=  sum yh yh^T + yh yl^T + yl yh^T          (yl yl^T ~ 2^-22 is dropped)
+// Every fp16 x fp16 product is exact in the fp32 accumulator; the accumulation itself is cut
+// every 256 rows and drained into an fp64 tile, because tensor-core fp32 adds truncate.
+//
+// stats_umma_kernel   One CTA = one job = (128x128 output tile (ti <= tj), row range).
+//   E is row-major, so both operands of E^T E are "MN-major": a TMA box [32 rows x 64 cols] with
+//   128-B swizzle IS the canonical MN-major SWIZZLE_128B UMMA layout (K = row index).
+//     warp 0       TMA producer: per 32-row stage, two 64-column boxes per panel
+//     warps 4-11   transform: in smem, x -> (yh in place, yl into a second panel), zero rows past
+//                  the end, exact column sums of x - s and of yh + yl in fp64 registers
+//     warp 1       MMA issuer: per stage 2 k-steps x {hh, hl, lh} tcgen05.mma, fp32 in TMEM
+//     warps 12-15  drain: every 256 rows the TMEM tile is added into an fp64 tile in shared memory
 //   Each job stores its fp64 tile to a workspace; stats_reduce_kernel sums jobs in a fixed
 //   order (deterministic) into the caller's packed accumulator.
 // stats_simt_kernel    plain fp64 CUDA-core version of the same contraction (verification).
 //
 // Packed accumulator (fp64, caller-owned, all-reduced across GPUs as-is):
-//   acc[0] = n,  acc[1 .. d] = sum(x - shift) (exact, fp64),  acc[1+d .. 1+d+d*d) = sum(y y^T)
-//   (d x d, full, row-major),  acc[1+d+d*d ..] = sum(y)  (the fp16-rounded rows, for centring)
+//   acc[0] = n,  acc[1 .. d] = sum(x - s) (exact),  acc[1+d .. 1+d+d*d) = sum(y y^T)
+//   (d x d, full, row-major),  acc[1+d+d*d ..] = sum(yh + yl)  (centring term of the covariance)
 #pragma once
 #include "sm100.cuh"
 
 namespace fad {
 
 constexpr int kStTile = 128;
-constexpr int kStStageRows = 64;
-constexpr int kStChunkRows = 256;                  // rows per fp32 TMEM accumulation
+constexpr int kStStageRows = 32;
+constexpr int kStStagesPerChunk = 8;               // 256 rows per fp32 TMEM accumulation
 constexpr int kStStages = 3;
-constexpr uint32_t kStPanelBytes = kStStageRows * kStTile * 2;   // 16 KiB: two 64x64 boxes
-constexpr uint32_t kStStageBytes = 2 * kStPanelBytes;            // A panel + B panel
-constexpr int kStThreads = 384;
+constexpr uint32_t kStBlockBytes = kStStageRows * 128;            // one 64-col box: 4 KiB
+constexpr uint32_t kStPanelBytes = 2 * kStBlockBytes;             // 128 cols x 32 rows: 8 KiB
+constexpr uint32_t kStStageBytes = 4 * kStPanelBytes;             // Ah | Bh | Al | Bl = 32 KiB
+constexpr int kStThreads = 512;
+constexpr int kStTransformThreads = 256;
 constexpr uint32_t kStSmemBytes = kStStages * kStStageBytes + kStTile * kStTile * 8 + 1024 + 256;
 
 struct StatsJobParams {
@@ -39,10 +47,10 @@ struct StatsJobParams {
     int n_tiles;               // d / 128
     int n_pairs;               // n_tiles (n_tiles + 1) / 2
     int n_splits;              // row splits per tile pair
-    long long rows_per_split;  // multiple of 64
+    long long rows_per_split;  // multiple of 32
     const __half* shift;       // [d]
     double* ws_tiles;          // [n_pairs * n_splits][128 (col)][128 (row)]
-    double* ws_sums;           // [n_tiles * n_splits][2][128]  (exact x-shift sums | rounded y sums)
+    double* ws_sums;           // [n_tiles * n_splits][2][128]  (exact x-s sums | yh+yl sums)
 };
 
 __device__ __forceinline__ void pair_to_tiles(int pair, int n_tiles, int& ti, int& tj) {
@@ -50,6 +58,15 @@ __device__ __forceinline__ void pair_to_tiles(int pair, int n_tiles, int& ti, in
     int rem = pair;
     while (rem >= n_tiles - ti) { rem -= n_tiles - ti; ++ti; }
     tj = ti + rem;
+}
+
+// y = x - s (exact in fp32) -> hi/lo fp16 pair
+__device__ __forceinline__ void split_hi_lo(__half2 x, __half2 s, __half2& hi, __half2& lo, float2& y) {
+    const float2 fx = __half22float2(x), fs = __half22float2(s);
+    y = make_float2(fx.x - fs.x, fx.y - fs.y);
+    hi = __floats2half2_rn(y.x, y.y);
+    const float2 fh = __half22float2(hi);
+    lo = __floats2half2_rn(y.x - fh.x, y.y - fh.y);
 }
 
 __global__ void __launch_bounds__(kStThreads, 1)
@@ -80,11 +97,13 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParam
     if (row_end > p.n_rows) row_end = p.n_rows;
     const long long span = row_end > row_begin ? row_end - row_begin : 0;
     const int n_stages_total = (int)((span + kStStageRows - 1) / kStStageRows);
-    const int n_chunks = (n_stages_total + 3) / 4;
+    const int n_chunks = (n_stages_total + kStStagesPerChunk - 1) / kStStagesPerChunk;
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_e);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStStages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kStStages; ++s) {
+            mbar_init(&full[s], 1); mbar_init(&ready[s], kStTransformThreads / 32); mbar_init(&empty[s], 1);
+        }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         mbar_fence_init();
     }
@@ -101,13 +120,13 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParam
             for (int it = 0; it < n_stages_total; ++it) {
                 const int r0 = (int)(row_begin + (long long)it * kStStageRows);
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], diag ? kStPanelBytes : kStStageBytes);
+                mbar_expect_tx(&full[s], diag ? kStPanelBytes : 2 * kStPanelBytes);
                 uint8_t* st = smem + s * kStStageBytes;
                 tma_load_2d(st, &map_e, &full[s], ti * kStTile, r0);
-                tma_load_2d(st + 8192, &map_e, &full[s], ti * kStTile + 64, r0);
+                tma_load_2d(st + kStBlockBytes, &map_e, &full[s], ti * kStTile + 64, r0);
                 if (!diag) {
                     tma_load_2d(st + kStPanelBytes, &map_e, &full[s], tj * kStTile, r0);
-                    tma_load_2d(st + kStPanelBytes + 8192, &map_e, &full[s], tj * kStTile + 64, r0);
+                    tma_load_2d(st + kStPanelBytes + kStBlockBytes, &map_e, &full[s], tj * kStTile + 64, r0);
                 }
                 if (++s == kStStages) { s = 0; ph ^= 1; }
             }
@@ -121,19 +140,24 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParam
                 mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + acc * kStTile;
-                const int n_st = min(4, n_stages_total - it);
+                const int n_st = min(kStStagesPerChunk, n_stages_total - it);
                 for (int q = 0; q < n_st; ++q, ++it) {
                     mbar_wait(&ready[s], ph);
                     tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(smem + s * kStStageBytes);
-                    const uint32_t b_addr = diag ? a_addr : a_addr + kStPanelBytes;
-                    // MN-major SW128: 64-col blocks 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO)
-                    const uint64_t a_desc = mnmajor_sw128_desc(a_addr, 8192, 1024);
-                    const uint64_t b_desc = mnmajor_sw128_desc(b_addr, 8192, 1024);
+                    const uint32_t base = smem_u32(smem + s * kStStageBytes);
+                    const uint32_t ah = base, bh = diag ? base : base + kStPanelBytes;
+                    const uint32_t al = base + 2 * kStPanelBytes, bl = diag ? al : al + kStPanelBytes;
+                    // MN-major SW128: 64-col blocks kStBlockBytes apart (LBO), 8-row K groups 1024 B apart (SBO)
+                    const uint64_t d_ah = mnmajor_sw128_desc(ah, kStBlockBytes, 1024);
+                    const uint64_t d_bh = mnmajor_sw128_desc(bh, kStBlockBytes, 1024);
+                    const uint64_t d_al = mnmajor_sw128_desc(al, kStBlockBytes, 1024);
+                    const uint64_t d_bl = mnmajor_sw128_desc(bl, kStBlockBytes, 1024);
 #pragma unroll
                     for (int k = 0; k < kStStageRows / 16; ++k) {
-                        // 16 K-rows = 2048 B -> +128 in the 16-B address field
-                        umma_f16(d_tmem, a_desc + 128 * k, b_desc + 128 * k, kIdesc, (q | k) != 0);
+                        const uint32_t off = 128 * k;          // 16 K-rows = 2048 B = 128 x 16 B
+                        umma_f16(d_tmem, d_ah + off, d_bh + off, kIdesc, (q | k) != 0);
+                        umma_f16(d_tmem, d_ah + off, d_bl + off, kIdesc, 1);
+                        umma_f16(d_tmem, d_al + off, d_bh + off, kIdesc, 1);
                     }
                     umma_commit(&empty[s]);
                     if (++s == kStStages) { s = 0; ph ^= 1; }
@@ -142,13 +166,14 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParam
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ---------------------------------------------------------- shift transform
-        const int t = threadIdx.x - 128;             // 0..127
+    } else if (warp >= 4 && warp < 12) {
+        // ------------------------------------------------------- shift + hi/lo split
+        const int t = threadIdx.x - 128;              // 0..255
         const int cg = t & 15;                        // 16-B column group inside the 128-col panel
-        const int rl = t >> 4;                        // row lane 0..7
+        const int rl = (t >> 4) & 7;                  // row lane inside an 8-row swizzle group
+        const int hf = t >> 7;                        // which half of the 32 rows
         const int cb = cg >> 3, lc = cg & 7;
-        const uint32_t chunk_off = cb * 8192 + ((lc ^ rl) << 4);   // swizzled position of (row%8==rl, lc)
+        const uint32_t chunk_off = cb * kStBlockBytes + ((lc ^ rl) << 4);   // swizzled (row%8 == rl, lc)
         __half2 shA[4], shB[4];
         {
             const uint4 a = *reinterpret_cast<const uint4*>(p.shift + ti * kStTile + cg * 8);
@@ -158,9 +183,9 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParam
             shB[0] = *reinterpret_cast<const __half2*>(&b.x); shB[1] = *reinterpret_cast<const __half2*>(&b.y);
             shB[2] = *reinterpret_cast<const __half2*>(&b.z); shB[3] = *reinterpret_cast<const __half2*>(&b.w);
         }
-        double colsum[8], colsum_x[8];
+        double sum_x[8], sum_y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { colsum[j] = 0.0; colsum_x[j] = 0.0; }
+        for (int j = 0; j < 8; ++j) { sum_x[j] = 0.0; sum_y[j] = 0.0; }
         int s = 0; uint32_t ph = 0;
         for (int it = 0; it < n_stages_total; ++it) {
             const long long r0 = row_begin + (long long)it * kStStageRows;
@@ -170,33 +195,31 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParam
             for (int panel = 0; panel < 2; ++panel) {
                 if (panel == 1 && diag) break;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rl + 8 * i;
-                    uint4* ptr = reinterpret_cast<uint4*>(st + panel * kStPanelBytes + chunk_off + r * 128);
-                    uint4 v = *ptr;
-                    __half2* h = reinterpret_cast<__half2*>(&v);
+                for (int i = 0; i < 2; ++i) {
+                    const int r = rl + 8 * (hf * 2 + i);
+                    uint4* ph_ptr = reinterpret_cast<uint4*>(st + panel * kStPanelBytes + chunk_off + r * 128);
+                    uint4* pl_ptr = reinterpret_cast<uint4*>(st + (2 + panel) * kStPanelBytes + chunk_off + r * 128);
+                    uint4 v = *ph_ptr, w = make_uint4(0, 0, 0, 0);
                     if (r0 + r < row_end) {
-                        if (panel == 0 && diag) {
-                            // x - shift is exact in fp32 (two fp16 values): exact column sums for the mean
+                        __half2* hx = reinterpret_cast<__half2*>(&v);
+                        __half2* hl = reinterpret_cast<__half2*>(&w);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 fx = __half22float2(h[j]), fs = __half22float2(shA[j]);
-                                colsum_x[2 * j] += (double)(fx.x - fs.x); colsum_x[2 * j + 1] += (double)(fx.y - fs.y);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) h[j] = __hsub2(h[j], panel ? shB[j] : shA[j]);
-                        if (panel == 0 && diag) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = __half22float2(h[j]);
-                                colsum[2 * j] += (double)f.x; colsum[2 * j + 1] += (double)f.y;
+                        for (int j = 0; j < 4; ++j) {
+                            __half2 hi, lo; float2 y;
+                            split_hi_lo(hx[j], panel ? shB[j] : shA[j], hi, lo, y);
+                            hx[j] = hi; hl[j] = lo;
+                            if (panel == 0 && diag) {
+                                const float2 fh = __half22float2(hi), fl = __half22float2(lo);
+                                sum_x[2 * j] += (double)y.x;            sum_x[2 * j + 1] += (double)y.y;
+                                sum_y[2 * j] += (double)fh.x + (double)fl.x;
+                                sum_y[2 * j + 1] += (double)fh.y + (double)fl.y;
                             }
                         }
                     } else {
                         v = make_uint4(0, 0, 0, 0);
                     }
-                    *ptr = v;
+                    *ph_ptr = v;
+                    *pl_ptr = w;
                 }
             }
             fence_proxy_async_smem();                 // generic-proxy stores -> visible to UMMA
@@ -204,29 +227,30 @@ stats_umma_kernel(const __grid_constant__ CUtensorMap map_e, const StatsJobParam
             if (lane == 0) mbar_arrive(&ready[s]);
             if (++s == kStStages) { s = 0; ph ^= 1; }
         }
-        // column sums: reduce the 8 row lanes through the (now idle) stage-0 buffer
+        // column sums: reduce the 16 row lanes through stage 0 once every MMA has retired
         if (diag) {
             if (n_chunks > 0) {
-                // every MMA of this job has retired once the last accumulator is committed
                 const int last = n_chunks - 1;
                 mbar_wait(&tmem_full[last & 1], (uint32_t)((last >> 1) & 1));
             }
-            __syncwarp();
-            asm volatile("bar.sync 1, 128;");
-            double* red = reinterpret_cast<double*>(smem);       // [2][8 row lanes][128 cols]
+            asm volatile("bar.sync 1, 256;");
+            double* red = reinterpret_cast<double*>(smem);       // [2][16 row lanes][128 cols] = 32 KiB
+            const int lane16 = hf * 8 + rl;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                red[rl * 128 + cg * 8 + j] = colsum_x[j];
-                red[1024 + rl * 128 + cg * 8 + j] = colsum[j];
+                red[lane16 * 128 + cg * 8 + j] = sum_x[j];
+                red[2048 + lane16 * 128 + cg * 8 + j] = sum_y[j];
             }
-            asm volatile("bar.sync 1, 128;");
-            double tot_x = 0.0, tot_y = 0.0;
-            for (int k = 0; k < 8; ++k) { tot_x += red[k * 128 + t]; tot_y += red[1024 + k * 128 + t]; }
-            double* wsum = p.ws_sums + ((size_t)ti * p.n_splits + split) * 2 * kStTile;
-            wsum[t] = tot_x;
-            wsum[kStTile + t] = tot_y;
+            asm volatile("bar.sync 1, 256;");
+            if (t < 128) {
+                double tx = 0.0, ty = 0.0;
+                for (int k = 0; k < 16; ++k) { tx += red[k * 128 + t]; ty += red[2048 + k * 128 + t]; }
+                double* wsum = p.ws_sums + ((size_t)ti * p.n_splits + split) * 2 * kStTile;
+                wsum[t] = tx;
+                wsum[kStTile + t] = ty;
+            }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // -------------------------------------------------- drain TMEM -> fp64 smem
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -300,21 +324,24 @@ stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
     const int ti = blockIdx.y, tj = blockIdx.z;
     if (tj < ti) return;
     __shared__ double yi[32][65], yj[32][65];
+    __shared__ float xi[32][65];        // x - shift is exact in fp32
     const long long r_begin = (long long)blockIdx.x * kSimtRows;
     const long long r_end = min(n_rows, r_begin + kSimtRows);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 4x4 outputs per thread
     double c[4][4] = {};
     double csum = 0.0, csum_x = 0.0;
-    __shared__ float xi[32][65];        // x - shift is exact in fp32
     for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
         for (int i = threadIdx.x; i < 32 * 64; i += 256) {
             const int r = i >> 6, cc = i & 63;
             double a = 0.0, b = 0.0; float ax = 0.0f;
             if (r0 + r < r_end) {
                 const __half* rowp = E + (size_t)(r0 + r) * d;
-                a = (double)__half2float(__hsub(rowp[ti * 64 + cc], shift[ti * 64 + cc]));
-                b = (double)__half2float(__hsub(rowp[tj * 64 + cc], shift[tj * 64 + cc]));
-                ax = __half2float(rowp[ti * 64 + cc]) - __half2float(shift[ti * 64 + cc]);
+                const float fa = __half2float(rowp[ti * 64 + cc]) - __half2float(shift[ti * 64 + cc]);
+                const float fb = __half2float(rowp[tj * 64 + cc]) - __half2float(shift[tj * 64 + cc]);
+                const __half ha = __float2half_rn(fa), hb = __float2half_rn(fb);
+                a = (double)__half2float(ha) + (double)__half2float(__float2half_rn(fa - __half2float(ha)));
+                b = (double)__half2float(hb) + (double)__half2float(__float2half_rn(fb - __half2float(hb)));
+                ax = fa;
             }
             yi[r][cc] = a; yj[r][cc] = b; xi[r][cc] = ax;
         }
@@ -349,7 +376,7 @@ stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
     if (blockIdx.x == 0 && ti == 0 && tj == 0 && threadIdx.x == 0) atomicAdd(&acc[0], (double)n_rows);
 }
 
-// mu = shift + sum(x-shift)/n ; cov = (outer - sum(y) sum(y)^T / n) / (n - 1)   (cov = 0 when n < 2,
+// mu = shift + sum(x-s)/n ; cov = (outer - sum(y) sum(y)^T / n) / (n - 1)   (cov = 0 when n < 2,
 // fadtk/utils.py:42-43).  grid-stride over d*d.
 __global__ void stats_finalize_kernel(const double* __restrict__ acc, const __half* __restrict__ shift,
                                       int d, double* __restrict__ mu, double* __restrict__ cov)

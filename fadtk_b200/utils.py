@@ -123,6 +123,36 @@ def calculate_embd_statistics_online(files: list[PathLike]) -> tuple[np.ndarray,
     return statistics_of_arrays(np.load(f) for f in files)
 
 
+def pack_statistics_numpy(rows: np.ndarray, shift: np.ndarray) -> np.ndarray:
+    """Host definition of the packed accumulator the GPU kernels produce (include/fadtk_b200.h):
+    [n | sum(x - shift) exact | sum y y^T | sum y] with y = x - shift carried as an fp16 hi/lo
+    pair.  Used to document and test the wire format of the cross-GPU all-reduce; the product
+    path never calls it."""
+    d = rows.shape[1]
+    x = rows.astype(np.float16)
+    y32 = x.astype(np.float32) - shift.astype(np.float32)          # exact
+    hi = y32.astype(np.float16)
+    lo = (y32 - hi.astype(np.float32)).astype(np.float16)
+    y = hi.astype(np.float64) + lo.astype(np.float64)
+    exact = y32.astype(np.float64)
+    acc = np.zeros(1 + 2 * d + d * d)
+    acc[0] = rows.shape[0]
+    acc[1:1 + d] = exact.sum(0)
+    acc[1 + d:1 + d + d * d] = (y.T @ y).ravel()
+    acc[1 + d + d * d:] = y.sum(0)
+    return acc
+
+
+def finalize_packed_numpy(acc: np.ndarray, shift: np.ndarray):
+    """mu, cov from a packed accumulator (same algebra as csrc/stats.cuh stats_finalize_kernel)."""
+    d = shift.shape[0]
+    n = acc[0]
+    sum_x, outer, sum_y = acc[1:1 + d], acc[1 + d:1 + d + d * d].reshape(d, d), acc[1 + d + d * d:]
+    mu = shift.astype(np.float64) + (sum_x / n if n > 0 else 0.0)
+    cov = np.zeros((d, d)) if n < 2 else (outer - np.outer(sum_y, sum_y) / n) / (n - 1)
+    return mu, cov
+
+
 def find_sox_formats(sox_path: str) -> list[str]:
     """File formats supported by SoX (fadtk/utils.py:49-57); empty when SoX is absent."""
     try:

@@ -100,6 +100,20 @@ int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, 
 int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const double* mu2,
                 const double* cov2, int d, int iters, double* out, void* stream);
 
+/* ---- measurement ----------------------------------------------------------------------
+ * When enabled, CUDA events are recorded on the launching stream around every kernel group;
+ * fad_profile_collect synchronises the device and returns accumulated milliseconds and launch
+ * counts per category (arrays of FAD_PROF_CATEGORIES entries). */
+#define FAD_PROF_LOGMEL        0
+#define FAD_PROF_CONV1         1
+#define FAD_PROF_LAYER0        2   /* +i: conv2, conv3_1, conv3_2, conv4_1, conv4_2, fc1, fc2, fc3 */
+#define FAD_PROF_STATS        10
+#define FAD_PROF_STATS_REDUCE 11
+#define FAD_PROF_FRECHET      12
+#define FAD_PROF_CATEGORIES   16
+int fad_profile_enable(fad_handle* h, int on);
+int fad_profile_collect(fad_handle* h, double* ms_out, long long* count_out, int reset);
+
 /* Number of CUDA kernels this library has launched through `h` (bench.py's gpu_launches). */
 long long fad_launch_count(fad_handle* h);
 

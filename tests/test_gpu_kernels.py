@@ -133,9 +133,9 @@ def test_statistics_match_numpy_float64(engine, n, d, simt):
     assert acc[0].item() == n
     assert np.abs(mu.cpu().numpy() - mu_ref).max() < 1e-9 * (1 + np.abs(mu_ref).max())
     err = np.abs(cov.cpu().numpy() - cov_ref).max() / np.abs(cov_ref).max()
-    # y = fp16(x - shift) is exact when |x - shift| needs <= 11 bits; otherwise 2^-12 relative
-    # per element, unbiased -> ~1e-5 on a covariance entry for small n
-    assert err < (3e-5 if not simt else 3e-5), f"cov rel err {err}"
+    # y = x - shift is carried as an fp16 hi/lo pair (2^-22) and fp32 tensor-core accumulation is
+    # cut every 256 rows -> ~1e-6 of the largest entry
+    assert err < 5e-6, f"cov rel err {err}"
 
 
 def test_statistics_umma_equals_simt_bitwise_inputs(engine):

@@ -1,0 +1,156 @@
+"""CPU tests: plugin surface, cache paths, planning, ABI export list, sharding + the 2-rank
+gloo exchange of packed statistics.  No GPU compute is called here."""
+import ctypes
+import os
+import pickle
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import fadtk_b200 as fk
+from fadtk_b200 import _native, dist, synth, weights
+from oracle import vggish_oracle as vo
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_export_surface_matches_reference_init():
+    # fadtk/__init__.py:1-4 star-exports fad, fad_batch, model_loader, utils
+    for name in ["FrechetAudioDistance", "FADInfResults", "calc_embd_statistics", "calc_frechet_distance",
+                 "cache_embedding_files", "ModelLoader", "VGGishModel", "get_all_models",
+                 "calculate_embd_statistics_online", "get_cache_embedding_path", "find_sox_formats"]:
+        assert hasattr(fk, name), name
+
+
+def test_registry_names_match_reference():
+    models = fk.get_all_models()
+    names = [m.name for m in models]
+    assert len(names) == len(set(names)) == 143
+    for must in ["vggish", "clap-laion-audio", "clap-laion-music", "clap-2023", "encodec-emb", "encodec-emb-48k",
+                 "MERT-v1-95M", "MERT-v1-95M-1", "MERT-v1-95M-11", "w2v2-base", "w2v2-base-1", "w2v2-large",
+                 "w2v2-large-23", "hubert-base", "hubert-large-5", "wavlm-base-plus", "wavlm-large",
+                 "whisper-tiny", "whisper-small", "whisper-large"]:
+        assert must in names, must
+    vgg = dict(zip(names, models))["vggish"]
+    assert (vgg.num_features, vgg.sr, vgg.min_len) == (128, 16000, 1)   # model_loader.py:94
+    # instances travel to worker processes before load_model (fad_batch.py:48)
+    clone = pickle.loads(pickle.dumps(vgg))
+    assert clone.name == "vggish" and clone.model is None
+
+
+def test_cache_path_scheme():
+    p = fk.get_cache_embedding_path("vggish", "/data/set/clip 01.flac")
+    assert p == Path("/data/set/embeddings/vggish/clip 01.npy")       # utils.py:60-68
+
+
+def test_load_wav_and_min_len(tmp_path):
+    pcm = synth.sine_clip(3, 0.4, 16000)
+    synth.write_wav(tmp_path / "a.wav", pcm, 16000)
+    ml = fk.VGGishModel()
+    wav = ml.load_wav(tmp_path / "a.wav")
+    assert wav.dtype == np.float64 and wav.shape[0] == 16000          # zero-padded to min_len = 1 s
+    assert np.array_equal(wav[:pcm.shape[0]], pcm / 32768.0)
+    assert np.all(wav[pcm.shape[0]:] == 0)
+    assert np.array_equal(vo.load_wav_semantics(pcm), wav)            # oracle agrees
+
+
+def test_synthetic_audio_is_deterministic_pcm16():
+    a, b = synth.musiclike_clip(7, 1.0, 16000), synth.musiclike_clip(7, 1.0, 16000)
+    assert a.dtype == np.int16 and np.array_equal(a, b)
+    assert not np.array_equal(a, synth.musiclike_clip(7, 1.0, 16000, baseline=True))
+    s = synth.sine_clip(12, 1.0, 16000)                               # 220 Hz, amplitude 0.5
+    assert abs(int(s.max()) - 16384) <= 1
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "fadtk_b200.h").read_text()
+    declared = set(re.findall(r"\b(fad_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    lib = ctypes.CDLL(str(_native.library_path()))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _native.lib().fad_version() == 1
+
+
+def test_plan_counts_match_oracle_formula():
+    lens = [0, 399, 400, 15599, 15600, 15759, 16000, 30960, 160000, 160001, 480000]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ex, rows = _native.Engine.vggish_plan(off)
+    assert list(rows) == [vo.num_examples(n) for n in lens]
+    assert ex.shape[0] == rows.sum()
+    starts = np.concatenate([off[i] + 96 * 160 * np.arange(r) for i, r in enumerate(rows)])
+    assert np.array_equal(ex, starts)
+
+
+def test_weight_packing_layout():
+    sd = weights.synthetic_vggish_state(3)
+    pk = weights.pack_vggish(sd)
+    w = sd["features.3.weight"]                                        # [128, 64, 3, 3]
+    assert pk["conv2.w"].shape == (128, 9 * 64) and pk["conv2.w"].dtype == torch.float16
+    assert pk["conv2.w"][5, (1 * 3 + 2) * 64 + 7] == w[5, 7, 1, 2].to(torch.float16)
+    assert pk["fc1.w"].shape == (4096, 12288) and pk["conv1.w"].shape == (64, 9)
+    assert weights.state_fingerprint(sd) == weights.state_fingerprint(weights.synthetic_vggish_state(3))
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeError):
+        _native.Engine()
+    with pytest.raises(Exception):
+        fk.calc_frechet_distance(np.zeros(4), np.eye(4), np.zeros(4), np.eye(4))
+
+
+def test_shard_is_array_split():
+    files = list(range(10))
+    parts = [dist.shard(files, r, 4) for r in range(4)]
+    assert parts == [list(x) for x in np.array_split(files, 4)]       # fad_batch.py:43
+
+
+def test_cli_parsers_accept_reference_arguments():
+    out = subprocess.run([sys.executable, "-m", "fadtk_b200", "--help"], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0
+    for flag in ["--inf", "--indiv", "--workers", "--sox-path", "baseline", "eval", "csv"]:
+        assert flag in out.stdout
+    out = subprocess.run([sys.executable, "-m", "fadtk_b200.embeds", "--help"], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0 and "--models" in out.stdout and "--dirs" in out.stdout
+
+
+_WORKER = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from fadtk_b200 import dist
+from fadtk_b200.utils import pack_statistics_numpy, finalize_packed_numpy
+dist.init_from_env("gloo")
+r, w = dist.rank(), dist.world_size()
+rng = np.random.default_rng(0)
+rows = (rng.normal(1.0, 2.0, (1001, 16))).astype(np.float16)
+shift = rows[:64].astype(np.float32).mean(0).astype(np.float16)
+mine = dist.shard(list(range(rows.shape[0])), r, w)
+acc = torch.from_numpy(pack_statistics_numpy(rows[mine], shift))
+dist.allreduce_sum_(acc)
+mu, cov = finalize_packed_numpy(acc.numpy(), shift)
+x = rows.astype(np.float64)
+assert acc[0].item() == rows.shape[0]
+assert np.allclose(mu, x.mean(0), rtol=0, atol=1e-12), np.abs(mu - x.mean(0)).max()
+ref = np.cov(x, rowvar=False)
+assert np.abs(cov - ref).max() < 1e-4 * np.abs(ref).max(), np.abs(cov - ref).max()   # y = fp16(x - shift)
+assert dist.max_over_ranks(float(r)) == w - 1
+print("rank", r, "ok")
+"""
+
+
+def test_two_rank_statistics_allreduce_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script), str(ROOT)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
