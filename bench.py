@@ -92,7 +92,8 @@ class ClockSampler:
 
 def cpu_reference_leg(pcm_clips: np.ndarray, base_stats, state, budget_s: float = 15.0):
     """Reference CPU path on a bounded sample: per-clip loop (fad_batch.py semantics), fp32 torch
-    VGGish restatement, fp16 cache rounding, numpy mean/cov, eig-route Frechet.  -> dict"""
+    VGGish restatement, fp16 cache rounding, per-file statistics + Chan merge (utils.py:13-46),
+    eig-route Frechet.  -> dict"""
     from oracle import fad_oracle as fo, vggish_oracle as vo
     threads = torch.get_num_threads()
     t0 = time.perf_counter()
@@ -104,9 +105,8 @@ def cpu_reference_leg(pcm_clips: np.ndarray, base_stats, state, budget_s: float 
         if time.perf_counter() - t0 > budget_s and used >= 4:
             break
     t_embed = time.perf_counter() - t0
-    rows = np.concatenate(embs)
     t1 = time.perf_counter()
-    mu, cov = fo.embd_statistics(rows)
+    mu, cov = fo.online_statistics(embs)          # one clip = one file: utils.py:19-46 semantics
     t_stats = time.perf_counter() - t1
     t2 = time.perf_counter()
     fad = fo.frechet_distance(base_stats[0], base_stats[1], mu, cov)
@@ -152,7 +152,7 @@ def main():
         from oracle import fad_oracle as fo, vggish_oracle as vo
         base = np.concatenate([vo.embed(vo.load_wav_semantics(synth.musiclike_clip(i, CLIP_SECONDS, SR, True)), state)
                                for i in range(16)])
-        base_stats = fo.embd_statistics(base)
+        base_stats = (base.astype(np.float64).mean(0), np.cov(base.astype(np.float64), rowvar=False))
         sample = np.stack([synth.musiclike_clip(i, CLIP_SECONDS, SR) for i in range(64)])
         per_step = max(4.0, 40.0 / max(1, args.steps + args.warmup))
         for _ in range(args.warmup):

@@ -197,11 +197,11 @@ class Engine:
     def stats_new(self, d: int) -> torch.Tensor:
         return torch.zeros(self.stats_acc_len(d), dtype=torch.float64, device=self.torch_device)
 
-    def stats_accumulate(self, emb, shift, acc, simt=False):
+    def stats_accumulate(self, emb, shift, acc, tensor_core=False):
         assert emb.dtype == torch.float16 and emb.is_contiguous() and shift.dtype == torch.float16
         n, d = emb.shape
         _check(lib().fad_stats_accumulate(self._h, emb.data_ptr(), n, d, shift.data_ptr(),
-                                          acc.data_ptr(), int(simt), _stream()))
+                                          acc.data_ptr(), int(tensor_core), _stream()))
         return acc
 
     def stats_accumulate_gather(self, emb, idx, shift, acc):

@@ -14,11 +14,18 @@
 // zero-filled by hardware - that is the conv padding, and there is no im2col buffer.  TMA
 // writes the 128-byte swizzled K-major layout tcgen05.mma consumes directly.
 //
-// Warp roles (256 threads, persistent over tiles):
+// Accumulation.  The tensor core adds into its fp32 accumulator with truncation: measured on
+// B200, a K-long reduction comes out scaled by (1 - 1.0e-9 K) (tests/diag_accum_bias.py: -1.25e-5
+// at K = 12288) - over the eight layers that alone moves the FAD by ~6e-5 relative.  So the MMA
+// warp accumulates at most kChunkSteps x 64 = 512 of K into one TMEM buffer, and the epilogue
+// warps sum the chunks in registers with ordinary round-to-nearest fp32 adds.  The two TMEM
+// buffers alternate per CHUNK, so draining chunk c overlaps the MMAs of chunk c+1.
+//
+// Warp roles (384 threads, persistent over tiles):
 //   warp 0  TMA producer (one elected lane)        warp 2  TMEM allocator
-//   warp 1  MMA issuer   (one elected lane)        warps 4-7  epilogue (TMEM lane quarter = warp%4)
-// Pipelines: smem ring full[]/empty[] (TMA <-> MMA), TMEM double buffer
-// tmem_full[]/tmem_empty[] (MMA <-> epilogue) so tile i's epilogue overlaps tile i+1's MMAs.
+//   warp 1  MMA issuer   (one elected lane)        warps 4-11 epilogue: TMEM lane quarter = warp%4,
+//                                                  column half = (warp-4)/4
+// Pipelines: smem ring full[]/empty[] (TMA <-> MMA), TMEM chunk buffers tmem_full[]/tmem_empty[].
 #pragma once
 #include "sm100.cuh"
 
@@ -40,7 +47,9 @@ struct ConvGemmParams {
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                        // fp16 elements per 128-B swizzled row
-constexpr int kConvGemmThreads = 256;
+constexpr int kConvGemmThreads = 384;
+constexpr int kEpilogueWarps = 8;
+constexpr int kChunkSteps = 8;                     // k-steps (of 64) per TMEM accumulation chunk
 constexpr uint32_t kABytes = kTileM * kBlockK * 2; // 16 KiB per stage
 
 template <int N_TILE>
@@ -68,8 +77,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
 {
     using namespace sm100;
     constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE>();
-    constexpr uint32_t kTmemCols = 2 * N_TILE;          // double-buffered fp32 accumulator
+    constexpr uint32_t kTmemCols = 2 * N_TILE;          // two chunk buffers
     constexpr uint32_t kIdesc = make_idesc(FMT_F16, kTileM, N_TILE);
+    constexpr int kColsPerWarp = N_TILE / 2;            // each lane quarter is shared by two warps
+    constexpr int kGroups = kColsPerWarp / 32;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -83,6 +94,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ksteps = p.taps * p.cblks;
+    const int n_chunks = (ksteps + kChunkSteps - 1) / kChunkSteps;
+    const int chunk_len = (ksteps + n_chunks - 1) / n_chunks;       // balanced chunks
     const int m_tiles = p.img_groups * p.tiles_h * p.tiles_w;
     const int total_tiles = m_tiles * p.n_tiles;
 
@@ -92,7 +105,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpilogueWarps); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_base_slot);
@@ -101,7 +114,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    if (warp == 0) {
+    // warps 0-3 (one warpgroup) only issue TMA / MMA: hand their registers to the two epilogue
+    // warpgroups, which hold N_TILE/2 fp32 partial sums per thread.  128*88 + 256*208 <= 64 K.
+    if (warp < 4) {
+      setmaxnreg_dec<88>();
+      if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (elect_one()) {
             int s = 0; uint32_t ph = 0;
@@ -125,42 +142,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
         if (elect_one()) {
             int s = 0; uint32_t ph = 0;
-            int acc = 0; uint32_t acc_ph = 0;
+            int buf = 0; uint32_t buf_ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
-                tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + acc * N_TILE;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full[s], ph);
+                for (int ks0 = 0; ks0 < ksteps; ks0 += chunk_len) {
+                    const int ks1 = min(ks0 + chunk_len, ksteps);
+                    mbar_wait(&tmem_empty[buf], buf_ph ^ 1);
                     tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-                    const uint64_t a_desc = kmajor_sw128_desc(a_addr);
-                    const uint64_t b_desc = kmajor_sw128_desc(a_addr + kABytes);
+                    const uint32_t d_tmem = tmem_base + buf * N_TILE;
+                    for (int ks = ks0; ks < ks1; ++ks) {
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after_sync();
+                        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                        const uint64_t a_desc = kmajor_sw128_desc(a_addr);
+                        const uint64_t b_desc = kmajor_sw128_desc(a_addr + kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 B along K inside the 128-B swizzle atom == +2 in the 16-B address field
-                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks | k) != 0);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // +32 B along K inside the 128-B swizzle atom == +2 in the 16-B address field
+                            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
+                        }
+                        umma_commit(&empty[s]);           // smem slot free once these MMAs retire
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(&empty[s]);               // smem slot free once these MMAs retire
-                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                    umma_commit(&tmem_full[buf]);         // chunk complete -> epilogue warps
+                    if (++buf == 2) { buf = 0; buf_ph ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);             // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+      }
+    } else {
         // ---------------------------------------------------------------- epilogue
+        setmaxnreg_inc<208>();
         const int q = warp & 3;                           // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;                 // which half of the tile's columns
         const int r = q * 32 + lane;                      // row of the tile == TMEM lane
         const int bw = p.box_w, bh = p.box_h;
         const int pw = r % bw;
         const int phh = (r / bw) % bh;
         const int pn = r / (bw * bh);
-        int acc = 0; uint32_t acc_ph = 0;
+        int buf = 0; uint32_t buf_ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
             const int m = tile / p.n_tiles;
@@ -169,24 +192,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             const int n = (m / (p.tiles_w * p.tiles_h)) * p.box_n + pn;
             const bool valid = n < p.NB;
 
-            mbar_wait(&tmem_full[acc], acc_ph);
-            tc_fence_after_sync();
-            const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * N_TILE;
-            const int ch0 = nt * N_TILE;
-#pragma unroll 1
-            for (int c = 0; c < N_TILE / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + c * 32, v);
-                tmem_ld_wait();
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ch0 + c * 32);
+            // sum the K chunks in registers (round-to-nearest adds)
+            float acc[kColsPerWarp];
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&tmem_full[buf], buf_ph);
+                tc_fence_after_sync();
+                const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + buf * N_TILE + half * kColsPerWarp;
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + g * 32, v);
+                    tmem_ld_wait();
+                    if (c == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = __uint_as_float(v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(v[j]);
+                    }
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (++buf == 2) { buf = 0; buf_ph ^= 1; }
+            }
+
+            const int ch0 = nt * N_TILE + half * kColsPerWarp;
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ch0 + g * 32);
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 b = __ldg(bias4 + j);
-                    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-                    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-                    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-                    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                    f[4 * j + 0] = acc[g * 32 + 4 * j + 0] + b.x;
+                    f[4 * j + 1] = acc[g * 32 + 4 * j + 1] + b.y;
+                    f[4 * j + 2] = acc[g * 32 + 4 * j + 2] + b.z;
+                    f[4 * j + 3] = acc[g * 32 + 4 * j + 3] + b.w;
                 }
                 if (p.relu) {
 #pragma unroll
@@ -199,12 +241,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 if (!p.pool) {
                     if (valid) {
                         const size_t pix = (size_t(n) * p.H + h) * p.W + w;
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + c * 32);
+                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + g * 32);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             dst[j] = make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
                         if (p.out_f32) {
-                            float4* d32 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + ch0 + c * 32);
+                            float4* d32 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + ch0 + g * 32);
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 d32[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -228,14 +270,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     o.w = sub == 0 ? h2[3] : sub == 1 ? h2[7] : sub == 2 ? h2[11] : h2[15];
                     if (valid) {
                         const size_t pix = (size_t(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-                        *reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + c * 32 + sub * 8) = o;
+                        *reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + g * 32 + sub * 8) = o;
                     }
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     }
 

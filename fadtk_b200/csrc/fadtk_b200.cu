@@ -432,7 +432,7 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
     if (!h->vgg_loaded) return fail("fad_vggish_load has not been called");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    static const int fe_double = []() { const char* e = getenv("FADTK_FRONTEND_FP32"); return (e && e[0] == '1') ? 0 : 1; }();
+    static const int fe_double = []() { const char* e = getenv("FADTK_FRONTEND_FP64"); return (e && e[0] == '1') ? 1 : 0; }();
     for (long long base = 0; base < n_examples; base += h->max_examples) {
         const int nb = (int)((n_examples - base) < h->max_examples ? (n_examples - base) : h->max_examples);
         size_t ev = prof_begin(h, st);
@@ -471,14 +471,14 @@ int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int C
 size_t fad_stats_acc_len(int d) { return 1 + 2 * (size_t)d + (size_t)d * d; }
 
 int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, int d,
-                         const void* shift_f16, double* acc, int use_simt, void* stream) {
+                         const void* shift_f16, double* acc, int tensor_core, void* stream) {
     if (!h) return fail("null handle");
     if (n_rows <= 0) return 0;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const __half* E = reinterpret_cast<const __half*>(emb_f16);
     const __half* shift = reinterpret_cast<const __half*>(shift_f16);
-    if (use_simt) {
+    if (!tensor_core) {
         if (d % 64 != 0) return fail("d must be a multiple of 64");
         dim3 grid((unsigned)((n_rows + fad::kSimtRows - 1) / fad::kSimtRows), d / 64, d / 64);
         fad::stats_simt_kernel<<<grid, 256, 0, st>>>(E, n_rows, d, shift, acc);
@@ -536,7 +536,7 @@ int fad_stats_accumulate_gather(fad_handle* h, const void* emb_f16, long long n_
         reinterpret_cast<const __half*>(emb_f16), idx, n_idx, d, h->gather_buf);
     CK(cudaGetLastError());
     h->launches++;
-    return fad_stats_accumulate(h, h->gather_buf, n_idx, d, shift_f16, acc, 0, stream);
+    return fad_stats_accumulate(h, h->gather_buf, n_idx, d, shift_f16, acc, 0, stream);   // exact fp64 path
 }
 
 int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, int d,
@@ -555,13 +555,24 @@ int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, 
 
 // ----------------------------------------------------------------------------- Frechet
 namespace {
-int launch_dgemm(fad_handle* h, const double* A, const double* B, double* C, int d, double alpha,
-                 double beta_diag, double* trace, cudaStream_t st) {
-    dim3 grid((d + 63) / 64, (d + 63) / 64);
-    fad::dgemm_kernel<<<grid, 256, 0, st>>>(A, B, C, d, alpha, beta_diag, trace);
+int launch_dgemm2(fad_handle* h, const fad::DgemmBatch& batch, int nprob, int d, cudaStream_t st) {
+    if (d <= 256) {
+        dim3 grid((d + 31) / 32, (d + 31) / 32, nprob);
+        fad::dgemm_kernel<32><<<grid, 256, 0, st>>>(batch, d);
+    } else {
+        dim3 grid((d + 63) / 64, (d + 63) / 64, nprob);
+        fad::dgemm_kernel<64><<<grid, 256, 0, st>>>(batch, d);
+    }
     CK(cudaGetLastError());
     h->launches++;
     return 0;
+}
+int launch_dgemm(fad_handle* h, const double* A, const double* B, double* C, int d, double alpha,
+                 double beta_diag, double* trace, cudaStream_t st) {
+    fad::DgemmBatch batch;
+    batch.p[0] = {A, B, C, alpha, beta_diag, trace};
+    batch.p[1] = batch.p[0];
+    return launch_dgemm2(h, batch, 1, d, st);
 }
 
 // Coupled Newton-Schulz: on return Y ~ sqrt(sym(A)/|A|_F); scal[0..1] = |A|_F, tr A; trY set.
@@ -579,8 +590,10 @@ int newton_schulz(fad_handle* h, const double* A, int d, int iters, double* Y, d
         if (launch_dgemm(h, Zc, Yc, W, d, -0.5, 1.5, nullptr, st)) return 1;      // W = 1.5 I - 0.5 Z Y
         const bool last = (it == iters - 1);
         if (last) { CK(cudaMemsetAsync(trY, 0, sizeof(double), st)); CK(cudaMemsetAsync(trZ, 0, sizeof(double), st)); }
-        if (launch_dgemm(h, Yc, W, Yn, d, 1.0, 0.0, last ? trY : nullptr, st)) return 1;   // Y <- Y W
-        if (launch_dgemm(h, W, Zc, Zn, d, 1.0, 0.0, last ? trZ : nullptr, st)) return 1;   // Z <- W Z
+        fad::DgemmBatch yz;
+        yz.p[0] = {Yc, W, Yn, 1.0, 0.0, last ? trY : nullptr};                   // Y <- Y W
+        yz.p[1] = {W, Zc, Zn, 1.0, 0.0, last ? trZ : nullptr};                   // Z <- W Z
+        if (launch_dgemm2(h, yz, 2, d, st)) return 1;
         double* t = Yc; Yc = Yn; Yn = t;
         t = Zc; Zc = Zn; Zn = t;
     }

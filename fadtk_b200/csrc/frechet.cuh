@@ -19,52 +19,61 @@
 namespace fad {
 
 // C = alpha * A * B + beta_diag * I   (row-major d x d, fp64), optional trace(C) accumulation.
-// 64x64 tile / 256 threads / 4x4 per thread, K step 16.
+// Up to two independent problems per launch (blockIdx.z): the Y <- Y W and Z <- W Z updates of
+// one Newton-Schulz iteration run side by side.  TM x TM tile / 256 threads, K step 16;
+// TM = 32 for small d (more CTAs), 64 otherwise.
+struct DgemmProblem { const double* A; const double* B; double* C; double alpha, beta_diag; double* trace_out; };
+struct DgemmBatch { DgemmProblem p[2]; };
+
+template <int TM>
 __global__ void __launch_bounds__(256)
-dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
-             int d, double alpha, double beta_diag, double* __restrict__ trace_out)
+dgemm_kernel(const DgemmBatch batch, int d)
 {
-    __shared__ double As[16][65], Bs[16][65];
-    const int bi = blockIdx.y * 64, bj = blockIdx.x * 64;
+    constexpr int R = TM / 16;                                 // outputs per thread per dimension
+    const DgemmProblem pr = batch.p[blockIdx.z];
+    const double* __restrict__ A = pr.A;
+    const double* __restrict__ B = pr.B;
+    __shared__ double As[16][TM + 1], Bs[16][TM + 1];
+    const int bi = blockIdx.y * TM, bj = blockIdx.x * TM;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double c[4][4] = {};
+    double c[R][R] = {};
     for (int k0 = 0; k0 < d; k0 += 16) {
-        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-            const int r = i >> 4, k = i & 15;                  // A tile: 64 rows x 16 k
+        for (int i = threadIdx.x; i < TM * 16; i += 256) {
+            const int r = i >> 4, k = i & 15;                  // A tile: TM rows x 16 k
             const int gi = bi + r, gk = k0 + k;
             As[k][r] = (gi < d && gk < d) ? A[(size_t)gi * d + gk] : 0.0;
         }
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-            const int k = i >> 6, cc = i & 63;                 // B tile: 16 k x 64 cols
+        for (int i = threadIdx.x; i < 16 * TM; i += 256) {
+            const int k = i / TM, cc = i % TM;                 // B tile: 16 k x TM cols
             const int gk = k0 + k, gj = bj + cc;
             Bs[k][cc] = (gk < d && gj < d) ? B[(size_t)gk * d + gj] : 0.0;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            double a[4], b[4];
+            double a[R], b[R];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { a[u] = As[k][ty * 4 + u]; b[u] = Bs[k][tx * 4 + u]; }
+            for (int u = 0; u < R; ++u) { a[u] = As[k][ty * R + u]; b[u] = Bs[k][tx * R + u]; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < R; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) c[u][v] = fma(a[u], b[v], c[u][v]);
+                for (int v = 0; v < R; ++v) c[u][v] = fma(a[u], b[v], c[u][v]);
         }
         __syncthreads();
     }
     double tr = 0.0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < R; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int gi = bi + ty * 4 + u, gj = bj + tx * 4 + v;
+        for (int v = 0; v < R; ++v) {
+            const int gi = bi + ty * R + u, gj = bj + tx * R + v;
             if (gi < d && gj < d) {
-                double val = alpha * c[u][v];
-                if (gi == gj) { val += beta_diag; tr += val; }
-                C[(size_t)gi * d + gj] = val;
+                double val = pr.alpha * c[u][v];
+                if (gi == gj) { val += pr.beta_diag; tr += val; }
+                pr.C[(size_t)gi * d + gj] = val;
             }
         }
-    if (trace_out != nullptr && bi == bj) {
+    if (pr.trace_out != nullptr && bi == bj) {
         // diagonal blocks only; reduce inside the block, one atomic per block
         __shared__ double red[256];
         red[threadIdx.x] = tr;
@@ -73,7 +82,7 @@ dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double*
             if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
             __syncthreads();
         }
-        if (threadIdx.x == 0) atomicAdd(trace_out, red[0]);
+        if (threadIdx.x == 0) atomicAdd(pr.trace_out, red[0]);
     }
 }
 

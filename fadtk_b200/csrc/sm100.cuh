@@ -28,6 +28,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ------------------------------------------------- register redistribution (per warpgroup)
+template <uint32_t kRegs> __device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <uint32_t kRegs> __device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 // ------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -51,22 +59,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// Watchdog: no wait in this library is legitimately longer than a few milliseconds; a
-// protocol bug traps (-> cudaErrorLaunchFailure on the host) instead of hanging the GPU.
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+// Watchdog: no wait in this library is legitimately longer than a few milliseconds; a protocol
+// bug traps (-> cudaErrorLaunchFailure on the host) instead of hanging the GPU.  Kept free of
+// function calls (no printf) so ptxas can give each warp role its own setmaxnreg budget.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) {
-            printf("fadtk_b200: mbarrier watchdog (block %d thread %d bar %u parity %u)\n",
-                   blockIdx.x, threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
+        if (clock64() - t0 > 8000000000LL) asm volatile("trap;");
     }
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (int i = 0; i < 64; ++i)
-        if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(bar, parity);
 }
 
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA reads)

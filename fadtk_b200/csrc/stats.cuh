@@ -20,7 +20,14 @@
 //     warps 12-15  drain: every 256 rows the TMEM tile is added into an fp64 tile in shared memory
 //   Each job stores its fp64 tile to a workspace; stats_reduce_kernel sums jobs in a fixed
 //   order (deterministic) into the caller's packed accumulator.
-// stats_simt_kernel    plain fp64 CUDA-core version of the same contraction (verification).
+// stats_simt_kernel    fp64 CUDA-core contraction of the EXACT y = x - s (fp32 value, fp64 products
+//   and sums): the result is the Gram matrix of the data to ~1e-16, hence positive semi-definite.
+//   This is the product default.  Parity needs it: a covariance with cond ~1e9 (CLAP/MERT) or a
+//   rank-deficient per-song covariance perturbed at the 1e-6 level of the fp32-accumulating
+//   tensor-core path is indefinite - Newton-Schulz diverges on it and tr sqrt(C1 C2) moves by
+//   percents (eigenvalues below the perturbation are destroyed).  The tensor-core kernel stays
+//   available (tensor_core = 1) for full-rank, well-conditioned sets; cost is irrelevant either
+//   way (3.3 GFLOP for 100 000 x 128, vs 173 TFLOP for the embeddings that produced them).
 //
 // Packed accumulator (fp64, caller-owned, all-reduced across GPUs as-is):
 //   acc[0] = n,  acc[1 .. d] = sum(x - s) (exact),  acc[1+d .. 1+d+d*d) = sum(y y^T)
@@ -324,7 +331,6 @@ stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
     const int ti = blockIdx.y, tj = blockIdx.z;
     if (tj < ti) return;
     __shared__ double yi[32][65], yj[32][65];
-    __shared__ float xi[32][65];        // x - shift is exact in fp32
     const long long r_begin = (long long)blockIdx.x * kSimtRows;
     const long long r_end = min(n_rows, r_begin + kSimtRows);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 4x4 outputs per thread
@@ -333,17 +339,16 @@ stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
     for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
         for (int i = threadIdx.x; i < 32 * 64; i += 256) {
             const int r = i >> 6, cc = i & 63;
-            double a = 0.0, b = 0.0; float ax = 0.0f;
+            double a = 0.0, b = 0.0, ax = 0.0;
             if (r0 + r < r_end) {
                 const __half* rowp = E + (size_t)(r0 + r) * d;
-                const float fa = __half2float(rowp[ti * 64 + cc]) - __half2float(shift[ti * 64 + cc]);
-                const float fb = __half2float(rowp[tj * 64 + cc]) - __half2float(shift[tj * 64 + cc]);
-                const __half ha = __float2half_rn(fa), hb = __float2half_rn(fb);
-                a = (double)__half2float(ha) + (double)__half2float(__float2half_rn(fa - __half2float(ha)));
-                b = (double)__half2float(hb) + (double)__half2float(__float2half_rn(fb - __half2float(hb)));
-                ax = fa;
+                // x - s in fp64 is exact for any two fp16 values; products of such differences carry
+                // <= 2 x 40 bits, rounded once to fp64: relative error 1e-16 per term
+                a = (double)__half2float(rowp[ti * 64 + cc]) - (double)__half2float(shift[ti * 64 + cc]);
+                b = (double)__half2float(rowp[tj * 64 + cc]) - (double)__half2float(shift[tj * 64 + cc]);
+                ax = a;
             }
-            yi[r][cc] = a; yj[r][cc] = b; xi[r][cc] = ax;
+            yi[r][cc] = a; yj[r][cc] = b; (void)ax;
         }
         __syncthreads();
 #pragma unroll 4
@@ -357,7 +362,8 @@ stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
                 for (int v = 0; v < 4; ++v) c[u][v] = fma(a[u], b[v], c[u][v]);
         }
         if (ti == tj && threadIdx.x < 64)
-            for (int r = 0; r < 32; ++r) { csum += yi[r][threadIdx.x]; csum_x += (double)xi[r][threadIdx.x]; }
+            for (int r = 0; r < 32; ++r) { csum += yi[r][threadIdx.x]; }
+        csum_x = csum;                                      // y is exact here: both sums coincide
         __syncthreads();
     }
     double* outer = acc + 1 + d;

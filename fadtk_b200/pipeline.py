@@ -4,7 +4,11 @@ The reference moves everything between stages through files (.wav -> .npy -> mu/
 SURVEY.md section 1).  ``cache_embedding_files`` / ``FrechetAudioDistance`` keep that contract;
 this module is the same arithmetic with the stages chained on one CUDA stream, used when the
 caller already holds PCM in memory (and by bench.py).  Under torch.distributed every rank feeds
-its own shard of clips and the packed statistics are all-reduced once before the Frechet chain.
+its own shard of clips and ONE all-reduce of the packed statistics precedes the Frechet chain.
+
+Semantics = the reference's directory flow with one clip per file: embeddings are rounded to
+fp16 (model_loader.py:47-48), per-file means are rounded to fp16 before the merge
+(utils.py:13-46) - mirrored here from per-clip means, see utils.mirror_file_mean_rounding.
 """
 from __future__ import annotations
 
@@ -12,14 +16,13 @@ import numpy as np
 import torch
 
 from . import _native, dist
-from .utils import DeviceStatistics
 
 
 class EvalSetFAD:
     """FAD of equal-length PCM16 clips against fixed baseline statistics."""
 
     def __init__(self, engine: _native.Engine, mu_base: torch.Tensor, cov_base: torch.Tensor,
-                 clip_samples: int, clips_per_chunk: int = 1000):
+                 clip_samples: int, clips_per_chunk: int = 1000, mirror_file_means: bool = True):
         self.eng = engine
         self.dev = engine.torch_device
         self.mu_base = mu_base.to(self.dev, torch.float64).contiguous()
@@ -27,6 +30,8 @@ class EvalSetFAD:
         self.clip_samples = int(clip_samples)
         self.clips_per_chunk = int(clips_per_chunk)
         self.rows_per_clip = int(_native.lib().fad_vggish_num_examples(self.clip_samples))
+        self.mirror = mirror_file_means
+        self.d = 128
         self.shift = None
         self._copy_stream = torch.cuda.Stream(device=self.dev)
         self._staging = None
@@ -36,33 +41,53 @@ class EvalSetFAD:
         ex, _ = self.eng.vggish_plan(off)
         return torch.from_numpy(ex).to(self.dev, non_blocking=True)
 
-    def _finish(self, st: DeviceStatistics) -> torch.Tensor:
-        st.allreduce()                                   # one NCCL all-reduce of d^2+2d+1 doubles
-        mu, cov = st.finalize()
-        return self.eng.frechet(self.mu_base, self.cov_base, mu, cov)
-
-    def _stats(self, emb_first: torch.Tensor) -> DeviceStatistics:
-        st = DeviceStatistics(128, self.eng)
+    def _shared_shift(self, emb: torch.Tensor) -> torch.Tensor:
         if self.shift is None:
-            # shared shift: every rank must use the same vector, take rank 0's first-chunk mean
-            s = emb_first[:4096].float().mean(0)
+            # every rank must use the same vector: rank 0's first-rows mean
+            s = emb[:4096].float().mean(0)
             if dist.is_distributed():
                 torch.distributed.broadcast(s, src=0)
             self.shift = s.to(torch.float16)
-        st.wide = False
-        st.shift = self.shift
-        st.acc = self.eng.stats_new(128)
-        return st
+        return self.shift
+
+    def _score(self, emb: torch.Tensor) -> torch.Tensor:
+        """fp16 [n_clips * rows_per_clip, d] (this rank's shard) -> fp64[8] (device)."""
+        d, r = self.d, self.rows_per_clip
+        shift = self._shared_shift(emb)
+        n_acc = self.eng.stats_acc_len(d)
+        buf = torch.zeros(n_acc + (2 * d * d + d if self.mirror else 0), dtype=torch.float64, device=self.dev)
+        acc = buf[:n_acc]
+        self.eng.stats_accumulate(emb, shift, acc)
+        if self.mirror:
+            # per-clip means: exact (fp64) and as numpy would return them for an fp16 file (fp16)
+            per = emb.view(-1, r, d)
+            m64 = per.double().mean(1)
+            m16 = per.float().mean(1).to(torch.float16).double()
+            w = float(r)
+            buf[n_acc:n_acc + d * d] = (w * (m64.t() @ m64)).reshape(-1)
+            buf[n_acc + d * d:n_acc + 2 * d * d] = (w * (m16.t() @ m16)).reshape(-1)
+            buf[n_acc + 2 * d * d:] = w * m16.sum(0)
+        dist.allreduce_sum_(buf)                              # the only cross-GPU exchange
+        mu, cov = self.eng.stats_finalize(acc, shift, d)
+        if self.mirror:
+            n = acc[0]
+            p64 = buf[n_acc:n_acc + d * d].view(d, d)
+            p16 = buf[n_acc + d * d:n_acc + 2 * d * d].view(d, d)
+            s16 = buf[n_acc + 2 * d * d:]
+            s64 = mu * n                                      # sum of all rows
+            mu_ref = s16 / n
+            # sum_f n_f (m_f - c)(m_f - c)^T = P - c s^T - s c^T + n c c^T
+            b64 = p64 - torch.outer(mu, s64) - torch.outer(s64, mu) + n * torch.outer(mu, mu)
+            b16 = p16 - torch.outer(mu_ref, s16) - torch.outer(s16, mu_ref) + n * torch.outer(mu_ref, mu_ref)
+            cov = (cov * (n - 1) - b64 + b16) / (n - 1)
+            mu = mu_ref
+        return self.eng.frechet(self.mu_base, self.cov_base, mu.contiguous(), cov.contiguous())
 
     def run_device(self, pcm_dev: torch.Tensor) -> torch.Tensor:
         """pcm_dev int16 [n_clips, clip_samples] resident in HBM -> fp64[8] result (device)."""
         n_clips = pcm_dev.shape[0]
-        flat = pcm_dev.reshape(-1)
-        ex = self._plan(n_clips)
-        emb = self.eng.vggish_forward(flat, ex)
-        st = self._stats(emb)
-        self.eng.stats_accumulate(emb, st.shift, st.acc)
-        return self._finish(st)
+        emb = self.eng.vggish_forward(pcm_dev.reshape(-1), self._plan(n_clips))
+        return self._score(emb)
 
     def run_host(self, pcm_host: torch.Tensor) -> float:
         """pcm_host: PINNED int16 [n_clips, clip_samples].  H2D copies (double-buffered on a copy
@@ -77,8 +102,7 @@ class EvalSetFAD:
             self._free = [torch.cuda.Event() for _ in range(2)]
         main = torch.cuda.current_stream(self.dev)
         ex_chunk = self._plan(cpc)
-        emb_all = torch.empty((n_clips * self.rows_per_clip, 128), dtype=torch.float16, device=self.dev)
-        st = None
+        emb_all = torch.empty((n_clips * self.rows_per_clip, self.d), dtype=torch.float16, device=self.dev)
         for i, s in enumerate(range(0, n_clips, cpc)):
             b = i & 1
             c = min(cpc, n_clips - s)
@@ -92,7 +116,4 @@ class EvalSetFAD:
             out = emb_all[s * self.rows_per_clip:(s + c) * self.rows_per_clip]
             self.eng.vggish_forward(self._staging[b][:c].reshape(-1), ex, out)
             self._free[b].record(main)
-        st = self._stats(emb_all)
-        self.eng.stats_accumulate(emb_all, st.shift, st.acc)
-        res = self._finish(st)
-        return float(res[0].item())
+        return float(self._score(emb_all)[0].item())

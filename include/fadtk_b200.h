@@ -84,8 +84,14 @@ int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int C
  * It is additive: accumulate batches into it, all-reduce (sum) it across GPUs, then finalize.
  * `shift` (fp16 [d], device) must be identical for every contribution to one accumulator. */
 size_t fad_stats_acc_len(int d);
+/* tensor_core = 0 (default everywhere in the product): fp64 accumulation on the CUDA cores -
+ * the products (x - s)(x - s)^T of fp16 data are exact in fp64, so the result is the Gram matrix
+ * of the data to ~1e-16 and stays positive semi-definite (rank-deficient per-song sets and
+ * covariances with cond ~1e9 need that).
+ * tensor_core = 1: tcgen05 hi/lo-split E^T E (fp32 accumulation, ~1e-6 relative) for
+ * well-conditioned, full-rank sets. */
 int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, int d,
-                         const void* shift_f16, double* acc, int use_simt, void* stream);
+                         const void* shift_f16, double* acc, int tensor_core, void* stream);
 /* rows emb[idx[i]] for i < n_idx (FAD-inf bootstrap, fadtk/fad.py:333-336) */
 int fad_stats_accumulate_gather(fad_handle* h, const void* emb_f16, long long n_src_rows,
                                 const long long* idx, long long n_idx, int d,

@@ -141,7 +141,7 @@ assert np.allclose(mu, x.mean(0), rtol=0, atol=1e-12), np.abs(mu - x.mean(0)).ma
 ref = np.cov(x, rowvar=False)
 assert np.abs(cov - ref).max() < 1e-4 * np.abs(ref).max(), np.abs(cov - ref).max()   # y = fp16(x - shift)
 assert dist.max_over_ranks(float(r)) == w - 1
-print("rank", r, "ok")
+sys.stdout.write(f"[rank{r}:ok]\n"); sys.stdout.flush()
 """
 
 
@@ -153,4 +153,4 @@ def test_two_rank_statistics_allreduce_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29531", str(script), str(ROOT)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    assert "rank0:ok" in out.stdout and "rank1:ok" in out.stdout, out.stdout
