@@ -27,7 +27,7 @@ class NativeError(RuntimeError):
 class VggishWeights(C.Structure):
     _fields_ = [("conv1_w_host", c_vp), ("conv1_b_host", c_vp),
                 ("conv_w_host", c_vp * 5), ("conv_b_host", c_vp * 5),
-                ("fc_w_host", c_vp * 3), ("fc_b_host", c_vp * 3)]
+                ("fc_w_host", c_vp * 3), ("fc_b_host", c_vp * 3), ("split_mask", C.c_uint32)]
 
 
 # name -> (restype, argtypes); mirrors include/fadtk_b200.h one to one
@@ -42,7 +42,7 @@ SIGNATURES = {
     "fad_vggish_forward": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_vggish_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, C.c_int, c_vp]),
     "fad_umma_layer": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
-                                 C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_stats_acc_len": (C.c_size_t, [C.c_int]),
     "fad_stats_accumulate": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
     "fad_stats_accumulate_gather": (C.c_int, [c_vp, c_vp, c_ll, c_vp, c_ll, C.c_int, c_vp, c_vp, c_vp]),
@@ -137,7 +137,7 @@ class Engine:
     def vggish_load(self, packed: dict):
         """``packed`` comes from fadtk_b200.weights.pack_vggish (CPU tensors)."""
         w = VggishWeights()
-        keep = {k: v.contiguous() for k, v in packed.items()}
+        keep = {k: v.contiguous() for k, v in packed.items() if hasattr(v, "contiguous")}
         w.conv1_w_host = keep["conv1.w"].data_ptr()
         w.conv1_b_host = keep["conv1.b"].data_ptr()
         for i in range(5):
@@ -146,6 +146,7 @@ class Engine:
         for i in range(3):
             w.fc_w_host[i] = keep[f"fc{i + 1}.w"].data_ptr()
             w.fc_b_host[i] = keep[f"fc{i + 1}.b"].data_ptr()
+        w.split_mask = int(packed.get("split_mask", 0))
         _check(lib().fad_vggish_load(self._h, C.byref(w)))
 
     @staticmethod
@@ -178,15 +179,17 @@ class Engine:
                                        out.data_ptr(), int(use_double), _stream()))
         return out
 
-    def umma_layer(self, x, w, bias, taps, relu, pool, want_f32=False):
-        """x fp16 NHWC [NB,H,W,Cin]; w fp16 [Cout, taps*Cin]; bias fp32 [Cout]."""
+    def umma_layer(self, x, w, bias, taps, relu, pool, want_f32=False, split_w=False):
+        """x fp16 NHWC [NB,H,W,Cin]; w fp16 [Cout, taps*Cin] (or [2*Cout, taps*Cin] hi/lo tiles when
+        split_w, see weights.split_hi_lo_tiles); bias fp32 [Cout]."""
         nb, hh, ww, cin = x.shape
-        cout = w.shape[0]
+        cout = w.shape[0] // (2 if split_w else 1)
         oh, ow = (hh // 2, ww // 2) if pool else (hh, ww)
         out = torch.empty((nb, oh, ow, cout), dtype=torch.float16, device=x.device)
         out32 = torch.empty((nb, oh, ow, cout), dtype=torch.float32, device=x.device) if want_f32 else None
         _check(lib().fad_umma_layer(self._h, x.data_ptr(), nb, hh, ww, cin, w.data_ptr(), bias.data_ptr(),
-                                    cout, taps, int(relu), int(pool), out.data_ptr(), _ptr(out32), _stream()))
+                                    cout, taps, int(relu), int(pool), int(split_w), out.data_ptr(), _ptr(out32),
+                                    _stream()))
         return (out, out32) if want_f32 else out
 
     # -------------------------------------------------------------- statistics

@@ -70,10 +70,12 @@ int encode_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t*
 struct LayerGeom {
     int taps, Cin, Cout, H, W, relu, pool;
     int box_w, box_h, box_n, n_tile;
+    int split_w;      // weights are an fp16 hi/lo pair, interleaved per 128-row tile
 };
 
-int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu, int pool) {
+int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu, int pool, int split_w) {
     g.taps = taps; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.relu = relu; g.pool = pool;
+    g.split_w = split_w ? 1 : 0;
     if (Cin % 64 != 0) return fail("Cin must be a multiple of 64");
     if (taps != 1 && taps != 9) return fail("taps must be 1 or 9");
     if (H == 1 && W == 1) { g.box_w = 1; g.box_h = 1; g.box_n = 128; }
@@ -87,9 +89,8 @@ int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu,
         g.box_n = 128 / (g.box_w * g.box_h);
     }
     if (pool && (g.box_h % 2 != 0 || g.box_w % 2 != 0)) return fail("pooling needs even tile boxes");
-    if (Cout % 256 == 0) g.n_tile = 256;
-    else if (Cout % 128 == 0) g.n_tile = 128;
-    else return fail("Cout must be a multiple of 128");
+    if (Cout % 128 != 0) return fail("Cout must be a multiple of 128");
+    g.n_tile = (!g.split_w && Cout % 256 == 0) ? 256 : 128;
     return 0;
 }
 
@@ -144,12 +145,12 @@ struct fad_handle {
 
 namespace {
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, bool SPLIT_W>
 int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw,
                      const fad::ConvGemmParams& p, cudaStream_t st) {
     static bool attr_set = false;
-    constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES>();
-    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES>;
+    constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES, SPLIT_W>();
+    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, SPLIT_W>;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -170,9 +171,10 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
     const uint32_t xb[4] = {64, (uint32_t)g.box_w, (uint32_t)g.box_h, (uint32_t)g.box_n};
     if (encode_f16_map(mx, x, 4, xd, xs, xb)) return 1;
     const uint64_t K = (uint64_t)g.taps * g.Cin;
-    const uint64_t wd[2] = {K, (uint64_t)g.Cout};
+    const uint64_t rows_mul = g.split_w ? 2 : 1;
+    const uint64_t wd[2] = {K, (uint64_t)g.Cout * rows_mul};
     const uint64_t ws[1] = {K * 2};
-    const uint32_t wb[2] = {64, (uint32_t)g.n_tile};
+    const uint32_t wb[2] = {64, (uint32_t)(g.n_tile * rows_mul)};
     return encode_f16_map(mw, w, 2, wd, ws, wb);
 }
 
@@ -187,8 +189,9 @@ int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CU
     p.H = g.H; p.W = g.W; p.NB = NB; p.Cout = g.Cout;
     p.relu = g.relu; p.pool = g.pool;
     p.bias = bias; p.out = reinterpret_cast<__half*>(out); p.out_f32 = out_f32;
-    if (g.n_tile == 256) return launch_conv_gemm<256, 4>(h, mx, mw, p, st);
-    return launch_conv_gemm<128, 6>(h, mx, mw, p, st);
+    if (g.split_w) return launch_conv_gemm<128, 4, true>(h, mx, mw, p, st);
+    if (g.n_tile == 256) return launch_conv_gemm<256, 4, false>(h, mx, mw, p, st);
+    return launch_conv_gemm<128, 6, false>(h, mx, mw, p, st);
 }
 
 // VGGish layer table: H, W are the conv's spatial size (input == un-pooled output)
@@ -347,7 +350,8 @@ int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
     CK(cudaSetDevice(h->device));
     auto up = [&](void** dst, const void* src, size_t bytes) -> int {
         if (!src) return fail("missing weight pointer");
-        if (!*dst) CK(cudaMalloc(dst, bytes));
+        if (*dst) { cudaFree(*dst); *dst = nullptr; }          // sizes depend on split_mask
+        CK(cudaMalloc(dst, bytes));
         CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
         return 0;
     };
@@ -355,12 +359,14 @@ int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
     if (up((void**)&h->conv1_b, w->conv1_b_host, 64 * 4)) return 1;
     for (int i = 0; i < 5; ++i) {
         const VggLayer& L = kVgg[i];
-        if (up((void**)&h->conv_w[i], w->conv_w_host[i], (size_t)L.Cout * 9 * L.Cin * 2)) return 1;
+        const size_t mul = ((w->split_mask >> i) & 1) ? 2 : 1;
+        if (up((void**)&h->conv_w[i], w->conv_w_host[i], mul * L.Cout * 9 * L.Cin * 2)) return 1;
         if (up((void**)&h->conv_b[i], w->conv_b_host[i], (size_t)L.Cout * 4)) return 1;
     }
     for (int i = 0; i < 3; ++i) {
         const VggLayer& L = kVgg[5 + i];
-        if (up((void**)&h->fc_w[i], w->fc_w_host[i], (size_t)L.Cout * L.Cin * 2)) return 1;
+        const size_t mul = ((w->split_mask >> (5 + i)) & 1) ? 2 : 1;
+        if (up((void**)&h->fc_w[i], w->fc_w_host[i], mul * L.Cout * L.Cin * 2)) return 1;
         if (up((void**)&h->fc_b[i], w->fc_b_host[i], (size_t)L.Cout * 4)) return 1;
     }
     const size_t B = (size_t)h->max_examples;
@@ -371,7 +377,7 @@ int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
     // batch are never scheduled and rows past it are masked in the epilogue)
     for (int i = 0; i < 8; ++i) {
         const VggLayer& L = kVgg[i];
-        if (make_geom(h->geom[i], L.H, L.W, L.Cin, L.Cout, L.taps, L.relu, L.pool)) return 1;
+        if (make_geom(h->geom[i], L.H, L.W, L.Cin, L.Cout, L.taps, L.relu, L.pool, (w->split_mask >> i) & 1)) return 1;
         const void* wptr = i < 5 ? (const void*)h->conv_w[i] : (const void*)h->fc_w[i - 5];
         if (encode_layer_maps(h->geom[i], h->act[i], (long long)B, wptr, &h->map_x[i], &h->map_w[i])) return 1;
     }
@@ -456,11 +462,11 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
 
 int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int Cin,
                    const void* w_f16, const float* bias, int Cout, int taps, int relu, int pool,
-                   void* out_f16, float* out_f32_or_null, void* stream) {
+                   int split_w, void* out_f16, float* out_f32_or_null, void* stream) {
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->device));
     LayerGeom g;
-    if (make_geom(g, H, W, Cin, Cout, taps, relu, pool)) return 1;
+    if (make_geom(g, H, W, Cin, Cout, taps, relu, pool, split_w)) return 1;
     if (pool && out_f32_or_null) return fail("fp32 copy is only available for un-pooled layers");
     CUtensorMap mx, mw;
     if (encode_layer_maps(g, x_f16, NB, w_f16, &mx, &mw)) return 1;
@@ -569,38 +575,52 @@ int launch_dgemm2(fad_handle* h, const fad::DgemmBatch& batch, int nprob, int d,
 }
 int launch_dgemm(fad_handle* h, const double* A, const double* B, double* C, int d, double alpha,
                  double beta_diag, double* trace, cudaStream_t st) {
-    fad::DgemmBatch batch;
+    fad::DgemmBatch batch = {};
     batch.p[0] = {A, B, C, alpha, beta_diag, trace};
     batch.p[1] = batch.p[0];
     return launch_dgemm2(h, batch, 1, d, st);
 }
 
-// Coupled Newton-Schulz: on return Y ~ sqrt(sym(A)/|A|_F); scal[0..1] = |A|_F, tr A; trY set.
+// Coupled Newton-Schulz: on return Y ~ sqrt(sym(A)/|A|_F + delta I), Z its inverse;
+// scal[0..1] = |A|_F, tr A; trY / trZ = traces of the converged iterates.
 int newton_schulz(fad_handle* h, const double* A, int d, int iters, double* Y, double* Z, double* W,
-                  double* T, double* scal, double* trY, double* trZ, cudaStream_t st) {
+                  double* T, double* scal, double* trY, double* trZ, float* dev /*3 floats*/, cudaStream_t st) {
     const size_t total = (size_t)d * d;
     unsigned eb = (unsigned)((total + 255) / 256);
     if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
+    static const float dev_init[3] = {0.0f, 0.0f, 1.0e30f};            // slot (k-1)%3 for k = 0 is slot 2
+    CK(cudaMemcpyAsync(dev, dev_init, sizeof dev_init, cudaMemcpyHostToDevice, st));
     fad::norm_trace_kernel<<<1, 256, 0, st>>>(A, d, scal);
     fad::ns_init_kernel<<<eb, 256, 0, st>>>(A, d, scal, Y, Z);
     CK(cudaGetLastError());
     h->launches += 2;
+    // (Y, Z) <-> (T, T+total) ping-pong on a fixed host schedule; an even iteration count lands the
+    // last scheduled update in (Y, Z).  If the device stops early (dev < tol) the two pairs differ by
+    // one factor W with |W - I| < tol, i.e. by < 1e-12 relative - either is the converged iterate.
+    if (iters & 1) ++iters;
     double* Yc = Y; double* Zc = Z; double* Yn = T; double* Zn = T + total;
+    const float tol = 1e-12f;
     for (int it = 0; it < iters; ++it) {
-        if (launch_dgemm(h, Zc, Yc, W, d, -0.5, 1.5, nullptr, st)) return 1;      // W = 1.5 I - 0.5 Z Y
-        const bool last = (it == iters - 1);
-        if (last) { CK(cudaMemsetAsync(trY, 0, sizeof(double), st)); CK(cudaMemsetAsync(trZ, 0, sizeof(double), st)); }
-        fad::DgemmBatch yz;
-        yz.p[0] = {Yc, W, Yn, 1.0, 0.0, last ? trY : nullptr};                   // Y <- Y W
-        yz.p[1] = {W, Zc, Zn, 1.0, 0.0, last ? trZ : nullptr};                   // Z <- W Z
+        float* d_prev = dev + (it + 2) % 3;       // max |W - I| of iteration it-1
+        float* d_cur = dev + it % 3;
+        float* d_next = dev + (it + 1) % 3;
+        fad::DgemmBatch wb = {};
+        wb.p[0] = {Zc, Yc, W, -0.5, 1.5, nullptr};                               // W = 1.5 I - 0.5 Z Y
+        wb.p[1] = wb.p[0];
+        wb.dev_in = d_prev; wb.dev_out = d_cur; wb.dev_clear = nullptr; wb.tol = tol;
+        if (launch_dgemm2(h, wb, 1, d, st)) return 1;
+        fad::DgemmBatch yz = {};
+        yz.p[0] = {Yc, W, Yn, 1.0, 0.0, nullptr};                                // Y <- Y W
+        yz.p[1] = {W, Zc, Zn, 1.0, 0.0, nullptr};                                // Z <- W Z
+        yz.dev_in = d_prev; yz.dev_out = nullptr; yz.dev_clear = d_next; yz.tol = tol;
         if (launch_dgemm2(h, yz, 2, d, st)) return 1;
         double* t = Yc; Yc = Yn; Yn = t;
         t = Zc; Zc = Zn; Zn = t;
     }
-    if (Yc != Y) {
-        CK(cudaMemcpyAsync(Y, Yc, total * 8, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(Z, Zc, total * 8, cudaMemcpyDeviceToDevice, st));
-    }
+    fad::trace_kernel<<<1, 256, 0, st>>>(Y, d, trY);
+    fad::trace_kernel<<<1, 256, 0, st>>>(Z, d, trZ);
+    CK(cudaGetLastError());
+    h->launches += 2;
     return 0;
 }
 }  // namespace
@@ -621,12 +641,13 @@ int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const doub
     double* scalA = h->fr_scal;      double* scalB = scalA + 2;  double* scalM = scalA + 4;
     double* trY = scalA + 6;         double* resid = scalA + 7;  double* trS = scalA + 8;
     double* trZ = scalA + 9;         double* trZs = scalA + 10;
+    float* devf = reinterpret_cast<float*>(scalA + 16);
     unsigned eb = (unsigned)((total + 255) / 256);
     if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
 
     const size_t ev_fr = prof_begin(h, st);
     // S = C1^(1/2)
-    if (newton_schulz(h, cov1, d, iters, Y, Z, W, T, scalA, trS, trZs, st)) return 1;
+    if (newton_schulz(h, cov1, d, iters, Y, Z, W, T, scalA, trS, trZs, devf, st)) return 1;
     fad::ns_unscale_kernel<<<eb, 256, 0, st>>>(Y, d, scalA, S);
     // M = S C2 S
     fad::norm_trace_kernel<<<1, 256, 0, st>>>(cov2, d, scalB);
@@ -635,7 +656,7 @@ int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const doub
     if (launch_dgemm(h, S, cov2, P, d, 1.0, 0.0, nullptr, st)) return 1;
     if (launch_dgemm(h, P, S, M, d, 1.0, 0.0, nullptr, st)) return 1;
     // tr sqrt(M)
-    if (newton_schulz(h, M, d, iters, Y, Z, W, T, scalM, trY, trZ, st)) return 1;
+    if (newton_schulz(h, M, d, iters, Y, Z, W, T, scalM, trY, trZ, devf, st)) return 1;
     // residual | Y^2 - sym(M)/|M|_F |_F
     CK(cudaMemsetAsync(resid, 0, sizeof(double), st));
     if (launch_dgemm(h, Y, Y, P, d, 1.0, 0.0, nullptr, st)) return 1;

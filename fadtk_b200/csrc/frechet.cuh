@@ -22,14 +22,25 @@ namespace fad {
 // Up to two independent problems per launch (blockIdx.z): the Y <- Y W and Z <- W Z updates of
 // one Newton-Schulz iteration run side by side.  TM x TM tile / 256 threads, K step 16;
 // TM = 32 for small d (more CTAs), 64 otherwise.
+//
+// Convergence control without host round trips: a launch whose `dev_in` (max |W - I| of the previous
+// iteration) is below `tol` returns immediately, so a fixed-length launch sequence costs only
+// launch latency once the iteration has converged.  `dev_out` receives max |C - I| (float bits,
+// atomicMax), `dev_clear` is zeroed for a later iteration (three rotating slots, see host code).
 struct DgemmProblem { const double* A; const double* B; double* C; double alpha, beta_diag; double* trace_out; };
-struct DgemmBatch { DgemmProblem p[2]; };
+struct DgemmBatch {
+    DgemmProblem p[2];
+    const float* dev_in; float* dev_out; float* dev_clear; float tol;
+};
 
 template <int TM>
 __global__ void __launch_bounds__(256)
 dgemm_kernel(const DgemmBatch batch, int d)
 {
     constexpr int R = TM / 16;                                 // outputs per thread per dimension
+    if (batch.dev_in != nullptr && *batch.dev_in < batch.tol) return;      // already converged
+    if (batch.dev_clear != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+        *batch.dev_clear = 0.0f;
     const DgemmProblem pr = batch.p[blockIdx.z];
     const double* __restrict__ A = pr.A;
     const double* __restrict__ B = pr.B;
@@ -62,6 +73,7 @@ dgemm_kernel(const DgemmBatch batch, int d)
         __syncthreads();
     }
     double tr = 0.0;
+    float dev = 0.0f;
 #pragma unroll
     for (int u = 0; u < R; ++u)
 #pragma unroll
@@ -71,8 +83,13 @@ dgemm_kernel(const DgemmBatch batch, int d)
                 double val = pr.alpha * c[u][v];
                 if (gi == gj) { val += pr.beta_diag; tr += val; }
                 pr.C[(size_t)gi * d + gj] = val;
+                dev = fmaxf(dev, (float)fabs(val - (gi == gj ? 1.0 : 0.0)));
             }
         }
+    if (batch.dev_out != nullptr) {
+        for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(batch.dev_out), __float_as_uint(dev));
+    }
     if (pr.trace_out != nullptr && bi == bj) {
         // diagonal blocks only; reduce inside the block, one atomic per block
         __shared__ double red[256];
@@ -84,6 +101,21 @@ dgemm_kernel(const DgemmBatch batch, int d)
         }
         if (threadIdx.x == 0) atomicAdd(pr.trace_out, red[0]);
     }
+}
+
+// out[0] = tr A      (single block)
+__global__ void trace_kernel(const double* __restrict__ A, int d, double* __restrict__ out)
+{
+    __shared__ double r[256];
+    double t = 0.0;
+    for (int i = threadIdx.x; i < d; i += 256) t += A[(size_t)i * d + i];
+    r[threadIdx.x] = t;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) r[threadIdx.x] += r[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = r[0];
 }
 
 // scal[0] = |A|_F, scal[1] = tr A     (single block)

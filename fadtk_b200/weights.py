@@ -59,8 +59,26 @@ def load_vggish_state(path=None, seed: int = 0) -> dict:
     return synthetic_vggish_state(seed)
 
 
-def pack_vggish(sd: dict) -> dict:
+LAYER_NAMES = ("conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2", "fc1", "fc2", "fc3")
+ALL_LAYERS_SPLIT = 0xFF
+
+
+def split_hi_lo_tiles(w32: torch.Tensor, tile: int = 128) -> torch.Tensor:
+    """fp32 [Cout, K] -> fp16 [2*Cout, K]: per 128-row tile, the hi rows (fp16(w)) followed by the
+    lo rows (fp16(w - hi)); hi + lo carries 22 bits of the weight."""
+    cout, k = w32.shape
+    hi = w32.to(torch.float16)
+    lo = (w32 - hi.float()).to(torch.float16)
+    out = torch.stack([hi.view(cout // tile, tile, k), lo.view(cout // tile, tile, k)], dim=1)
+    return out.reshape(2 * cout, k).contiguous()
+
+
+def pack_vggish(sd: dict, split_mask: int = ALL_LAYERS_SPLIT) -> dict:
     """Re-lay the state-dict for the sm_100a kernels (all on CPU, contiguous).
+
+    ``split_mask`` bit i (LAYER_NAMES order) stores that layer's weights as an fp16 hi/lo pair
+    (split_hi_lo_tiles); default: every tensor-core layer.
+
 
     conv1   : float32 [64, 9]                     (CUDA-core stencil, fp32 input)
     conv2-6 : float16 [Cout, 9*Cin], k = (kh*3+kw)*Cin + cin   (UMMA B operand, K-major)
@@ -72,13 +90,19 @@ def pack_vggish(sd: dict) -> dict:
     key, _, cout, _ = VGGISH_CONVS[0]
     out["conv1.w"] = sd[key + ".weight"].reshape(cout, 9).float().contiguous()
     out["conv1.b"] = sd[key + ".bias"].float().contiguous()
+    def lay(w32, layer_idx):
+        if (split_mask >> layer_idx) & 1:
+            return split_hi_lo_tiles(w32.float().contiguous())
+        return w32.to(torch.float16).contiguous()
+
     for i, (key, cin, cout, _) in enumerate(VGGISH_CONVS[1:], start=2):
         w = sd[key + ".weight"].permute(0, 2, 3, 1).reshape(cout, 9 * cin)
-        out[f"conv{i}.w"] = w.to(torch.float16).contiguous()
+        out[f"conv{i}.w"] = lay(w, i - 2)
         out[f"conv{i}.b"] = sd[key + ".bias"].float().contiguous()
     for i, (key, fin, fout, _) in enumerate(VGGISH_FCS, start=1):
-        out[f"fc{i}.w"] = sd[key + ".weight"].to(torch.float16).contiguous()
+        out[f"fc{i}.w"] = lay(sd[key + ".weight"], 4 + i)
         out[f"fc{i}.b"] = sd[key + ".bias"].float().contiguous()
+    out["split_mask"] = int(split_mask)
     return out
 
 

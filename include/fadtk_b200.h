@@ -44,6 +44,11 @@ typedef struct {
     const float*    conv_b_host[5];
     const uint16_t* fc_w_host[3];   /* fc1..fc3: fp16 [out, in]                           */
     const float*    fc_b_host[3];
+    /* bit i set (i = 0..7: conv2, conv3_1, conv3_2, conv4_1, conv4_2, fc1, fc2, fc3): that layer's
+     * weights are an fp16 hi/lo pair W = Wh + Wl stored as [2*Cout, K] with the 128 hi rows of
+     * each 128-channel tile followed by its 128 lo rows.  fp16-only weights are a fixed model
+     * perturbation worth ~1.4e-4 relative on FAD, the split removes it. */
+    uint32_t        split_mask;
 } fad_vggish_weights;
 
 int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w);
@@ -74,6 +79,7 @@ int fad_vggish_logmel(fad_handle* h, const int16_t* pcm, const long long* ex_sta
  * optional 2x2 max-pool; fp16 NHWC output (and optional fp32 copy of the un-pooled output). */
 int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int Cin,
                    const void* w_f16, const float* bias, int Cout, int taps, int relu, int pool,
+                   int split_w /* weights are [2*Cout, K] hi/lo tiles */,
                    void* out_f16, float* out_f32_or_null, void* stream);
 
 /* ---- statistics: replaces calc_embd_statistics (fadtk/fad.py:42-48) and

@@ -29,6 +29,8 @@ def main():
         w = (torch.randn((cout, taps * cin), generator=g) * (2.0 / (taps * cin)) ** 0.5).to(torch.float16).to(dev)
         b = torch.zeros(cout, device=dev)
         _, out32 = eng.umma_layer(x, w, b, taps, False, False, want_f32=True)
+        from fadtk_b200 import weights as wts
+        _, out32s = eng.umma_layer(x, wts.split_hi_lo_tiles(w.float().cpu()).to(dev), b, taps, False, False, want_f32=True, split_w=True)
         if taps == 9:
             wt = w.double().reshape(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
             ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)
@@ -42,7 +44,8 @@ def main():
         s32 = (ref32.double() * ref).sum() / (ref * ref).sum()
         # magnitude-wise: mean of (|out| - |ref|) / mean |ref|
         shrink = ((o.abs() - ref.abs()).mean() / ref.abs().mean()).item()
-        print(f"K={taps * cin:6d} N={cout:5d}: tcgen05 slope-1 = {slope.item() - 1:+.3e}  |.|-shrink = {shrink:+.3e}  "
+        os_ = out32s.double(); slope_s = (os_ * ref).sum() / (ref * ref).sum()
+        print(f"K={taps * cin:6d} N={cout:5d}: split-W slope-1 = {slope_s.item() - 1:+.3e} rms {((os_ - slope_s * ref).norm() / ref.norm()).item():.2e} | tcgen05 slope-1 = {slope.item() - 1:+.3e}  |.|-shrink = {shrink:+.3e}  "
               f"noise rms = {rms:.2e}   (torch fp32 CUDA slope-1 = {s32.item() - 1:+.3e})")
 
 

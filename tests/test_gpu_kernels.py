@@ -61,21 +61,29 @@ LAYERS = [
 ]
 
 
+@pytest.mark.parametrize("split_w", [False, True])
 @pytest.mark.parametrize("nb,hh,ww,cin,cout,taps,relu,pool", LAYERS)
-def test_umma_layer_matches_fp32_reference(engine, nb, hh, ww, cin, cout, taps, relu, pool):
+def test_umma_layer_matches_fp32_reference(engine, nb, hh, ww, cin, cout, taps, relu, pool, split_w):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = engine.torch_device
     g = torch.Generator(device="cpu").manual_seed(nb * 1000 + cin + cout)
     x = (torch.randn((nb, hh, ww, cin), generator=g) * 1.0).to(torch.float16)
-    w = (torch.randn((cout, taps * cin), generator=g) * (2.0 / (taps * cin)) ** 0.5).to(torch.float16)
+    w32 = torch.randn((cout, taps * cin), generator=g) * (2.0 / (taps * cin)) ** 0.5
     b = torch.randn((cout,), generator=g) * 0.1
+    if split_w:
+        from fadtk_b200 import weights as wts
+        w_dev = wts.split_hi_lo_tiles(w32).to(dev)          # [2*Cout, K] hi/lo tiles, 22-bit weights
+        w = w32                                              # reference uses the fp32 weights
+    else:
+        w = w32.to(torch.float16)
+        w_dev = w.to(dev)
     xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)
     if pool:
-        out = engine.umma_layer(xd, wd, bd, taps, relu, pool)
+        out = engine.umma_layer(xd, w_dev, bd, taps, relu, pool, split_w=split_w)
         out32 = None
     else:
-        out, out32 = engine.umma_layer(xd, wd, bd, taps, relu, pool, want_f32=True)
+        out, out32 = engine.umma_layer(xd, w_dev, bd, taps, relu, pool, want_f32=True, split_w=split_w)
     torch.cuda.synchronize()
     # fp32 reference on the same fp16-rounded operands
     if taps == 9:

@@ -89,11 +89,18 @@ def test_plan_counts_match_oracle_formula():
 
 def test_weight_packing_layout():
     sd = weights.synthetic_vggish_state(3)
-    pk = weights.pack_vggish(sd)
+    pk = weights.pack_vggish(sd, split_mask=0)
     w = sd["features.3.weight"]                                        # [128, 64, 3, 3]
     assert pk["conv2.w"].shape == (128, 9 * 64) and pk["conv2.w"].dtype == torch.float16
     assert pk["conv2.w"][5, (1 * 3 + 2) * 64 + 7] == w[5, 7, 1, 2].to(torch.float16)
     assert pk["fc1.w"].shape == (4096, 12288) and pk["conv1.w"].shape == (64, 9)
+    # default: every tensor-core layer carries hi/lo weights, 128 hi rows then 128 lo rows per tile
+    ps = weights.pack_vggish(sd)
+    assert ps["split_mask"] == 0xFF and ps["fc2.w"].shape == (2 * 4096, 4096)
+    w2 = sd["embeddings.2.weight"]
+    hi, lo = ps["fc2.w"][256 + 3].float(), ps["fc2.w"][256 + 128 + 3].float()   # row 131 of the layer
+    assert torch.equal(hi, w2[131].to(torch.float16).float())
+    assert (hi + lo - w2[131]).abs().max() <= 2.0 ** -21 * w2[131].abs().max()
     assert weights.state_fingerprint(sd) == weights.state_fingerprint(weights.synthetic_vggish_state(3))
 
 
