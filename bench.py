@@ -1,17 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: VGGish FAD on 10 000 x 10 s synthetic 16 kHz clips per GPU
-(BASELINE.json configs[1]).
+"""Benchmark of the hot path.  Default workload = BASELINE.json configs[1]: VGGish FAD on
+10 000 x 10 s synthetic 16 kHz clips per GPU.  `--model clap-laion-audio` runs the configs[2]-style
+workload (CLAP-LAION HTSAT-tiny, 10 s 48 kHz clips, 10 windows per clip) at a single-GPU size.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model M]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the whole hot path over the eval set: PCM16 -> log-mel -> VGGish ->
+One "step" = one pass of the whole hot path over the eval set: PCM16 -> front-end -> embedder ->
 fp16 embeddings -> (n, sum, outer-product) statistics -> [all-reduce] -> Frechet distance against
 fixed baseline statistics.  `value` is audio-seconds embedded per second over all ranks with the
 PCM already resident in HBM; `e2e` is the same step fed from pinned HOST memory (H2D inside the
 timed region, FAD scalar read back).  `--impl reference` times the reference's CPU implementation
-of the path (torch-CPU fp32 VGGish restatement + reference-pinned numpy statistics/Frechet,
-oracle/) on a bounded sample of the same workload.
+of the path (torch-CPU fp32 restatement of the third-party model + reference-pinned numpy
+statistics/Frechet, oracle/) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -30,16 +31,26 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-SR = 16000
 CLIP_SECONDS = 10.0
-CLIP_SAMPLES = int(SR * CLIP_SECONDS)
 ROWS_PER_CLIP = 10
-GFLOP_PER_EXAMPLE = 1.727791104            # BASELINE.md section 5 (conv 1.5925 + FC 0.1353)
-# tensor-core layers only (conv1's 7.1 MFLOP run on the CUDA cores): 2*M*N*K per example
+# tensor-core layers of VGGish (conv1's 7.1 MFLOP run on the CUDA cores): 2*M*N*K per example
 UMMA_LAYER_FLOP = {
     "conv2": 2 * 48 * 32 * 128 * 576, "conv3_1": 2 * 24 * 16 * 256 * 1152, "conv3_2": 2 * 24 * 16 * 256 * 2304,
     "conv4_1": 2 * 12 * 8 * 512 * 2304, "conv4_2": 2 * 12 * 8 * 512 * 4608,
     "fc1": 2 * 12288 * 4096, "fc2": 2 * 4096 * 4096, "fc3": 2 * 4096 * 128,
+}
+# HTSAT-tiny GEMMs per 10-s window: 24 T C^2 per Swin block + 3 patch-merging reductions
+CLAP_GEMM_FLOP = sum(d * 24 * t * c * c for d, t, c in ((2, 4096, 96), (2, 1024, 192), (6, 256, 384), (2, 64, 768))) \
+    + sum(2 * t * 4 * c * 2 * c for t, c in ((1024, 96), (256, 192), (64, 384)))
+
+MODELS = {
+    "vggish": dict(sr=16000, clips=10000, baseline_clips=1000, chunk_clips=1000, d=128,
+                   workload="VGGish FAD, {clips} x 10 s synthetic 16 kHz clips per GPU vs {base}-clip baseline (BASELINE.json configs[1])",
+                   rows_flop=sum(UMMA_LAYER_FLOP.values())),
+    "clap-laion-audio": dict(sr=48000, clips=500, baseline_clips=100, chunk_clips=50, d=512,
+                             workload="clap-laion-audio (HTSAT-tiny) FAD, {clips} x 10 s synthetic 48 kHz clips per GPU vs {base}-clip "
+                                      "baseline (BASELINE.json configs[2] at single-GPU size)",
+                             rows_flop=CLAP_GEMM_FLOP),
 }
 
 
@@ -90,17 +101,26 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_leg(pcm_clips: np.ndarray, base_stats, state, budget_s: float = 15.0):
+def oracle_embed_fn(model: str, state):
+    if model == "vggish":
+        from oracle import vggish_oracle as vo
+        return lambda pcm: vo.embed(vo.load_wav_semantics(pcm), state)
+    from oracle import clap_oracle as co
+    return lambda pcm: co.embed(pcm / 32768.0, state)
+
+
+def cpu_reference_leg(model, pcm_clips: np.ndarray, base_stats, state, budget_s: float = 15.0):
     """Reference CPU path on a bounded sample: per-clip loop (fad_batch.py semantics), fp32 torch
-    VGGish restatement, fp16 cache rounding, per-file statistics + Chan merge (utils.py:13-46),
+    restatement of the model, fp16 cache rounding, per-file statistics + Chan merge (utils.py:13-46),
     eig-route Frechet.  -> dict"""
-    from oracle import fad_oracle as fo, vggish_oracle as vo
+    from oracle import fad_oracle as fo
+    embed = oracle_embed_fn(model, state)
     threads = torch.get_num_threads()
     t0 = time.perf_counter()
     embs = []
     used = 0
     for i in range(pcm_clips.shape[0]):
-        embs.append(vo.embed(vo.load_wav_semantics(pcm_clips[i]), state))
+        embs.append(embed(pcm_clips[i]))
         used += 1
         if time.perf_counter() - t0 > budget_s and used >= 4:
             break
@@ -114,7 +134,7 @@ def cpu_reference_leg(pcm_clips: np.ndarray, base_stats, state, budget_s: float 
     total = t_embed + t_stats + t_fr
     return {"value": used * CLIP_SECONDS / total, "unit": "audio-s/s", "cores": threads, "kind": "port",
             "sample": f"{used} of the eval clips ({used * CLIP_SECONDS:.0f} audio-s): embed {t_embed:.2f}s, "
-                      f"stats {t_stats:.3f}s, frechet {t_fr:.3f}s; oracle/ torch-CPU fp32 VGGish + numpy/scipy "
+                      f"stats {t_stats:.3f}s, frechet {t_fr:.3f}s; oracle/ torch-CPU fp32 {model} + numpy/scipy "
                       f"(reference third-party model is not installable offline)",
             "fad": float(fad), "clips": used, "seconds": total}
 
@@ -125,39 +145,46 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=10000, help="eval clips per GPU")
-    ap.add_argument("--baseline-clips", type=int, default=1000)
-    ap.add_argument("--chunk-clips", type=int, default=1000)
+    ap.add_argument("--model", default="vggish", choices=list(MODELS))
+    ap.add_argument("--clips", type=int, default=0, help="eval clips per GPU (0 = the model's default)")
+    ap.add_argument("--baseline-clips", type=int, default=0)
+    ap.add_argument("--chunk-clips", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    spec = MODELS[args.model]
+    args.clips = args.clips or spec["clips"]
+    args.baseline_clips = args.baseline_clips or spec["baseline_clips"]
+    args.chunk_clips = args.chunk_clips or spec["chunk_clips"]
+    sr = spec["sr"]
+    clip_samples = int(sr * CLIP_SECONDS)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"VGGish FAD, {args.clips} x 10 s synthetic 16 kHz clips per GPU vs {args.baseline_clips}-clip baseline "
-                          f"(BASELINE.json configs[1])",
-              "model": "vggish (seeded synthetic weights, real architecture)", "clips_per_gpu": args.clips,
+    pcm_gb = args.clips * clip_samples * 2 / 1e9
+    config = {"workload": spec["workload"].format(clips=args.clips, base=args.baseline_clips),
+              "model": f"{args.model} (seeded synthetic weights, real architecture)", "clips_per_gpu": args.clips,
               "clip_seconds": CLIP_SECONDS, "chunk_clips": args.chunk_clips,
-              "l2": "inputs (3.2 GB PCM per GPU) exceed L2; no explicit flush", "parallelism": f"dp{world}"}
+              "l2": f"inputs ({pcm_gb:.1f} GB PCM per GPU) exceed L2; no explicit flush", "parallelism": f"dp{world}"}
 
-    from fadtk_b200 import synth, weights
-    state = weights.synthetic_vggish_state(0)
+    from fadtk_b200 import synth, weights, weights_clap
+    state = weights.synthetic_vggish_state(0) if args.model == "vggish" else weights_clap.synthetic_clap_state(0)
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        from oracle import fad_oracle as fo, vggish_oracle as vo
-        base = np.concatenate([vo.embed(vo.load_wav_semantics(synth.musiclike_clip(i, CLIP_SECONDS, SR, True)), state)
-                               for i in range(16)])
+        embed = oracle_embed_fn(args.model, state)
+        n_base, n_eval = (16, 64) if args.model == "vggish" else (4, 16)
+        base = np.concatenate([embed(synth.musiclike_clip(i, CLIP_SECONDS, sr, True)) for i in range(n_base)])
         base_stats = (base.astype(np.float64).mean(0), np.cov(base.astype(np.float64), rowvar=False))
-        sample = np.stack([synth.musiclike_clip(i, CLIP_SECONDS, SR) for i in range(64)])
+        sample = np.stack([synth.musiclike_clip(i, CLIP_SECONDS, sr) for i in range(n_eval)])
         per_step = max(4.0, 40.0 / max(1, args.steps + args.warmup))
         for _ in range(args.warmup):
-            cpu_reference_leg(sample, base_stats, state, budget_s=per_step)
-        legs = [cpu_reference_leg(sample, base_stats, state, budget_s=per_step) for _ in range(args.steps)]
+            cpu_reference_leg(args.model, sample, base_stats, state, budget_s=per_step)
+        legs = [cpu_reference_leg(args.model, sample, base_stats, state, budget_s=per_step) for _ in range(args.steps)]
         secs = sum(l["seconds"] for l in legs)
         clips = sum(l["clips"] for l in legs)
         val = clips * CLIP_SECONDS / secs
@@ -179,20 +206,24 @@ def main():
         dist.init_from_env("nccl")
     dev = torch.device("cuda", local_rank)
     eng = _native.Engine(local_rank, max_examples=args.chunk_clips * ROWS_PER_CLIP)
-    eng.vggish_load(weights.pack_vggish(state))
+    if args.model == "vggish":
+        eng.vggish_load(weights.pack_vggish(state))
+    else:
+        eng.clap_load(weights_clap.pack_clap(state), max_chunks=args.chunk_clips * ROWS_PER_CLIP)
 
     # baseline statistics (identical on every rank), outside the timed region
-    base_pcm = synth.musiclike_device(args.baseline_clips, CLIP_SECONDS, SR, seed=30_000, device=dev)
-    off = np.arange(args.baseline_clips + 1, dtype=np.int64) * CLIP_SAMPLES
-    ex, _ = eng.vggish_plan(off)
-    base_emb = eng.vggish_forward(base_pcm.reshape(-1), torch.from_numpy(ex).to(dev))
+    d = spec["d"]
+    zero_mu, eye = torch.zeros(d, dtype=torch.float64), torch.eye(d, dtype=torch.float64)
+    helper = EvalSetFAD(eng, zero_mu, eye, clip_samples, clips_per_chunk=args.chunk_clips, model=args.model)
+    base_pcm = synth.musiclike_device(args.baseline_clips, CLIP_SECONDS, sr, seed=30_000, device=dev)
+    base_emb = torch.cat([helper.embed(base_pcm[s:s + args.chunk_clips]) for s in range(0, args.baseline_clips, args.chunk_clips)])
     shift = base_emb[:4096].float().mean(0).to(torch.float16)
-    acc = eng.stats_accumulate(base_emb, shift, eng.stats_new(128))
-    mu_b, cov_b = eng.stats_finalize(acc, shift, 128)
+    acc = eng.stats_accumulate(base_emb, shift, eng.stats_new(d))
+    mu_b, cov_b = eng.stats_finalize(acc, shift, d)
     del base_pcm
 
-    pcm = synth.musiclike_device(args.clips, CLIP_SECONDS, SR, seed=20_000 + rank, device=dev)
-    job = EvalSetFAD(eng, mu_b, cov_b, CLIP_SAMPLES, clips_per_chunk=args.chunk_clips)
+    pcm = synth.musiclike_device(args.clips, CLIP_SECONDS, sr, seed=20_000 + rank, device=dev)
+    job = EvalSetFAD(eng, mu_b, cov_b, clip_samples, clips_per_chunk=args.chunk_clips, model=args.model)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -221,28 +252,31 @@ def main():
     audio_s = world * args.clips * CLIP_SECONDS * args.steps
     value = audio_s / (ms / 1000.0)
 
-    # ---- roofline of the dominant kernel (the tcgen05 conv/FC kernel, all 8 layers)
+    # ---- roofline of the dominant kernel: the tcgen05 conv/FC (GEMM) kernel
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    umma_ms = sum(prof[k][0] for k in UMMA_LAYER_FLOP if k in prof)
-    umma_launch = sum(prof[k][1] for k in UMMA_LAYER_FLOP if k in prof)
-    examples = args.clips * ROWS_PER_CLIP * args.steps
-    umma_flop = sum(UMMA_LAYER_FLOP.values()) * examples
+    rows = args.clips * ROWS_PER_CLIP * args.steps                  # examples (VGGish) / 10-s windows (CLAP)
+    gemm_keys = list(UMMA_LAYER_FLOP) if args.model == "vggish" else ["clap_gemm"]
+    umma_ms = sum(prof[k][0] for k in gemm_keys if k in prof)
+    umma_launch = sum(prof[k][1] for k in gemm_keys if k in prof)
+    umma_flop = spec["rows_flop"] * rows
     achieved = umma_flop / (umma_ms / 1000.0) / 1e12 if umma_ms > 0 else 0.0
-    per_layer = {k: {"ms_per_launch": prof[k][0] / prof[k][1], "tflops": UMMA_LAYER_FLOP[k] * examples / (prof[k][0] / 1000.0) / 1e12}
-                 for k in UMMA_LAYER_FLOP if k in prof and prof[k][0] > 0}
-    other = {k: {"ms_total": v[0], "launches": v[1]} for k, v in prof.items() if k not in UMMA_LAYER_FLOP}
-    roofline = {"kernel": "fad::conv_gemm_kernel (tcgen05 kind::f16 implicit-GEMM conv3x3 / FC, 8 layer launches per chunk)",
+    per_layer = {k: {"ms_per_launch": prof[k][0] / prof[k][1], "tflops": UMMA_LAYER_FLOP[k] * rows / (prof[k][0] / 1000.0) / 1e12}
+                 for k in UMMA_LAYER_FLOP if k in prof and prof[k][0] > 0} if args.model == "vggish" else None
+    other = {k: {"ms_total": v[0], "launches": v[1]} for k, v in prof.items() if k not in gemm_keys}
+    roofline = {"kernel": "fad::conv_gemm_kernel<128,4,SPLIT_W> (tcgen05 kind::f16, hi/lo split fp16 weights: 2 MMAs per K step)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": None,
+                "issued_tflops": 2.0 * achieved, "issued_frac": 2.0 * achieved / peak_tf,
+                "note": "achieved counts ALGORITHMIC FLOPs (2*M*N*K once); the kernel issues twice that (W = Wh + Wl) to keep FAD within 1e-4",
                 "launches": umma_launch, "avg_launch_ms": umma_ms / max(1, umma_launch),
-                "algorithmic_gflop_per_example": sum(UMMA_LAYER_FLOP.values()) / 1e9,
+                "algorithmic_gflop_per_row": spec["rows_flop"] / 1e9,
                 "share_of_step": umma_ms / ms if ms > 0 else None,
                 "per_layer": per_layer, "other_kernels": other}
 
     # ---- end to end from pinned host memory
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((args.clips, CLIP_SAMPLES), dtype=torch.int16, pin_memory=True)
+        host = torch.empty((args.clips, clip_samples), dtype=torch.int16, pin_memory=True)
         host.copy_(pcm)
         torch.cuda.synchronize()
         for _ in range(2):
@@ -257,24 +291,24 @@ def main():
         sync_all()
         ms_e = dist.max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1000.0))
         e2e = {"value": audio_s / (ms_e / 1000.0), "unit": "audio-s/s", "ms_per_step": ms_e / args.steps,
-               "h2d_bytes_per_step": int(args.clips * CLIP_SAMPLES * 2 + args.chunk_clips * ROWS_PER_CLIP * 8),
-               "d2h_bytes_per_step": 8, "fad": fad_h,
+               "h2d_bytes_per_step": int(args.clips * clip_samples * 2), "d2h_bytes_per_step": 8, "fad": fad_h,
                "api": "fadtk_b200.pipeline.EvalSetFAD.run_host (pinned int16 PCM in, FAD float out)"}
 
     if rank != 0:
+        dist.shutdown()
         return
 
     # ---- CPU baseline + parity sample (rank 0, N = 1 only)
     cpu = None
     parity = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import fad_oracle as fo, vggish_oracle as vo
-        sample = pcm[:64].cpu().numpy()
+        n_sample = 64 if args.model == "vggish" else 24
+        sample = pcm[:n_sample].cpu().numpy()
         base_stats = (mu_b.cpu().numpy(), cov_b.cpu().numpy())
-        cpu = cpu_reference_leg(sample, base_stats, state, budget_s=15.0)
+        cpu = cpu_reference_leg(args.model, sample, base_stats, state, budget_s=15.0)
         n = cpu["clips"]
         # same clips through the GPU path -> FAD vs the CPU oracle's FAD on identical audio
-        sub = EvalSetFAD(eng, mu_b, cov_b, CLIP_SAMPLES, clips_per_chunk=args.chunk_clips)
+        sub = EvalSetFAD(eng, mu_b, cov_b, clip_samples, clips_per_chunk=args.chunk_clips, model=args.model)
         sub.shift = job.shift
         fad_gpu_sample = float(sub.run_device(pcm[:n].contiguous())[0].item())
         parity = {"clips": n, "fad_gpu": fad_gpu_sample, "fad_cpu_oracle": cpu["fad"],
@@ -288,6 +322,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "parity_sample": parity}
     print(json.dumps(line))
+    dist.shutdown()
 
 
 if __name__ == "__main__":

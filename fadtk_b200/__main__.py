@@ -42,6 +42,7 @@ def main():
         if Path(d).is_dir():
             cache_embedding_files(d, model, workers=args.workers)
     if dist.rank() != 0:
+        dist.shutdown()
         return
 
     # 2. FAD
@@ -72,6 +73,7 @@ def main():
         log.info(f"FAD score appended to {args.csv}")
 
     log.info(f"The FAD {model.name} score between {baseline} and {eval} is: {score}")
+    dist.shutdown()
 
 
 if __name__ == "__main__":

@@ -43,19 +43,26 @@ SIGNATURES = {
     "fad_vggish_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, C.c_int, c_vp]),
     "fad_umma_layer": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "fad_clap_load": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int]),
+    "fad_clap_plan": (c_ll, [c_vp, c_ll, c_vp, c_vp, c_ll, c_vp]),
+    "fad_clap_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "fad_clap_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_stats_acc_len": (C.c_size_t, [C.c_int]),
     "fad_stats_accumulate": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
     "fad_stats_accumulate_gather": (C.c_int, [c_vp, c_vp, c_ll, c_vp, c_ll, C.c_int, c_vp, c_vp, c_vp]),
     "fad_stats_finalize": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "fad_sqrt_psd": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "fad_frechet_presqrt": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_launch_count": (c_ll, [c_vp]),
     "fad_profile_enable": (C.c_int, [c_vp, C.c_int]),
     "fad_profile_collect": (C.c_int, [c_vp, c_vp, c_vp, C.c_int]),
 }
 
-PROF_CATEGORIES = 16
+PROF_CATEGORIES = 20
 PROF_NAMES = {0: "logmel", 1: "conv1", 2: "conv2", 3: "conv3_1", 4: "conv3_2", 5: "conv4_1", 6: "conv4_2",
-              7: "fc1", 8: "fc2", 9: "fc3", 10: "stats_umma", 11: "stats_reduce", 12: "frechet"}
+              7: "fc1", 8: "fc2", 9: "fc3", 10: "stats_umma", 11: "stats_reduce", 12: "frechet",
+              13: "clap_front", 14: "clap_gemm", 15: "clap_attn", 16: "clap_other"}
 
 
 def library_path() -> Path:
@@ -192,6 +199,42 @@ class Engine:
                                     _stream()))
         return (out, out32) if want_f32 else out
 
+    # -------------------------------------------------------------------- CLAP
+    def clap_load(self, tensors: list, max_chunks: int = 32):
+        """``tensors`` comes from fadtk_b200.weights_clap.pack_clap (CPU tensors, fixed order)."""
+        keep = [t.contiguous() for t in tensors]
+        arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
+        _check(lib().fad_clap_load(self._h, arr, len(keep), int(max_chunks)))
+
+    @staticmethod
+    def clap_plan(clip_offsets: np.ndarray):
+        """-> (chunk_start int64 [n], chunk_valid int32 [n], rows_per_clip int64 [n_clips])"""
+        off = np.ascontiguousarray(clip_offsets, dtype=np.int64)
+        n_clips = off.shape[0] - 1
+        rows = np.empty(n_clips, dtype=np.int64)
+        n = lib().fad_clap_plan(off.ctypes.data, n_clips, None, None, 0, rows.ctypes.data)
+        start = np.empty(n, dtype=np.int64)
+        valid = np.empty(n, dtype=np.int32)
+        lib().fad_clap_plan(off.ctypes.data, n_clips, start.ctypes.data, valid.ctypes.data, n, None)
+        return start, valid, rows
+
+    def clap_forward(self, pcm: torch.Tensor, chunk_start: torch.Tensor, chunk_valid: torch.Tensor):
+        """pcm int16 (cuda, 48 kHz); chunk_start int64 / chunk_valid int32 (cuda) -> fp16 [n, 512]."""
+        assert pcm.dtype == torch.int16 and pcm.is_cuda and chunk_start.dtype == torch.int64
+        assert chunk_valid.dtype == torch.int32
+        n = chunk_start.shape[0]
+        out = torch.empty((n, 512), dtype=torch.float16, device=pcm.device)
+        _check(lib().fad_clap_forward(self._h, pcm.data_ptr(), chunk_start.data_ptr(), chunk_valid.data_ptr(), n,
+                                      out.data_ptr(), _stream()))
+        return out
+
+    def clap_logmel(self, pcm, chunk_start, chunk_valid):
+        n = chunk_start.shape[0]
+        out = torch.empty((n, 1001, 64), dtype=torch.float32, device=pcm.device)
+        _check(lib().fad_clap_logmel(self._h, pcm.data_ptr(), chunk_start.data_ptr(), chunk_valid.data_ptr(), n,
+                                     out.data_ptr(), _stream()))
+        return out
+
     # -------------------------------------------------------------- statistics
     @staticmethod
     def stats_acc_len(d: int) -> int:
@@ -230,6 +273,27 @@ class Engine:
         out = torch.zeros(8, dtype=torch.float64, device=mu1.device)
         _check(lib().fad_frechet(self._h, mu1.data_ptr(), cov1.data_ptr(), mu2.data_ptr(), cov2.data_ptr(),
                                  d, iters, out.data_ptr(), _stream()))
+        return out
+
+
+class Baseline:
+    """Device-resident baseline statistics with the matrix square root precomputed."""
+
+    def __init__(self, eng: "Engine", mu, cov):
+        dev = eng.torch_device
+        self.eng = eng
+        self.mu = torch.as_tensor(np.ascontiguousarray(mu, dtype=np.float64)).to(dev)
+        cov = torch.as_tensor(np.ascontiguousarray(cov, dtype=np.float64)).to(dev)
+        self.d = self.mu.shape[0]
+        self.sqrt = torch.empty((self.d, self.d), dtype=torch.float64, device=dev)
+        self.scal = torch.empty(2, dtype=torch.float64, device=dev)
+        _check(lib().fad_sqrt_psd(eng._h, cov.data_ptr(), self.d, 0, self.sqrt.data_ptr(), self.scal.data_ptr(), _stream()))
+
+    def frechet(self, mu2: torch.Tensor, cov2: torch.Tensor) -> torch.Tensor:
+        """fp64 device tensors -> fp64 [8] device (same layout as Engine.frechet)."""
+        out = torch.zeros(8, dtype=torch.float64, device=self.mu.device)
+        _check(lib().fad_frechet_presqrt(self.eng._h, self.mu.data_ptr(), self.sqrt.data_ptr(), self.scal.data_ptr(),
+                                         mu2.data_ptr(), cov2.data_ptr(), self.d, 0, out.data_ptr(), _stream()))
         return out
 
 

@@ -1,0 +1,456 @@
+// CLAP-LAION audio branch (HTSAT-tiny Swin transformer) - the CUDA-core kernels around the
+// tcgen05 GEMMs.  Replaces laion_clap / torchlibrosa behind CLAPLaionModel._get_embedding
+// (fadtk/model_loader.py:389-411); architecture per SURVEY.md appendix B and the HF port of
+// htsat.py (oracle/clap_oracle.py is pinned to it).
+//
+//   clap_logmel_kernel     int16 PCM window -> reference int16 round trip (:413-418) -> centre/reflect
+//                          framing, Hann(1024), |rFFT_1024|^2, 64 Slaney mel bands, 10 log10(clamp),
+//                          BatchNorm(eval) per mel bin -> fp32 [B, 1001, 64].  One warp per frame:
+//                          512-point complex FFT = 16 (registers) x 32 (lanes, shuffles).
+//   clap_patch_embed_kernel bicubic time resize 1001 -> 1024 (align_corners), fold into the 256x256
+//                          "image", 4x4/4 conv 1 -> 96, LayerNorm -> fp32 residual stream [B,4096,96]
+//   clap_ln_kernel         LayerNorm of the fp32 residual stream -> fp16 GEMM operand, rows emitted in
+//                          (shifted-)window order, zero padded to the GEMM's K; merge mode gathers the
+//                          2x2 neighbourhood (4C) for patch merging
+//   clap_window_attention_kernel  softmax(q k^T / sqrt(24) + rel-pos bias (+ shift mask)) v per
+//                          (window, head); fp32 math, one warp per unit
+//   clap_residual_add_kernel      x[token] += y[row]  (row -> token is the inverse window map)
+//   clap_head_kernel       final LayerNorm, token mean, 768->512 ReLU 512->512, L2 normalise -> fp16
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "frontend.cuh"   // Cx, cmul, cadd, csub, mul_neg_i, shfl_xor_t
+
+namespace fad {
+
+constexpr int kClFft = 1024, kClHop = 480, kClMel = 64, kClChunk = 480000, kClFrames = 1001, kClBins = 513;
+constexpr int kClMelTaps = 32;
+constexpr int kClWarps = 8;
+
+struct ClapFrontTables {
+    const float* twiddle;    // [512][2] exp(-2 pi i k / 1024)
+    const float* hann;       // [1024] periodic Hann
+    const float* pcm_lut;    // [65536] reference int16 round trip: index = int16 + 32768
+    const float* mel_w;      // [64][kClMelTaps]
+    const int* mel_start;    // [64]
+    const int* mel_count;    // [64]
+    const float* bn_scale;   // [64] gamma / sqrt(var + eps)
+    const float* bn_shift;   // [64] beta - mean * scale
+};
+
+__host__ __device__ constexpr size_t clap_logmel_smem_bytes() {
+    return sizeof(float) * (size_t)(kClWarps * (2 * 512 + 516) + 2 * 512 + kClFft + kClMel * kClMelTaps + 2 * kClMel)
+         + sizeof(int) * 2 * kClMel;
+}
+
+__device__ __forceinline__ void fft4(Cx<float>& a, Cx<float>& b, Cx<float>& c, Cx<float>& d) {
+    const Cx<float> s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = mul_neg_i(csub(b, d));
+    a = cadd(s0, s2); c = csub(s0, s2); b = cadd(s1, s3); d = csub(s1, s3);
+}
+
+// natural order in / out, forward transform; n = 4a + b, k = ka + 4 kb
+__device__ __forceinline__ void fft16(Cx<float> (&x)[16]) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, c2 = 0.70710678118654752f;
+    // W16^m = (cos, -sin)(2 pi m / 16)
+    const Cx<float> w1 = {c1, -s1}, w2 = {c2, -c2}, w3 = {s1, -c1}, w4 = {0.f, -1.f},
+                    w6 = {-c2, -c2}, w9 = {-c1, s1};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) fft4(x[b], x[4 + b], x[8 + b], x[12 + b]);     // over a -> ka, stored at x[4 ka + b]
+    x[5] = cmul(x[5], w1);  x[9] = cmul(x[9], w2);   x[13] = cmul(x[13], w3);      // b = 1: ka = 1,2,3
+    x[6] = cmul(x[6], w2);  x[10] = cmul(x[10], w4); x[14] = cmul(x[14], w6);      // b = 2
+    x[7] = cmul(x[7], w3);  x[11] = cmul(x[11], w6); x[15] = cmul(x[15], w9);      // b = 3
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) fft4(x[4 * ka], x[4 * ka + 1], x[4 * ka + 2], x[4 * ka + 3]);   // over b -> kb
+    // element (ka, kb) now sits at x[4 ka + kb]; output index k = ka + 4 kb -> transpose
+    Cx<float> t;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) { t = x[4 * i + j]; x[4 * i + j] = x[4 * j + i]; x[4 * j + i] = t; }
+}
+
+__global__ void __launch_bounds__(kClWarps * 32)
+clap_logmel_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ chunk_start,
+                   const int* __restrict__ chunk_valid, int n_chunks, ClapFrontTables tab,
+                   float* __restrict__ out /*[B,1001,64]*/)
+{
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    float* sm = reinterpret_cast<float*>(cl_smem);
+    Cx<float>* tw = reinterpret_cast<Cx<float>*>(sm);            // 512 complex
+    float* hann = sm + 1024;
+    float* melw = hann + kClFft;
+    float* bns = melw + kClMel * kClMelTaps;
+    float* bnb = bns + kClMel;
+    float* wbuf = bnb + kClMel;                                   // per warp: 512 complex + 516 floats
+    int* mstart = reinterpret_cast<int*>(wbuf + kClWarps * (1024 + 516));
+    int* mcount = mstart + kClMel;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { tw[i].re = tab.twiddle[2 * i]; tw[i].im = tab.twiddle[2 * i + 1]; }
+    for (int i = threadIdx.x; i < kClFft; i += blockDim.x) hann[i] = tab.hann[i];
+    for (int i = threadIdx.x; i < kClMel * kClMelTaps; i += blockDim.x) melw[i] = tab.mel_w[i];
+    for (int i = threadIdx.x; i < kClMel; i += blockDim.x) {
+        mstart[i] = tab.mel_start[i]; mcount[i] = tab.mel_count[i]; bns[i] = tab.bn_scale[i]; bnb[i] = tab.bn_shift[i];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Cx<float>* z = reinterpret_cast<Cx<float>*>(wbuf + warp * (1024 + 516));
+    float* pw = wbuf + warp * (1024 + 516) + 1024;
+
+    float hw[16][2];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) { const int n = 32 * n1 + lane; hw[n1][0] = hann[2 * n]; hw[n1][1] = hann[2 * n + 1]; }
+    Cx<float> tw1[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+        const int m = 2 * lane * k1;                              // W_512^(lane k1) = W_1024^(2 lane k1)
+        const Cx<float> w = tw[m & 511];
+        tw1[k1] = (m & 512) ? Cx<float>{-w.re, -w.im} : w;
+    }
+    Cx<float> tw2[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) { const int h = 16 >> s; tw2[s] = tw[(lane & (h - 1)) * (512 / h)]; }
+    const int rev = __brev((unsigned)lane) >> 27;
+
+    const long long total = (long long)n_chunks * kClFrames;
+    for (long long g = (long long)blockIdx.x * kClWarps + warp; g < total; g += (long long)gridDim.x * kClWarps) {
+        const int c = (int)(g / kClFrames), f = (int)(g % kClFrames);
+        const int16_t* src = pcm + chunk_start[c];
+        const int valid = chunk_valid[c];
+        Cx<float> a[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int n = 32 * n1 + lane;
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int i = f * kClHop - kClFft / 2 + 2 * n + e;      // centre=True: frame starts 512 before f*hop
+                if (i < 0) i = -i;                                // reflect padding of the zero-padded window
+                if (i >= kClChunk) i = 2 * (kClChunk - 1) - i;
+                v[e] = i < valid ? tab.pcm_lut[(int)src[i] + 32768] : 0.0f;
+            }
+            a[n1].re = v[0] * hw[n1][0];
+            a[n1].im = v[1] * hw[n1][1];
+        }
+        fft16(a);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) a[k1] = cmul(a[k1], tw1[k1]);
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int h = 16 >> s;
+            const bool upper = (lane & h) != 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                Cx<float> p = {shfl_xor_t(a[r].re, h), shfl_xor_t(a[r].im, h)};
+                a[r] = upper ? cmul(csub(p, a[r]), tw2[s]) : cadd(a[r], p);
+            }
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) z[k1 + 16 * rev] = a[k1];
+        __syncwarp();
+        for (int k = lane; k <= 256; k += 32) {
+            const Cx<float> x = z[k], y = z[(512 - k) & 511];
+            const float er = 0.5f * (x.re + y.re), ei = 0.5f * (x.im - y.im);
+            const float orr = 0.5f * (x.im + y.im), oi = -0.5f * (x.re - y.re);
+            const Cx<float> w = tw[k & 511];
+            const float pr = orr * w.re - oi * w.im, pi = orr * w.im + oi * w.re;
+            const float xr = er + pr, xi = ei + pi, yr = er - pr, yi = ei - pi;
+            pw[k] = xr * xr + xi * xi;                             // power spectrum
+            pw[512 - k] = yr * yr + yi * yi;
+        }
+        __syncwarp();
+        float* dst = out + g * kClMel;
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const int b = hsel ? 63 - lane : lane;
+            const int st = mstart[b], cnt = mcount[b];
+            float acc = 0.f;
+            for (int i = 0; i < cnt; ++i) acc = fmaf(pw[st + i], melw[b * kClMelTaps + i], acc);
+            const float lm = 10.0f * log10f(fmaxf(acc, 1e-10f));
+            dst[b] = lm * bns[b] + bnb[b];
+        }
+        __syncwarp();
+    }
+}
+
+// cubic convolution coefficients (A = -0.75, as torch's upsample_bicubic2d)
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+    const float A = -0.75f;
+    float x = t + 1.0f; c[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+    x = t;              c[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+    x = 1.0f - t;       c[2] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+    x = 2.0f - t;       c[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+
+// one warp per token (patch).  lm: [B,1001,64] (already BatchNorm-ed); w: [96][16]; x out: [B,4096,96]
+__global__ void __launch_bounds__(256)
+clap_patch_embed_kernel(const float* __restrict__ lm, const float* __restrict__ w, const float* __restrict__ bias,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int n_chunks,
+                        float* __restrict__ x)
+{
+    const int lane = threadIdx.x & 31;
+    const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tok >= (long long)n_chunks * 4096) return;
+    const int b = (int)(tok >> 12), p = (int)(tok & 4095);
+    const int ph = p >> 6, pwid = p & 63;                          // image row block / col block
+    const int j = ph >> 4, f0 = (ph & 15) * 4;                     // time block, first mel bin
+    // lanes 0..15: pixel (r = lane / 4 -> mel f0 + r, c = lane % 4 -> time)
+    float pix = 0.f;
+    if (lane < 16) {
+        const int r = lane >> 2, c = lane & 3;
+        const int t = j * 256 + pwid * 4 + c;                      // 0..1023 on the resized time axis
+        const float s = (float)t * (float)(kClFrames - 1) / 1023.0f;     // align_corners=True
+        const int i0 = (int)floorf(s);
+        float cf[4];
+        cubic_coeffs(s - (float)i0, cf);
+        const float* col = lm + (size_t)b * kClFrames * kClMel + f0 + r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int ti = i0 - 1 + k;
+            ti = ti < 0 ? 0 : (ti > kClFrames - 1 ? kClFrames - 1 : ti);
+            pix = fmaf(cf[k], col[(size_t)ti * kClMel], pix);
+        }
+    }
+    float o[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) o[u] = bias[lane + 32 * u];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const float v = __shfl_sync(0xffffffffu, pix, q);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) o[u] = fmaf(w[(lane + 32 * u) * 16 + q], v, o[u]);
+    }
+    float s1 = o[0] + o[1] + o[2];
+    for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+    const float mean = s1 / 96.0f;
+    float s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) { const float dlt = o[u] - mean; s2 += dlt * dlt; }
+    for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    const float rstd = rsqrtf(s2 / 96.0f + 1e-5f);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int ch = lane + 32 * u;
+        x[tok * 96 + ch] = (o[u] - mean) * rstd * gamma[ch] + beta[ch];
+    }
+}
+
+// token index (b*res*res + y*res + x) of window-ordered row o
+__device__ __forceinline__ long long window_row_to_token(long long o, int res, int shift) {
+    const int nw = res >> 3;
+    const int in = (int)(o & 63);
+    long long wi = o >> 6;
+    const int wx = (int)(wi % nw); wi /= nw;
+    const int wy = (int)(wi % nw);
+    const long long b = wi / nw;
+    int y = wy * 8 + (in >> 3) + shift, xx = wx * 8 + (in & 7) + shift;
+    if (y >= res) y -= res;
+    if (xx >= res) xx -= res;
+    return (b * res + y) * res + xx;
+}
+
+// mode 0: rows in (shifted-)window order; mode 1: patch-merge gather (output row = (b, i, j) on the
+// res/2 grid, features = [x(2i,2j), x(2i+1,2j), x(2i,2j+1), x(2i+1,2j+1)], LayerNorm over 4C).
+// One warp per output row.  out: fp16 [rows, ld_out] (columns >= width zero filled).
+__global__ void __launch_bounds__(256)
+clap_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+               long long n_rows, int C, int ld_out, int res, int shift, int mode, __half* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long o = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (o >= n_rows) return;
+    const int width = mode ? 4 * C : C;
+    const float* src[4];
+    if (mode == 0) {
+        src[0] = x + window_row_to_token(o, res, shift) * C;
+    } else {
+        const int half = res >> 1;
+        const int jx = (int)(o % half);
+        const int iy = (int)((o / half) % half);
+        const long long b = o / ((long long)half * half);
+        const float* base = x + ((b * res + 2 * iy) * res + 2 * jx) * C;
+        src[0] = base; src[1] = base + (size_t)res * C; src[2] = base + C; src[3] = base + (size_t)res * C + C;
+    }
+    auto load = [&](int i) -> float { return mode ? src[i / C][i % C] : src[0][i]; };
+    float s1 = 0.f;
+    for (int i = lane; i < width; i += 32) s1 += load(i);
+    for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+    const float mean = s1 / (float)width;
+    float s2 = 0.f;
+    for (int i = lane; i < width; i += 32) { const float dlt = load(i) - mean; s2 += dlt * dlt; }   // L1-resident re-read
+    for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    const float rstd = rsqrtf(s2 / (float)width + 1e-5f);
+    __half* dst = out + o * ld_out;
+    for (int i = lane; i < ld_out; i += 32)
+        dst[i] = i < width ? __float2half_rn((load(i) - mean) * rstd * gamma[i] + beta[i]) : __float2half_rn(0.f);
+}
+
+// x[token(o)][0:C] += y[o][0:C]   (windowed = 1: o is a window-ordered row)
+__global__ void __launch_bounds__(256)
+clap_residual_add_kernel(float* __restrict__ x, const float* __restrict__ y, long long n_rows, int C, int ld_y,
+                         int res, int shift, int windowed)
+{
+    const long long total = n_rows * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long o = e / C;
+        const int c = (int)(e % C);
+        const long long t = windowed ? window_row_to_token(o, res, shift) : o;
+        x[t * C + c] += y[o * ld_y + c];
+    }
+}
+
+// y[o][0:C] -> x[o][0:C]   (patch merging output becomes the new residual stream)
+__global__ void __launch_bounds__(256)
+clap_copy_rows_kernel(float* __restrict__ x, const float* __restrict__ y, long long n_rows, int C, int ld_y)
+{
+    const long long total = n_rows * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x)
+        x[e] = y[(e / C) * ld_y + (e % C)];
+}
+
+// One warp per (window, head).  qkv: fp16 [rows, ld] with q | k | v at column offsets 0, C, 2C and
+// head h at h*24.  relbias: fp32 [heads][64][64].  out: fp16 [rows, ld_out] (head h at h*24).
+constexpr int kAttWarps = 3;
+__global__ void __launch_bounds__(kAttWarps * 32)
+clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int heads,
+                             const float* __restrict__ relbias, int res, int shift, long long n_windows,
+                             __half* __restrict__ out, int ld_out)
+{
+    __shared__ float Ks[kAttWarps][64][24];
+    __shared__ float Vs[kAttWarps][64][24];
+    __shared__ int rid[kAttWarps][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long units = n_windows * heads;
+    const int nw = res >> 3;
+    const float scale = 0.20412414523193151f;                      // 1 / sqrt(24)
+    for (long long u = (long long)blockIdx.x * kAttWarps + warp; u < units; u += (long long)gridDim.x * kAttWarps) {
+        const long long win = u / heads;
+        const int h = (int)(u % heads);
+        const __half* base = qkv + win * 64 * ld + h * 24;
+        for (int i = lane; i < 64 * 24; i += 32) {
+            const int r = i / 24, d = i % 24;
+            Ks[warp][r][d] = __half2float(base[(size_t)r * ld + C + d]);
+            Vs[warp][r][d] = __half2float(base[(size_t)r * ld + 2 * C + d]);
+        }
+        if (shift) {
+            const int wx = (int)(win % nw), wy = (int)((win / nw) % nw);
+            for (int i = lane; i < 64; i += 32) {
+                const int y = wy * 8 + (i >> 3), xx = wx * 8 + (i & 7);   // coordinates in the SHIFTED image
+                const int ry = y < res - 8 ? 0 : (y < res - shift ? 1 : 2);
+                const int rx = xx < res - 8 ? 0 : (xx < res - shift ? 1 : 2);
+                rid[warp][i] = ry * 3 + rx;
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+            const int i = lane + 32 * rr;
+            float q[24];
+#pragma unroll
+            for (int d = 0; d < 24; ++d) q[d] = __half2float(base[(size_t)i * ld + d]) * scale;
+            const float* bias = relbias + ((size_t)h * 64 + i) * 64;
+            const int my = shift ? rid[warp][i] : 0;
+            float s[64];
+            float mx = -3.0e38f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                float acc = bias[j];
+#pragma unroll
+                for (int d = 0; d < 24; ++d) acc = fmaf(q[d], Ks[warp][j][d], acc);
+                if (shift && rid[warp][j] != my) acc += -100.0f;
+                s[j] = acc;
+                mx = fmaxf(mx, acc);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
+            const float inv = 1.0f / sum;
+            float o[24];
+#pragma unroll
+            for (int d = 0; d < 24; ++d) o[d] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float pj = s[j] * inv;
+#pragma unroll
+                for (int d = 0; d < 24; ++d) o[d] = fmaf(pj, Vs[warp][j][d], o[d]);
+            }
+            __half* dst = out + (win * 64 + i) * ld_out + h * 24;
+#pragma unroll
+            for (int d = 0; d < 24; d += 2) *reinterpret_cast<__half2*>(dst + d) = __floats2half2_rn(o[d], o[d + 1]);
+            if (h == 0)                                         // keep the GEMM's K padding columns at zero
+                for (int cpad = C; cpad < ld_out; ++cpad) out[(win * 64 + i) * ld_out + cpad] = __float2half_rn(0.f);
+        }
+        __syncwarp();
+    }
+}
+
+// one block (256 threads) per chunk: LayerNorm(768) of the 64 tokens, mean over tokens,
+// 768 -> 512 ReLU -> 512, L2 normalise, fp16 out [B, 512]
+__global__ void __launch_bounds__(256)
+clap_head_kernel(const float* __restrict__ x /*[B,64,768]*/, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ w2, const float* __restrict__ b2, __half* __restrict__ out)
+{
+    __shared__ float pooled[768];
+    __shared__ float part[8][768];                                 // per-warp partial means (fixed-order reduce)
+    __shared__ float h1[512];
+    __shared__ float h2[512];
+    __shared__ float red[8];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc_tok[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) acc_tok[k] = 0.f;
+    for (int t = warp; t < 64; t += 8) {
+        const float* row = x + ((size_t)b * 64 + t) * 768;
+        float v[24];
+        float s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 24; ++k) { v[k] = row[lane + 32 * k]; s1 += v[k]; }
+        for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        const float mean = s1 / 768.0f;
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 24; ++k) { const float dlt = v[k] - mean; s2 += dlt * dlt; }
+        for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+        const float rstd = rsqrtf(s2 / 768.0f + 1e-5f);
+#pragma unroll
+        for (int k = 0; k < 24; ++k) {
+            const int c = lane + 32 * k;
+            acc_tok[k] += (v[k] - mean) * rstd * gamma[c] + beta[c];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 24; ++k) part[warp][lane + 32 * k] = acc_tok[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) sacc += part[wv][i];
+        pooled[i] = sacc * (1.0f / 64.0f);
+    }
+    __syncthreads();
+    for (int o = warp; o < 512; o += 8) {
+        float acc = 0.f;
+        for (int k = lane; k < 768; k += 32) acc = fmaf(w1[(size_t)o * 768 + k], pooled[k], acc);
+        for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (lane == 0) h1[o] = fmaxf(acc + b1[o], 0.f);
+    }
+    __syncthreads();
+    float sq = 0.f;
+    for (int o = warp; o < 512; o += 8) {
+        float acc = 0.f;
+        for (int k = lane; k < 512; k += 32) acc = fmaf(w2[(size_t)o * 512 + k], h1[k], acc);
+        for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (lane == 0) { h2[o] = acc + b2[o]; sq += h2[o] * h2[o]; }
+    }
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+    for (int k = 0; k < 8; ++k) tot += red[k];
+    const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);            // F.normalize eps
+    for (int i = threadIdx.x; i < 512; i += 256) out[(size_t)b * 512 + i] = __float2half_rn(h2[i] * inv);
+}
+
+}  // namespace fad

@@ -39,9 +39,9 @@ struct ConvGemmParams {
     int img_groups;            // ceil(NB / box_n)
     int n_tiles;               // Cout / N_TILE
     int H, W, NB, Cout;
-    int relu, pool;
+    int relu, pool;            // relu: 0 = none, 1 = ReLU, 2 = GELU (erf form)
     const float* bias;         // [Cout]
-    __half* out;               // NHWC fp16 [NB, H(/2), W(/2), Cout]
+    __half* out;               // NHWC fp16 [NB, H(/2), W(/2), Cout]; may be null when out_f32 is set
     float* out_f32;            // optional fp32 copy of the un-pooled output (may be null)
 };
 
@@ -241,9 +241,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     f[4 * j + 2] = acc[g * 32 + 4 * j + 2] + b.z;
                     f[4 * j + 3] = acc[g * 32 + 4 * j + 3] + b.w;
                 }
-                if (p.relu) {
+                if (p.relu == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                } else if (p.relu == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
                 }
                 uint32_t h2[16];
 #pragma unroll
@@ -252,10 +255,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 if (!p.pool) {
                     if (valid) {
                         const size_t pix = (size_t(n) * p.H + h) * p.W + w;
-                        uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + g * 32);
+                        if (p.out) {
+                            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + g * 32);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j)
+                                dst[j] = make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+                        }
                         if (p.out_f32) {
                             float4* d32 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + ch0 + g * 32);
 #pragma unroll

@@ -15,6 +15,7 @@
 #include "frontend.cuh"
 #include "stats.cuh"
 #include "frechet.cuh"
+#include "clap.cuh"
 
 namespace {
 
@@ -132,6 +133,8 @@ struct fad_handle {
     double* fr_buf = nullptr;
     size_t fr_cap = 0;
     double* fr_scal = nullptr;   // 32 doubles
+
+    void* clap_state = nullptr;  // ClapState (clap_host.inc)
 
     // optional per-category timing with CUDA events recorded on the launching stream
     bool prof_on = false;
@@ -329,9 +332,12 @@ int fad_create(int device, int max_examples, fad_handle** out) {
     return 0;
 }
 
+static void clap_free_state(void* p);
+
 int fad_destroy(fad_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    clap_free_state(h->clap_state);
     void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
                     h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -625,47 +631,81 @@ int newton_schulz(fad_handle* h, const double* A, int d, int iters, double* Y, d
 }
 }  // namespace
 
-int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const double* mu2,
-                const double* cov2, int d, int iters, double* out, void* stream) {
+// S = C^(1/2) and tr C of a baseline covariance, computed once and reused for every eval set
+// (FAD-inf steps, per-song scores).  sqrt_out: d*d doubles, scal_out: 2 doubles (|C|_F, tr C), device.
+int fad_sqrt_psd(fad_handle* h, const double* cov, int d, int iters, double* sqrt_out, double* scal_out,
+                 void* stream) {
     if (!h) return fail("null handle");
     if (d <= 0) return fail("bad dimension");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (iters <= 0) iters = 60;
     const size_t total = (size_t)d * d;
-    // buffers: Y Z W T(2) S M P  -> 8 matrices
     if (ensure((void**)&h->fr_buf, &h->fr_cap, 8 * total * 8)) return 1;
-    double* Y = h->fr_buf;           double* Z = Y + total;   double* W = Z + total;
-    double* T = W + total;           /* T uses 2 matrices */  double* S = T + 2 * total;
-    double* M = S + total;           double* P = M + total;
-    double* scalA = h->fr_scal;      double* scalB = scalA + 2;  double* scalM = scalA + 4;
-    double* trY = scalA + 6;         double* resid = scalA + 7;  double* trS = scalA + 8;
-    double* trZ = scalA + 9;         double* trZs = scalA + 10;
+    double* Y = h->fr_buf;  double* Z = Y + total;  double* W = Z + total;  double* T = W + total;
+    double* scalA = h->fr_scal;  double* trS = scalA + 8;  double* trZs = scalA + 10;
     float* devf = reinterpret_cast<float*>(scalA + 16);
     unsigned eb = (unsigned)((total + 255) / 256);
     if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
+    const size_t ev = prof_begin(h, st);
+    if (newton_schulz(h, cov, d, iters, Y, Z, W, T, scalA, trS, trZs, devf, st)) return 1;
+    fad::ns_unscale_kernel<<<eb, 256, 0, st>>>(Y, d, scalA, sqrt_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(scal_out, scalA, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    h->launches++;
+    prof_end(h, FAD_PROF_FRECHET, ev, st);
+    return 0;
+}
 
+// FAD against a baseline given by (mu1, S1 = C1^(1/2), scal1 = {|C1|_F, tr C1}).
+int fad_frechet_presqrt(fad_handle* h, const double* mu1, const double* sqrt1, const double* scal1,
+                        const double* mu2, const double* cov2, int d, int iters, double* out, void* stream) {
+    if (!h) return fail("null handle");
+    if (d <= 0) return fail("bad dimension");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iters <= 0) iters = 60;
+    const size_t total = (size_t)d * d;
+    if (ensure((void**)&h->fr_buf, &h->fr_cap, 8 * total * 8)) return 1;
+    double* Y = h->fr_buf;  double* Z = Y + total;  double* W = Z + total;  double* T = W + total;
+    double* M = T + 2 * total;  double* P = h->fr_buf + 7 * total;   // slots: Y Z W T T M S(fad_frechet) P
+    double* scalB = h->fr_scal + 2;  double* scalM = h->fr_scal + 4;
+    double* trY = h->fr_scal + 6;    double* resid = h->fr_scal + 7;  double* trZ = h->fr_scal + 9;
+    float* devf = reinterpret_cast<float*>(h->fr_scal + 16);
+    unsigned eb = (unsigned)((total + 255) / 256);
+    if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
     const size_t ev_fr = prof_begin(h, st);
-    // S = C1^(1/2)
-    if (newton_schulz(h, cov1, d, iters, Y, Z, W, T, scalA, trS, trZs, devf, st)) return 1;
-    fad::ns_unscale_kernel<<<eb, 256, 0, st>>>(Y, d, scalA, S);
-    // M = S C2 S
     fad::norm_trace_kernel<<<1, 256, 0, st>>>(cov2, d, scalB);
     CK(cudaGetLastError());
-    h->launches += 2;
-    if (launch_dgemm(h, S, cov2, P, d, 1.0, 0.0, nullptr, st)) return 1;
-    if (launch_dgemm(h, P, S, M, d, 1.0, 0.0, nullptr, st)) return 1;
-    // tr sqrt(M)
+    h->launches++;
+    if (launch_dgemm(h, sqrt1, cov2, P, d, 1.0, 0.0, nullptr, st)) return 1;     // M = S C2 S
+    if (launch_dgemm(h, P, sqrt1, M, d, 1.0, 0.0, nullptr, st)) return 1;
     if (newton_schulz(h, M, d, iters, Y, Z, W, T, scalM, trY, trZ, devf, st)) return 1;
-    // residual | Y^2 - sym(M)/|M|_F |_F
     CK(cudaMemsetAsync(resid, 0, sizeof(double), st));
     if (launch_dgemm(h, Y, Y, P, d, 1.0, 0.0, nullptr, st)) return 1;
     fad::resid_kernel<<<eb, 256, 0, st>>>(P, M, d, scalM, resid);
-    fad::frechet_assemble_kernel<<<1, 256, 0, st>>>(mu1, mu2, d, scalA, scalB, scalM, trY, trZ, resid, iters, out);
+    fad::frechet_assemble_kernel<<<1, 256, 0, st>>>(mu1, mu2, d, scal1, scalB, scalM, trY, trZ, resid, iters, out);
     CK(cudaGetLastError());
     h->launches += 2;
     prof_end(h, FAD_PROF_FRECHET, ev_fr, st);
     return 0;
 }
 
+int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const double* mu2,
+                const double* cov2, int d, int iters, double* out, void* stream) {
+    if (!h) return fail("null handle");
+    if (d <= 0) return fail("bad dimension");
+    CK(cudaSetDevice(h->device));
+    const size_t total = (size_t)d * d;
+    if (ensure((void**)&h->fr_buf, &h->fr_cap, 8 * total * 8)) return 1;
+    double* S = h->fr_buf + 6 * total;            // scratch slot not used by the chains
+    double* scal1 = h->fr_scal + 12;
+    if (fad_sqrt_psd(h, cov1, d, iters, S, scal1, stream)) return 1;
+    return fad_frechet_presqrt(h, mu1, S, scal1, mu2, cov2, d, iters, out, stream);
+}
+
 }  // extern "C"
+
+#include "clap_host.inc"
+
+static void clap_free_state(void* p) { clap_free(reinterpret_cast<ClapState*>(p)); }

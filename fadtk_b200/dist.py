@@ -34,9 +34,17 @@ def init_from_env(backend: str | None = None) -> bool:
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    td.init_process_group(backend=backend)
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        td.init_process_group(backend=backend, device_id=torch.device("cuda", local))
+    else:
+        td.init_process_group(backend=backend)
     return True
+
+
+def shutdown():
+    if td.is_available() and td.is_initialized():
+        td.destroy_process_group()
 
 
 def shard(items, r: int | None = None, w: int | None = None):

@@ -96,6 +96,23 @@ def calc_frechet_distance(mu1, cov1, mu2, cov2, eps=1e-6):
     return (diff.dot(diff) + tr1 + tr2 - 2 * tr_covmean)
 
 
+def _device_score(baseline, emb_dev, eng, idx_dev=None):
+    """FAD of fp16 device rows (optionally gathered by idx) against a cached Baseline, with the
+    reference's calc_embd_statistics semantics: fp16 mean (np.mean dtype rule, fad.py:48), fp64 cov."""
+    st = DeviceStatistics(emb_dev.shape[1], eng)
+    if idx_dev is None:
+        st.add(emb_dev)
+    else:
+        st.add_gather(emb_dev, idx_dev)
+    mu_d, cov_d = st.finalize()
+    mu_d = mu_d.to(torch.float16).to(torch.float64)
+    out = baseline.frechet(mu_d.contiguous(), cov_d).cpu().numpy()
+    if not np.isfinite(out[1]):
+        raise ValueError("non-finite covariance statistics (NaN/Inf input)")
+    diff = baseline.mu_host - mu_d.cpu().numpy()
+    return float(diff.dot(diff) + out[5] + out[6] - 2 * out[1])
+
+
 class FrechetAudioDistance:
     """Same constructor and methods as fadtk.fad.FrechetAudioDistance (fad.py:123-395)."""
     loaded = False
@@ -252,20 +269,19 @@ class FrechetAudioDistance:
         from . import _native
         eng = _native.engine()
         fp16_rows = embeds.dtype == np.float16
-        emb_dev = torch.from_numpy(np.ascontiguousarray(embeds)).to(eng.torch_device) if fp16_rows else None
+        if fp16_rows:      # baseline sqrt computed once, every bootstrap step stays on the device
+            base = _native.Baseline(eng, mu_base, cov_base)
+            base.mu_host = np.asarray(mu_base, dtype=np.float64)
+            emb_dev = torch.from_numpy(np.ascontiguousarray(embeds)).to(eng.torch_device)
 
         results = []
         for n in ns:
             indices = np.random.choice(embeds.shape[0], size=n, replace=True)
             if fp16_rows:
-                st = DeviceStatistics(embeds.shape[1], eng)
-                st.add_gather(emb_dev, torch.from_numpy(indices).to(eng.torch_device))
-                mu_d, cov_d = st.finalize()
-                mu_eval = mu_d.cpu().numpy().astype(np.float16)      # np.mean dtype quirk, fad.py:48
-                cov_eval = cov_d.cpu().numpy()
+                fad_score = _device_score(base, emb_dev, eng, torch.from_numpy(indices).to(eng.torch_device))
             else:
                 mu_eval, cov_eval = calc_embd_statistics(embeds[indices])
-            fad_score = calc_frechet_distance(mu_base, cov_base, mu_eval, cov_eval)
+                fad_score = calc_frechet_distance(mu_base, cov_base, mu_eval, cov_eval)
             results.append([n, fad_score])
 
         ys = np.array(results)
@@ -285,12 +301,20 @@ class FrechetAudioDistance:
             return csv
 
         mu, cov = self.load_stats(baseline)
+        from . import _native
+        eng = _native.engine()
+        base = _native.Baseline(eng, mu, cov)          # C1^(1/2) once, reused for every song
+        base.mu_host = np.asarray(mu, dtype=np.float64)
 
         def _find_z_helper(f):
             try:
                 embd = self.read_embedding_file(f)
-                mu_eval, cov_eval = calc_embd_statistics(embd)
-                return calc_frechet_distance(mu, cov, mu_eval, cov_eval)
+                if embd.dtype != np.float16:
+                    mu_eval, cov_eval = calc_embd_statistics(embd)
+                    return calc_frechet_distance(mu, cov, mu_eval, cov_eval)
+                assert embd.shape[0] >= 2, (f"FAD requires at least two embedding window frames, you have {embd.shape}."
+                    " (This probably means that your audio is too short)")
+                return _device_score(base, torch.from_numpy(np.ascontiguousarray(embd)).to(eng.torch_device), eng)
             except Exception as e:
                 traceback.print_exc()
                 log.error(f"An error occurred calculating individual FAD using model {self.ml.name} on file {f}")

@@ -154,6 +154,58 @@ class VGGishModel(ModelLoader):
         return list(torch.split(emb, [int(r) for r in rows]))
 
 
+class CLAPLaionModel(ModelLoader):
+    """CLAP from https://github.com/LAION-AI/CLAP, audio branch (HTSAT-tiny), B200-native.
+
+    Same registry name, dimensionality and sample rate as the reference (model_loader.py:296-297).
+    ``type='audio'`` (HTSAT-tiny, 630k-audioset) is implemented; ``'music'`` (HTSAT-base) is not.
+    The reference's per-window loop at batch one (model_loader.py:402-407) becomes one batched
+    launch sequence over all 10-s windows of all clips.
+    """
+
+    def __init__(self, type: str = 'audio', checkpoint=None, seed: int = 0):
+        super().__init__(f"clap-laion-{type}", 512, 48000)
+        self.type = type
+        self.checkpoint = checkpoint
+        self.seed = seed
+        self._engine = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st["model"] = None
+        return st
+
+    def load_model(self):
+        if self.type != 'audio':
+            raise NotImplementedError("clap-laion-music (HTSAT-base) has no sm_100a forward pass yet")
+        from . import _native, weights_clap
+        self._engine = _native.engine()
+        state = weights_clap.load_clap_state(self.checkpoint, self.seed)
+        self._engine.clap_load(weights_clap.pack_clap(state))
+        self.model = self._engine
+        self.device = self._engine.torch_device
+
+    def _get_embedding(self, audio: np.ndarray):
+        return self._embed_flat([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
+
+    def embed_pcm_batch(self, clips):
+        return [t.cpu().numpy() for t in self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])]
+
+    def _embed_flat(self, clips):
+        if self._engine is None:
+            raise RuntimeError("load_model() has not been called")
+        eng = self._engine
+        offsets = np.zeros(len(clips) + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum([len(c) for c in clips])
+        start, valid, rows = eng.clap_plan(offsets)
+        flat = torch.from_numpy(np.concatenate(clips)) if len(clips) > 1 else torch.from_numpy(np.ascontiguousarray(clips[0]))
+        pcm = flat.pin_memory().to(eng.torch_device, non_blocking=True)
+        emb = eng.clap_forward(pcm, torch.from_numpy(start).to(eng.torch_device),
+                               torch.from_numpy(valid).to(eng.torch_device))
+        return list(torch.split(emb, [int(r) for r in rows]))
+
+
 class UnbuiltModel(ModelLoader):
     """Registry entry whose forward pass has no B200-native implementation yet.
 
@@ -178,7 +230,7 @@ def get_all_models() -> list[ModelLoader]:
     """Same names, order and (num_features, sr) as fadtk/model_loader.py:676-701."""
     ms = [
         UnbuiltModel("clap-2023", 1024, 44100),
-        UnbuiltModel("clap-laion-audio", 512, 48000), UnbuiltModel("clap-laion-music", 512, 48000),
+        CLAPLaionModel('audio'), CLAPLaionModel('music'),
         VGGishModel(),
         *[UnbuiltModel("MERT-v1-95M" + ("" if v == 12 else f"-{v}"), 768, 24000) for v in range(1, 13)],
         UnbuiltModel("encodec-emb", 128, 24000), UnbuiltModel("encodec-emb-48k", 128, 48000),

@@ -1,4 +1,4 @@
-"""In-memory hot path: PCM -> VGGish embeddings -> statistics -> Frechet distance, no filesystem.
+"""In-memory hot path: PCM -> embeddings -> statistics -> Frechet distance, no filesystem.
 
 The reference moves everything between stages through files (.wav -> .npy -> mu/cov.npy,
 SURVEY.md section 1).  ``cache_embedding_files`` / ``FrechetAudioDistance`` keep that contract;
@@ -19,27 +19,58 @@ from . import _native, dist
 
 
 class EvalSetFAD:
-    """FAD of equal-length PCM16 clips against fixed baseline statistics."""
+    """FAD of equal-length PCM16 clips against fixed baseline statistics.
+
+    ``model``: "vggish" (16 kHz, 128-d, one row per 0.96 s) or "clap-laion-audio" (48 kHz, 512-d,
+    one row per started second); the engine must already hold that model's weights.
+    """
 
     def __init__(self, engine: _native.Engine, mu_base: torch.Tensor, cov_base: torch.Tensor,
-                 clip_samples: int, clips_per_chunk: int = 1000, mirror_file_means: bool = True):
+                 clip_samples: int, clips_per_chunk: int = 1000, mirror_file_means: bool = True,
+                 model: str = "vggish"):
         self.eng = engine
         self.dev = engine.torch_device
+        self.model = model
         self.mu_base = mu_base.to(self.dev, torch.float64).contiguous()
         self.cov_base = cov_base.to(self.dev, torch.float64).contiguous()
         self.clip_samples = int(clip_samples)
         self.clips_per_chunk = int(clips_per_chunk)
-        self.rows_per_clip = int(_native.lib().fad_vggish_num_examples(self.clip_samples))
+        if model == "vggish":
+            self.d = 128
+            self.rows_per_clip = int(_native.lib().fad_vggish_num_examples(self.clip_samples))
+        elif model == "clap-laion-audio":
+            self.d = 512
+            self.rows_per_clip = -(-self.clip_samples // 48000)
+        else:
+            raise ValueError(model)
         self.mirror = mirror_file_means
-        self.d = 128
         self.shift = None
         self._copy_stream = torch.cuda.Stream(device=self.dev)
         self._staging = None
+        self._plans = {}
 
-    def _plan(self, n_clips: int) -> torch.Tensor:
-        off = np.arange(n_clips + 1, dtype=np.int64) * self.clip_samples
-        ex, _ = self.eng.vggish_plan(off)
-        return torch.from_numpy(ex).to(self.dev, non_blocking=True)
+    def _plan(self, n_clips: int):
+        if n_clips not in self._plans:
+            off = np.arange(n_clips + 1, dtype=np.int64) * self.clip_samples
+            if self.model == "vggish":
+                ex, _ = self.eng.vggish_plan(off)
+                self._plans[n_clips] = (torch.from_numpy(ex).to(self.dev),)
+            else:
+                start, valid, _ = self.eng.clap_plan(off)
+                self._plans[n_clips] = (torch.from_numpy(start).to(self.dev), torch.from_numpy(valid).to(self.dev))
+        return self._plans[n_clips]
+
+    def embed(self, pcm_dev: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """int16 [n_clips, clip_samples] (device) -> fp16 [n_clips * rows_per_clip, d]"""
+        plan = self._plan(pcm_dev.shape[0])
+        flat = pcm_dev.reshape(-1)
+        if self.model == "vggish":
+            return self.eng.vggish_forward(flat, plan[0], out)
+        emb = self.eng.clap_forward(flat, plan[0], plan[1])
+        if out is not None:
+            out.copy_(emb)
+            return out
+        return emb
 
     def _shared_shift(self, emb: torch.Tensor) -> torch.Tensor:
         if self.shift is None:
@@ -50,7 +81,7 @@ class EvalSetFAD:
             self.shift = s.to(torch.float16)
         return self.shift
 
-    def _score(self, emb: torch.Tensor) -> torch.Tensor:
+    def score(self, emb: torch.Tensor) -> torch.Tensor:
         """fp16 [n_clips * rows_per_clip, d] (this rank's shard) -> fp64[8] (device)."""
         d, r = self.d, self.rows_per_clip
         shift = self._shared_shift(emb)
@@ -86,8 +117,14 @@ class EvalSetFAD:
     def run_device(self, pcm_dev: torch.Tensor) -> torch.Tensor:
         """pcm_dev int16 [n_clips, clip_samples] resident in HBM -> fp64[8] result (device)."""
         n_clips = pcm_dev.shape[0]
-        emb = self.eng.vggish_forward(pcm_dev.reshape(-1), self._plan(n_clips))
-        return self._score(emb)
+        cpc = min(self.clips_per_chunk, n_clips)
+        if cpc == n_clips:
+            return self.score(self.embed(pcm_dev))
+        emb_all = torch.empty((n_clips * self.rows_per_clip, self.d), dtype=torch.float16, device=self.dev)
+        for s in range(0, n_clips, cpc):
+            c = min(cpc, n_clips - s)
+            self.embed(pcm_dev[s:s + c], emb_all[s * self.rows_per_clip:(s + c) * self.rows_per_clip])
+        return self.score(emb_all)
 
     def run_host(self, pcm_host: torch.Tensor) -> float:
         """pcm_host: PINNED int16 [n_clips, clip_samples].  H2D copies (double-buffered on a copy
@@ -101,7 +138,6 @@ class EvalSetFAD:
             self._ready = [torch.cuda.Event() for _ in range(2)]
             self._free = [torch.cuda.Event() for _ in range(2)]
         main = torch.cuda.current_stream(self.dev)
-        ex_chunk = self._plan(cpc)
         emb_all = torch.empty((n_clips * self.rows_per_clip, self.d), dtype=torch.float16, device=self.dev)
         for i, s in enumerate(range(0, n_clips, cpc)):
             b = i & 1
@@ -112,8 +148,6 @@ class EvalSetFAD:
                 self._staging[b][:c].copy_(pcm_host[s:s + c], non_blocking=True)
                 self._ready[b].record(self._copy_stream)
             main.wait_event(self._ready[b])
-            ex = ex_chunk if c == cpc else self._plan(c)
-            out = emb_all[s * self.rows_per_clip:(s + c) * self.rows_per_clip]
-            self.eng.vggish_forward(self._staging[b][:c].reshape(-1), ex, out)
+            self.embed(self._staging[b][:c], emb_all[s * self.rows_per_clip:(s + c) * self.rows_per_clip])
             self._free[b].record(main)
-        return float(self._score(emb_all)[0].item())
+        return float(self.score(emb_all)[0].item())

@@ -82,6 +82,27 @@ int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int C
                    int split_w /* weights are [2*Cout, K] hi/lo tiles */,
                    void* out_f16, float* out_f32_or_null, void* stream);
 
+/* ---- CLAP-LAION audio embedder (HTSAT-tiny): replaces CLAPLaionModel.load_model/_get_embedding
+ * (fadtk/model_loader.py:382-418 -> laion_clap.CLAP_Module + torchlibrosa front-end).
+ * tensors_host: 180 host pointers in the order documented at the top of csrc/clap_host.inc
+ * (produced by fadtk_b200/weights_clap.py).  max_chunks bounds the 10-s windows per internal batch
+ * (~12 MB of workspace each). */
+int fad_clap_load(fad_handle* h, const void* const* tensors_host, int n_tensors, int max_chunks);
+
+/* Windows of a clip: one every 48 000 samples (range(0, T, sr), model_loader.py:396-398), each
+ * covering up to 480 000 samples and zero padded.  Returns the number of windows; fills
+ * chunk_start_host (sample offset into the flat PCM buffer) and chunk_valid_host (samples available). */
+long long fad_clap_plan(const long long* clip_offsets_host, long long n_clips, long long* chunk_start_host,
+                        int* chunk_valid_host, long long capacity, long long* rows_per_clip_host);
+
+/* pcm: int16 mono 48 kHz (device); chunk_start int64 / chunk_valid int32 [n_chunks] (device).
+ * emb_out: fp16 [n_chunks, 512], L2-normalised - what the reference caches as .npy. */
+int fad_clap_forward(fad_handle* h, const int16_t* pcm, const long long* chunk_start, const int* chunk_valid,
+                     long long n_chunks, void* emb_out_f16, void* stream);
+/* stage entry point: BatchNorm-ed log-mel [n_chunks, 1001, 64] fp32 */
+int fad_clap_logmel(fad_handle* h, const int16_t* pcm, const long long* chunk_start, const int* chunk_valid,
+                    long long n_chunks, float* out, void* stream);
+
 /* ---- statistics: replaces calc_embd_statistics (fadtk/fad.py:42-48) and
  * _process_file / calculate_embd_statistics_online (fadtk/utils.py:13-46) ----------------
  * Packed fp64 accumulator of length fad_stats_acc_len(d):
@@ -112,6 +133,13 @@ int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, 
 int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const double* mu2,
                 const double* cov2, int d, int iters, double* out, void* stream);
 
+/* The baseline's square root can be computed once and reused (FAD-inf, per-song scoring):
+ * fad_sqrt_psd -> sqrt_out (d*d doubles) and scal_out (2 doubles: |C|_F, tr C), both device. */
+int fad_sqrt_psd(fad_handle* h, const double* cov, int d, int iters, double* sqrt_out, double* scal_out,
+                 void* stream);
+int fad_frechet_presqrt(fad_handle* h, const double* mu1, const double* sqrt1, const double* scal1,
+                        const double* mu2, const double* cov2, int d, int iters, double* out, void* stream);
+
 /* ---- measurement ----------------------------------------------------------------------
  * When enabled, CUDA events are recorded on the launching stream around every kernel group;
  * fad_profile_collect synchronises the device and returns accumulated milliseconds and launch
@@ -122,7 +150,11 @@ int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const doub
 #define FAD_PROF_STATS        10
 #define FAD_PROF_STATS_REDUCE 11
 #define FAD_PROF_FRECHET      12
-#define FAD_PROF_CATEGORIES   16
+#define FAD_PROF_CLAP_FRONT   13   /* log-mel + patch embedding */
+#define FAD_PROF_CLAP_GEMM    14   /* tcgen05 GEMMs of the Swin blocks */
+#define FAD_PROF_CLAP_ATTN    15   /* window attention */
+#define FAD_PROF_CLAP_OTHER   16   /* LayerNorm, residual adds, head */
+#define FAD_PROF_CATEGORIES   20
 int fad_profile_enable(fad_handle* h, int on);
 int fad_profile_collect(fad_handle* h, double* ms_out, long long* count_out, int reset);
 
