@@ -45,8 +45,9 @@ SIGNATURES = {
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_clap_load": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int]),
     "fad_clap_plan": (c_ll, [c_vp, c_ll, c_vp, c_vp, c_ll, c_vp]),
-    "fad_clap_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
-    "fad_clap_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "fad_clap_plan_frames": (c_ll, [c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, c_vp]),
+    "fad_clap_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp]),
+    "fad_clap_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_stats_acc_len": (C.c_size_t, [C.c_int]),
     "fad_stats_accumulate": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
     "fad_stats_accumulate_gather": (C.c_int, [c_vp, c_vp, c_ll, c_vp, c_ll, C.c_int, c_vp, c_vp, c_vp]),
@@ -218,22 +219,46 @@ class Engine:
         lib().fad_clap_plan(off.ctypes.data, n_clips, start.ctypes.data, valid.ctypes.data, n, None)
         return start, valid, rows
 
-    def clap_forward(self, pcm: torch.Tensor, chunk_start: torch.Tensor, chunk_valid: torch.Tensor):
-        """pcm int16 (cuda, 48 kHz); chunk_start int64 / chunk_valid int32 (cuda) -> fp16 [n, 512]."""
-        assert pcm.dtype == torch.int16 and pcm.is_cuda and chunk_start.dtype == torch.int64
-        assert chunk_valid.dtype == torch.int32
-        n = chunk_start.shape[0]
+    @staticmethod
+    def clap_plan_frames(clip_offsets: np.ndarray):
+        """-> dict(pool_start int64, pool_valid int32, pool_frame int32, frame_index int32 [n_chunks,1001],
+        rows_per_clip int64): every distinct STFT frame once + the per-window index table."""
+        off = np.ascontiguousarray(clip_offsets, dtype=np.int64)
+        n_clips = off.shape[0] - 1
+        rows = np.empty(n_clips, dtype=np.int64)
+        n_chunks = lib().fad_clap_plan(off.ctypes.data, n_clips, None, None, 0, rows.ctypes.data)
+        n_pool = lib().fad_clap_plan_frames(off.ctypes.data, n_clips, None, None, None, 0, None)
+        ps = np.empty(n_pool, dtype=np.int64)
+        pv = np.empty(n_pool, dtype=np.int32)
+        pf = np.empty(n_pool, dtype=np.int32)
+        fi = np.empty((n_chunks, 1001), dtype=np.int32)
+        lib().fad_clap_plan_frames(off.ctypes.data, n_clips, ps.ctypes.data, pv.ctypes.data, pf.ctypes.data, n_pool,
+                                   fi.ctypes.data)
+        return {"pool_start": ps, "pool_valid": pv, "pool_frame": pf, "frame_index": fi, "rows_per_clip": rows}
+
+    def clap_plan_to_device(self, plan: dict) -> dict:
+        dev = self.torch_device
+        return {k: (torch.from_numpy(v).to(dev) if k != "rows_per_clip" else v) for k, v in plan.items()}
+
+    def clap_forward(self, pcm: torch.Tensor, plan_dev: dict):
+        """pcm int16 (cuda, 48 kHz); plan_dev from clap_plan_to_device -> fp16 [n_chunks, 512]."""
+        assert pcm.dtype == torch.int16 and pcm.is_cuda
+        fi = plan_dev["frame_index"]
+        n = fi.shape[0]
         out = torch.empty((n, 512), dtype=torch.float16, device=pcm.device)
-        _check(lib().fad_clap_forward(self._h, pcm.data_ptr(), chunk_start.data_ptr(), chunk_valid.data_ptr(), n,
-                                      out.data_ptr(), _stream()))
+        _check(lib().fad_clap_forward(self._h, pcm.data_ptr(), plan_dev["pool_start"].data_ptr(),
+                                      plan_dev["pool_valid"].data_ptr(), plan_dev["pool_frame"].data_ptr(),
+                                      plan_dev["pool_start"].shape[0], fi.data_ptr(), n, out.data_ptr(), _stream()))
         return out
 
-    def clap_logmel(self, pcm, chunk_start, chunk_valid):
-        n = chunk_start.shape[0]
-        out = torch.empty((n, 1001, 64), dtype=torch.float32, device=pcm.device)
-        _check(lib().fad_clap_logmel(self._h, pcm.data_ptr(), chunk_start.data_ptr(), chunk_valid.data_ptr(), n,
-                                     out.data_ptr(), _stream()))
-        return out
+    def clap_logmel(self, pcm, plan_dev: dict):
+        """-> fp32 [n_chunks, 1001, 64] BatchNorm-ed log-mel, gathered from the frame pool."""
+        n_pool = plan_dev["pool_start"].shape[0]
+        pool = torch.empty((n_pool, 64), dtype=torch.float32, device=pcm.device)
+        _check(lib().fad_clap_logmel(self._h, pcm.data_ptr(), plan_dev["pool_start"].data_ptr(),
+                                     plan_dev["pool_valid"].data_ptr(), plan_dev["pool_frame"].data_ptr(), n_pool,
+                                     pool.data_ptr(), _stream()))
+        return pool[plan_dev["frame_index"].long()]
 
     # -------------------------------------------------------------- statistics
     @staticmethod
@@ -282,8 +307,12 @@ class Baseline:
     def __init__(self, eng: "Engine", mu, cov):
         dev = eng.torch_device
         self.eng = eng
-        self.mu = torch.as_tensor(np.ascontiguousarray(mu, dtype=np.float64)).to(dev)
-        cov = torch.as_tensor(np.ascontiguousarray(cov, dtype=np.float64)).to(dev)
+        def to_dev(a):
+            if isinstance(a, torch.Tensor):
+                return a.to(dev, torch.float64).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+        self.mu = to_dev(mu)
+        cov = to_dev(cov)
         self.d = self.mu.shape[0]
         self.sqrt = torch.empty((self.d, self.d), dtype=torch.float64, device=dev)
         self.scal = torch.empty(2, dtype=torch.float64, device=dev)

@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "frontend.cuh"   // Cx, cmul, cadd, csub, mul_neg_i, shfl_xor_t
+#include "conv_gemm.cuh"  // window_row_to_token
 
 namespace fad {
 
@@ -70,10 +71,16 @@ __device__ __forceinline__ void fft16(Cx<float> (&x)[16]) {
         for (int j = i + 1; j < 4; ++j) { t = x[4 * i + j]; x[4 * i + j] = x[4 * j + i]; x[4 * j + i] = t; }
 }
 
+// Frame pool: the reference runs one forward per 10-s window at a 1-s hop (model_loader.py:396-407),
+// so a frame whose 1024 samples lie inside a window (frame index 2..998) is recomputed identically
+// by up to ten windows.  Here every DISTINCT frame is computed once: pool entry p describes
+// (window start sample, valid samples of that window, frame index inside the window); windows then
+// address the pool through an index table.  Edge frames (0, 1, 999, 1000: reflect padding / zero
+// tail) stay per window.  out: [n_pool, 64] BatchNorm-ed log-mel rows.
 __global__ void __launch_bounds__(kClWarps * 32)
-clap_logmel_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ chunk_start,
-                   const int* __restrict__ chunk_valid, int n_chunks, ClapFrontTables tab,
-                   float* __restrict__ out /*[B,1001,64]*/)
+clap_logmel_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ pool_start,
+                   const int* __restrict__ pool_valid, const int* __restrict__ pool_frame, long long n_pool,
+                   ClapFrontTables tab, float* __restrict__ out /*[n_pool,64]*/)
 {
     extern __shared__ __align__(16) unsigned char cl_smem[];
     float* sm = reinterpret_cast<float*>(cl_smem);
@@ -112,11 +119,11 @@ clap_logmel_kernel(const int16_t* __restrict__ pcm, const long long* __restrict_
     for (int s = 0; s < 5; ++s) { const int h = 16 >> s; tw2[s] = tw[(lane & (h - 1)) * (512 / h)]; }
     const int rev = __brev((unsigned)lane) >> 27;
 
-    const long long total = (long long)n_chunks * kClFrames;
+    const long long total = n_pool;
     for (long long g = (long long)blockIdx.x * kClWarps + warp; g < total; g += (long long)gridDim.x * kClWarps) {
-        const int c = (int)(g / kClFrames), f = (int)(g % kClFrames);
-        const int16_t* src = pcm + chunk_start[c];
-        const int valid = chunk_valid[c];
+        const int f = pool_frame[g];
+        const int16_t* src = pcm + pool_start[g];
+        const int valid = pool_valid[g];
         Cx<float> a[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
@@ -182,9 +189,11 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
     x = 2.0f - t;       c[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
 }
 
-// one warp per token (patch).  lm: [B,1001,64] (already BatchNorm-ed); w: [96][16]; x out: [B,4096,96]
+// one warp per token (patch).  lm: frame pool [n_pool,64] (already BatchNorm-ed), addressed through
+// frame_index [B][1001]; w: [96][16]; x out: [B,4096,96]
 __global__ void __launch_bounds__(256)
-clap_patch_embed_kernel(const float* __restrict__ lm, const float* __restrict__ w, const float* __restrict__ bias,
+clap_patch_embed_kernel(const float* __restrict__ lm, const int* __restrict__ frame_index,
+                        const float* __restrict__ w, const float* __restrict__ bias,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int n_chunks,
                         float* __restrict__ x)
 {
@@ -203,12 +212,12 @@ clap_patch_embed_kernel(const float* __restrict__ lm, const float* __restrict__ 
         const int i0 = (int)floorf(s);
         float cf[4];
         cubic_coeffs(s - (float)i0, cf);
-        const float* col = lm + (size_t)b * kClFrames * kClMel + f0 + r;
+        const int* fidx = frame_index + (size_t)b * kClFrames;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int ti = i0 - 1 + k;
             ti = ti < 0 ? 0 : (ti > kClFrames - 1 ? kClFrames - 1 : ti);
-            pix = fmaf(cf[k], col[(size_t)ti * kClMel], pix);
+            pix = fmaf(cf[k], lm[(size_t)fidx[ti] * kClMel + f0 + r], pix);
         }
     }
     float o[3];
@@ -235,23 +244,11 @@ clap_patch_embed_kernel(const float* __restrict__ lm, const float* __restrict__ 
     }
 }
 
-// token index (b*res*res + y*res + x) of window-ordered row o
-__device__ __forceinline__ long long window_row_to_token(long long o, int res, int shift) {
-    const int nw = res >> 3;
-    const int in = (int)(o & 63);
-    long long wi = o >> 6;
-    const int wx = (int)(wi % nw); wi /= nw;
-    const int wy = (int)(wi % nw);
-    const long long b = wi / nw;
-    int y = wy * 8 + (in >> 3) + shift, xx = wx * 8 + (in & 7) + shift;
-    if (y >= res) y -= res;
-    if (xx >= res) xx -= res;
-    return (b * res + y) * res + xx;
-}
-
 // mode 0: rows in (shifted-)window order; mode 1: patch-merge gather (output row = (b, i, j) on the
 // res/2 grid, features = [x(2i,2j), x(2i+1,2j), x(2i,2j+1), x(2i+1,2j+1)], LayerNorm over 4C).
-// One warp per output row.  out: fp16 [rows, ld_out] (columns >= width zero filled).
+// One warp per output row, the row lives in registers (EPL = width / 32 values per lane, read once).
+// out: fp16 [rows, ld_out] (columns >= width zero filled).
+template <int EPL>
 __global__ void __launch_bounds__(256)
 clap_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                long long n_rows, int C, int ld_out, int res, int shift, int mode, __half* __restrict__ out)
@@ -259,30 +256,43 @@ clap_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     const int lane = threadIdx.x & 31;
     const long long o = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (o >= n_rows) return;
-    const int width = mode ? 4 * C : C;
-    const float* src[4];
+    constexpr int width = EPL * 32;
+    float v[EPL];
     if (mode == 0) {
-        src[0] = x + window_row_to_token(o, res, shift) * C;
+        const float* src = x + window_row_to_token(o, res, shift) * C;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) v[k] = src[lane + 32 * k];
     } else {
         const int half = res >> 1;
         const int jx = (int)(o % half);
         const int iy = (int)((o / half) % half);
         const long long b = o / ((long long)half * half);
         const float* base = x + ((b * res + 2 * iy) * res + 2 * jx) * C;
-        src[0] = base; src[1] = base + (size_t)res * C; src[2] = base + C; src[3] = base + (size_t)res * C + C;
+        // concat order x0 | x1 | x2 | x3 = (2i,2j) (2i+1,2j) (2i,2j+1) (2i+1,2j+1); C is a multiple of 32
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int i = lane + 32 * k;
+            const int part = i / C, c = i - part * C;
+            v[k] = base[(size_t)((part & 1) ? res * C : 0) + ((part & 2) ? C : 0) + c];
+        }
     }
-    auto load = [&](int i) -> float { return mode ? src[i / C][i % C] : src[0][i]; };
     float s1 = 0.f;
-    for (int i = lane; i < width; i += 32) s1 += load(i);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) s1 += v[k];
     for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
     const float mean = s1 / (float)width;
     float s2 = 0.f;
-    for (int i = lane; i < width; i += 32) { const float dlt = load(i) - mean; s2 += dlt * dlt; }   // L1-resident re-read
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) { const float dlt = v[k] - mean; s2 += dlt * dlt; }
     for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
     const float rstd = rsqrtf(s2 / (float)width + 1e-5f);
     __half* dst = out + o * ld_out;
-    for (int i = lane; i < ld_out; i += 32)
-        dst[i] = i < width ? __float2half_rn((load(i) - mean) * rstd * gamma[i] + beta[i]) : __float2half_rn(0.f);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        const int i = lane + 32 * k;
+        dst[i] = __float2half_rn((v[k] - mean) * rstd * gamma[i] + beta[i]);
+    }
+    for (int i = width + lane; i < ld_out; i += 32) dst[i] = __float2half_rn(0.f);
 }
 
 // x[token(o)][0:C] += y[o][0:C]   (windowed = 1: o is a window-ordered row)
@@ -310,29 +320,64 @@ clap_copy_rows_kernel(float* __restrict__ x, const float* __restrict__ y, long l
         x[e] = y[(e / C) * ld_y + (e % C)];
 }
 
-// One warp per (window, head).  qkv: fp16 [rows, ld] with q | k | v at column offsets 0, C, 2C and
-// head h at h*24.  relbias: fp32 [heads][64][64].  out: fp16 [rows, ld_out] (head h at h*24).
+// Window attention on the warp-level tensor-core path (mma.sync m16n8k16, fp16 in / fp32 accumulate):
+// a 64 x 64 x 24 problem per (window, head) is far too small for a tcgen05/TMEM tile, but maps
+// exactly onto 16x8x16 fragments.  One warp per (window, head):
+//   S = Q K^T            4 m-tiles x 8 n-tiles x 2 k-steps (head dim 24 zero-padded to 32)
+//   S = S/sqrt(24) + relative-position bias (+ -100 across shift regions); row softmax in registers
+//   O = P V              per m-tile 3 n-tiles x 4 k-steps, P re-used straight from the S accumulators
+// qkv: fp16 [rows, ld] with q | k | v at column offsets 0, C, 2C and head h at h*24.
+// relbias: fp32 [heads][64][64].  out: fp16 [rows, ld_out] (head h at h*24).
 constexpr int kAttWarps = 3;
+constexpr int kQStride = 40;      // halves per Q/K smem row (32 used): conflict-free fragment loads
+constexpr int kVStride = 72;      // halves per V^T smem row (64 keys used)
+
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+    __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(kAttWarps * 32)
 clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int heads,
                              const float* __restrict__ relbias, int res, int shift, long long n_windows,
                              __half* __restrict__ out, int ld_out)
 {
-    __shared__ float Ks[kAttWarps][64][24];
-    __shared__ float Vs[kAttWarps][64][24];
+    __shared__ __align__(16) __half Qs[kAttWarps][64 * kQStride];
+    __shared__ __align__(16) __half Ks[kAttWarps][64 * kQStride];
+    __shared__ __align__(16) __half Vt[kAttWarps][24 * kVStride];
     __shared__ int rid[kAttWarps][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
     const long long units = n_windows * heads;
     const int nw = res >> 3;
     const float scale = 0.20412414523193151f;                      // 1 / sqrt(24)
+    __half* q_s = Qs[warp]; __half* k_s = Ks[warp]; __half* v_t = Vt[warp];
     for (long long u = (long long)blockIdx.x * kAttWarps + warp; u < units; u += (long long)gridDim.x * kAttWarps) {
         const long long win = u / heads;
         const int h = (int)(u % heads);
         const __half* base = qkv + win * 64 * ld + h * 24;
-        for (int i = lane; i < 64 * 24; i += 32) {
-            const int r = i / 24, d = i % 24;
-            Ks[warp][r][d] = __half2float(base[(size_t)r * ld + C + d]);
-            Vs[warp][r][d] = __half2float(base[(size_t)r * ld + 2 * C + d]);
+        // stage Q, K (rows padded with zeros to 32 dims) and V^T
+        for (int i = lane; i < 64 * 16; i += 32) {                 // 16 half2 slots per row
+            const int r = i >> 4, d2 = (i & 15) * 2;
+            uint32_t qv = 0, kv = 0;
+            if (d2 < 24) {
+                qv = *reinterpret_cast<const uint32_t*>(base + (size_t)r * ld + d2);
+                kv = *reinterpret_cast<const uint32_t*>(base + (size_t)r * ld + C + d2);
+            }
+            *reinterpret_cast<uint32_t*>(q_s + r * kQStride + d2) = qv;
+            *reinterpret_cast<uint32_t*>(k_s + r * kQStride + d2) = kv;
+        }
+        for (int i = lane; i < 64 * 12; i += 32) {
+            const int r = i / 12, d2 = (i % 12) * 2;
+            const __half2 vv = *reinterpret_cast<const __half2*>(base + (size_t)r * ld + 2 * C + d2);
+            v_t[d2 * kVStride + r] = __low2half(vv);
+            v_t[(d2 + 1) * kVStride + r] = __high2half(vv);
         }
         if (shift) {
             const int wx = (int)(win % nw), wy = (int)((win / nw) % nw);
@@ -344,43 +389,89 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
             }
         }
         __syncwarp();
+        const float* bias_h = relbias + (size_t)h * 64 * 64;
 #pragma unroll 1
-        for (int rr = 0; rr < 2; ++rr) {
-            const int i = lane + 32 * rr;
-            float q[24];
+        for (int mt = 0; mt < 4; ++mt) {
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            float sacc[8][4];
 #pragma unroll
-            for (int d = 0; d < 24; ++d) q[d] = __half2float(base[(size_t)i * ld + d]) * scale;
-            const float* bias = relbias + ((size_t)h * 64 + i) * 64;
-            const int my = shift ? rid[warp][i] : 0;
-            float s[64];
-            float mx = -3.0e38f;
+            for (int j = 0; j < 8; ++j) { sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f; }
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                float acc = bias[j];
+            for (int ks = 0; ks < 2; ++ks) {
+                const int k0 = ks * 16 + 2 * t;
+                const uint32_t a0 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kQStride + k0);
+                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kQStride + k0);
+                const uint32_t a2 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kQStride + k0 + 8);
+                const uint32_t a3 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kQStride + k0 + 8);
 #pragma unroll
-                for (int d = 0; d < 24; ++d) acc = fmaf(q[d], Ks[warp][j][d], acc);
-                if (shift && rid[warp][j] != my) acc += -100.0f;
-                s[j] = acc;
-                mx = fmaxf(mx, acc);
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(k_s + (j * 8 + g) * kQStride + k0);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(k_s + (j * 8 + g) * kQStride + k0 + 8);
+                    mma_m16n8k16(sacc[j], a0, a1, a2, a3, b0, b1);
+                }
             }
-            float sum = 0.f;
+            // scale + bias + mask, row max
+            const int id0 = shift ? rid[warp][r0] : 0, id1 = shift ? rid[warp][r1] : 0;
+            float mx0 = -3.0e38f, mx1 = -3.0e38f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
-            const float inv = 1.0f / sum;
-            float o[24];
-#pragma unroll
-            for (int d = 0; d < 24; ++d) o[d] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const float pj = s[j] * inv;
-#pragma unroll
-                for (int d = 0; d < 24; ++d) o[d] = fmaf(pj, Vs[warp][j][d], o[d]);
+            for (int j = 0; j < 8; ++j) {
+                const int c = j * 8 + 2 * t;
+                const float2 b0v = *reinterpret_cast<const float2*>(bias_h + r0 * 64 + c);
+                const float2 b1v = *reinterpret_cast<const float2*>(bias_h + r1 * 64 + c);
+                sacc[j][0] = sacc[j][0] * scale + b0v.x; sacc[j][1] = sacc[j][1] * scale + b0v.y;
+                sacc[j][2] = sacc[j][2] * scale + b1v.x; sacc[j][3] = sacc[j][3] * scale + b1v.y;
+                if (shift) {
+                    const int ic0 = rid[warp][c], ic1 = rid[warp][c + 1];
+                    if (ic0 != id0) sacc[j][0] -= 100.0f;
+                    if (ic1 != id0) sacc[j][1] -= 100.0f;
+                    if (ic0 != id1) sacc[j][2] -= 100.0f;
+                    if (ic1 != id1) sacc[j][3] -= 100.0f;
+                }
+                mx0 = fmaxf(mx0, fmaxf(sacc[j][0], sacc[j][1]));
+                mx1 = fmaxf(mx1, fmaxf(sacc[j][2], sacc[j][3]));
             }
-            __half* dst = out + (win * 64 + i) * ld_out + h * 24;
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-            for (int d = 0; d < 24; d += 2) *reinterpret_cast<__half2*>(dst + d) = __floats2half2_rn(o[d], o[d + 1]);
-            if (h == 0)                                         // keep the GEMM's K padding columns at zero
-                for (int cpad = C; cpad < ld_out; ++cpad) out[(win * 64 + i) * ld_out + cpad] = __float2half_rn(0.f);
+            for (int j = 0; j < 8; ++j) {
+                sacc[j][0] = __expf(sacc[j][0] - mx0); sacc[j][1] = __expf(sacc[j][1] - mx0);
+                sacc[j][2] = __expf(sacc[j][2] - mx1); sacc[j][3] = __expf(sacc[j][3] - mx1);
+                sum0 += sacc[j][0] + sacc[j][1];
+                sum1 += sacc[j][2] + sacc[j][3];
+            }
+            sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+            sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+            const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+            // O = P V : P fragments come straight from the (normalised) S accumulators
+            float oacc[3][4];
+#pragma unroll
+            for (int n = 0; n < 3; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t a0 = pack_h2(sacc[2 * kk][0] * inv0, sacc[2 * kk][1] * inv0);
+                const uint32_t a1 = pack_h2(sacc[2 * kk][2] * inv1, sacc[2 * kk][3] * inv1);
+                const uint32_t a2 = pack_h2(sacc[2 * kk + 1][0] * inv0, sacc[2 * kk + 1][1] * inv0);
+                const uint32_t a3 = pack_h2(sacc[2 * kk + 1][2] * inv1, sacc[2 * kk + 1][3] * inv1);
+#pragma unroll
+                for (int n = 0; n < 3; ++n) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(v_t + (n * 8 + g) * kVStride + kk * 16 + 2 * t);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(v_t + (n * 8 + g) * kVStride + kk * 16 + 2 * t + 8);
+                    mma_m16n8k16(oacc[n], a0, a1, a2, a3, b0, b1);
+                }
+            }
+            __half* d0 = out + (win * 64 + r0) * ld_out + h * 24;
+            __half* d1 = out + (win * 64 + r1) * ld_out + h * 24;
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                *reinterpret_cast<uint32_t*>(d0 + n * 8 + 2 * t) = pack_h2(oacc[n][0], oacc[n][1]);
+                *reinterpret_cast<uint32_t*>(d1 + n * 8 + 2 * t) = pack_h2(oacc[n][2], oacc[n][3]);
+            }
+            if (h == 0 && t == 0)                                   // keep the GEMM's K padding columns at zero
+                for (int cpad = C; cpad < ld_out; ++cpad) {
+                    out[(win * 64 + r0) * ld_out + cpad] = __float2half_rn(0.f);
+                    out[(win * 64 + r1) * ld_out + cpad] = __float2half_rn(0.f);
+                }
         }
         __syncwarp();
     }

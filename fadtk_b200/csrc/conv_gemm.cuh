@@ -43,7 +43,25 @@ struct ConvGemmParams {
     const float* bias;         // [Cout]
     __half* out;               // NHWC fp16 [NB, H(/2), W(/2), Cout]; may be null when out_f32 is set
     float* out_f32;            // optional fp32 copy of the un-pooled output (may be null)
+    // optional fused residual update (transformer blocks): resid[token(row)][0:resid_C] += result,
+    // where row -> token undoes the (shifted-)window ordering of the rows (resid_res = 0: identity)
+    float* resid;
+    int resid_C, resid_res, resid_shift;
 };
+
+// token index (b*res*res + y*res + x) of window-ordered row o (8x8 windows, cyclic shift)
+__device__ __forceinline__ long long window_row_to_token(long long o, int res, int shift) {
+    const int nw = res >> 3;
+    const int in = (int)(o & 63);
+    long long wi = o >> 6;
+    const int wx = (int)(wi % nw); wi /= nw;
+    const int wy = (int)(wi % nw);
+    const long long b = wi / nw;
+    int y = wy * 8 + (in >> 3) + shift, xx = wx * 8 + (in & 7) + shift;
+    if (y >= res) y -= res;
+    if (xx >= res) xx -= res;
+    return (b * res + y) * res + xx;
+}
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                        // fp16 elements per 128-B swizzled row
@@ -229,6 +247,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             }
 
             const int ch0 = nt * N_TILE + half * kColsPerWarp;
+            long long resid_row = 0;
+            if (p.resid != nullptr && valid)
+                resid_row = p.resid_res ? window_row_to_token((long long)n, p.resid_res, p.resid_shift) : (long long)n;
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
                 const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ch0 + g * 32);
@@ -266,6 +287,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 d32[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
+                        if (p.resid != nullptr && ch0 + g * 32 < p.resid_C) {     // resid_C is a multiple of 32
+                            float4* xr = reinterpret_cast<float4*>(p.resid + resid_row * p.resid_C + ch0 + g * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4 v = xr[j];
+                                v.x += f[4 * j]; v.y += f[4 * j + 1]; v.z += f[4 * j + 2]; v.w += f[4 * j + 3];
+                                xr[j] = v;
+                            }
                         }
                     }
                 } else {

@@ -182,7 +182,8 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
 }
 
 int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CUtensorMap& mw,
-              int NB, const float* bias, void* out, float* out_f32, cudaStream_t st) {
+              int NB, const float* bias, void* out, float* out_f32, cudaStream_t st,
+              float* resid = nullptr, int resid_C = 0, int resid_res = 0, int resid_shift = 0) {
     fad::ConvGemmParams p;
     p.taps = g.taps; p.cblks = g.Cin / 64;
     p.box_w = g.box_w; p.box_h = g.box_h; p.box_n = g.box_n;
@@ -192,6 +193,7 @@ int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CU
     p.H = g.H; p.W = g.W; p.NB = NB; p.Cout = g.Cout;
     p.relu = g.relu; p.pool = g.pool;
     p.bias = bias; p.out = reinterpret_cast<__half*>(out); p.out_f32 = out_f32;
+    p.resid = resid; p.resid_C = resid_C; p.resid_res = resid_res; p.resid_shift = resid_shift;
     if (g.split_w) return launch_conv_gemm<128, 4, true>(h, mx, mw, p, st);
     if (g.n_tile == 256) return launch_conv_gemm<256, 4, false>(h, mx, mw, p, st);
     return launch_conv_gemm<128, 6, false>(h, mx, mw, p, st);
@@ -568,7 +570,7 @@ int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, 
 // ----------------------------------------------------------------------------- Frechet
 namespace {
 int launch_dgemm2(fad_handle* h, const fad::DgemmBatch& batch, int nprob, int d, cudaStream_t st) {
-    if (d <= 256) {
+    if (d <= 768) {                                            // 32x32 tiles: >= 2 waves of CTAs from d = 512 down
         dim3 grid((d + 31) / 32, (d + 31) / 32, nprob);
         fad::dgemm_kernel<32><<<grid, 256, 0, st>>>(batch, d);
     } else {

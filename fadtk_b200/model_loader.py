@@ -198,12 +198,11 @@ class CLAPLaionModel(ModelLoader):
         eng = self._engine
         offsets = np.zeros(len(clips) + 1, dtype=np.int64)
         offsets[1:] = np.cumsum([len(c) for c in clips])
-        start, valid, rows = eng.clap_plan(offsets)
+        plan = eng.clap_plan_frames(offsets)
         flat = torch.from_numpy(np.concatenate(clips)) if len(clips) > 1 else torch.from_numpy(np.ascontiguousarray(clips[0]))
         pcm = flat.pin_memory().to(eng.torch_device, non_blocking=True)
-        emb = eng.clap_forward(pcm, torch.from_numpy(start).to(eng.torch_device),
-                               torch.from_numpy(valid).to(eng.torch_device))
-        return list(torch.split(emb, [int(r) for r in rows]))
+        emb = eng.clap_forward(pcm, eng.clap_plan_to_device(plan))
+        return list(torch.split(emb, [int(r) for r in plan["rows_per_clip"]]))
 
 
 class UnbuiltModel(ModelLoader):

@@ -48,6 +48,7 @@ class EvalSetFAD:
         self._copy_stream = torch.cuda.Stream(device=self.dev)
         self._staging = None
         self._plans = {}
+        self._baseline = None
 
     def _plan(self, n_clips: int):
         if n_clips not in self._plans:
@@ -56,8 +57,7 @@ class EvalSetFAD:
                 ex, _ = self.eng.vggish_plan(off)
                 self._plans[n_clips] = (torch.from_numpy(ex).to(self.dev),)
             else:
-                start, valid, _ = self.eng.clap_plan(off)
-                self._plans[n_clips] = (torch.from_numpy(start).to(self.dev), torch.from_numpy(valid).to(self.dev))
+                self._plans[n_clips] = (self.eng.clap_plan_to_device(self.eng.clap_plan_frames(off)),)
         return self._plans[n_clips]
 
     def embed(self, pcm_dev: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -66,7 +66,7 @@ class EvalSetFAD:
         flat = pcm_dev.reshape(-1)
         if self.model == "vggish":
             return self.eng.vggish_forward(flat, plan[0], out)
-        emb = self.eng.clap_forward(flat, plan[0], plan[1])
+        emb = self.eng.clap_forward(flat, plan[0])
         if out is not None:
             out.copy_(emb)
             return out
@@ -112,7 +112,9 @@ class EvalSetFAD:
             b16 = p16 - torch.outer(mu_ref, s16) - torch.outer(s16, mu_ref) + n * torch.outer(mu_ref, mu_ref)
             cov = (cov * (n - 1) - b64 + b16) / (n - 1)
             mu = mu_ref
-        return self.eng.frechet(self.mu_base, self.cov_base, mu.contiguous(), cov.contiguous())
+        if self._baseline is None:                            # sqrt(C_base) once per baseline, not per eval set
+            self._baseline = _native.Baseline(self.eng, self.mu_base, self.cov_base)
+        return self._baseline.frechet(mu.contiguous(), cov.contiguous())
 
     def run_device(self, pcm_dev: torch.Tensor) -> torch.Tensor:
         """pcm_dev int16 [n_clips, clip_samples] resident in HBM -> fp64[8] result (device)."""

@@ -95,13 +95,23 @@ int fad_clap_load(fad_handle* h, const void* const* tensors_host, int n_tensors,
 long long fad_clap_plan(const long long* clip_offsets_host, long long n_clips, long long* chunk_start_host,
                         int* chunk_valid_host, long long capacity, long long* rows_per_clip_host);
 
-/* pcm: int16 mono 48 kHz (device); chunk_start int64 / chunk_valid int32 [n_chunks] (device).
- * emb_out: fp16 [n_chunks, 512], L2-normalised - what the reference caches as .npy. */
-int fad_clap_forward(fad_handle* h, const int16_t* pcm, const long long* chunk_start, const int* chunk_valid,
-                     long long n_chunks, void* emb_out_f16, void* stream);
-/* stage entry point: BatchNorm-ed log-mel [n_chunks, 1001, 64] fp32 */
-int fad_clap_logmel(fad_handle* h, const int16_t* pcm, const long long* chunk_start, const int* chunk_valid,
-                    long long n_chunks, float* out, void* stream);
+/* Frame pool: windows of one clip are 1-s shifts of the same audio, so every STFT frame that does
+ * not touch a window edge is shared by up to ten windows.  fad_clap_plan_frames lists each DISTINCT
+ * frame once - pool_start (sample offset of the window it is taken from), pool_valid, pool_frame
+ * (frame index inside that window) - and fills frame_index [n_chunks][1001]: pool row of every
+ * (window, frame).  Returns the pool size (pass NULL outputs to only count). */
+long long fad_clap_plan_frames(const long long* clip_offsets_host, long long n_clips, long long* pool_start_host,
+                               int* pool_valid_host, int* pool_frame_host, long long pool_capacity,
+                               int* frame_index_host);
+
+/* pcm: int16 mono 48 kHz; pool_* [n_pool] and frame_index [n_chunks*1001] from fad_clap_plan_frames (all
+ * device).  emb_out: fp16 [n_chunks, 512], L2-normalised - what the reference caches as .npy. */
+int fad_clap_forward(fad_handle* h, const int16_t* pcm, const long long* pool_start, const int* pool_valid,
+                     const int* pool_frame, long long n_pool, const int* frame_index, long long n_chunks,
+                     void* emb_out_f16, void* stream);
+/* stage entry point: BatchNorm-ed log-mel rows [n_pool, 64] fp32 */
+int fad_clap_logmel(fad_handle* h, const int16_t* pcm, const long long* pool_start, const int* pool_valid,
+                    const int* pool_frame, long long n_pool, float* out, void* stream);
 
 /* ---- statistics: replaces calc_embd_statistics (fadtk/fad.py:42-48) and
  * _process_file / calculate_embd_statistics_online (fadtk/utils.py:13-46) ----------------

@@ -20,6 +20,35 @@ def test_plan_follows_reference_windowing():
     assert (start[13], valid[13]) == (off[3] + 48000, 1)
 
 
+def test_frame_pool_addresses_the_same_samples():
+    """Every (window, frame) must map to a pool entry reading the same absolute samples with the same
+    edge behaviour: interior frames (2..998) are shared between the windows of a clip, edge frames
+    (reflect padding at 0/1/999/1000) stay per window."""
+    lens = [480000, 1, 48000, 48001, 100000, 0, 600000]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    start, valid, rows = _native.Engine.clap_plan(off)
+    plan = _native.Engine.clap_plan_frames(off)
+    ps, pv, pf, fi = (plan[k] for k in ("pool_start", "pool_valid", "pool_frame", "frame_index"))
+    assert fi.shape == (len(start), 1001) and np.array_equal(plan["rows_per_clip"], rows)
+    assert fi.min() == 0 and fi.max() == len(ps) - 1 and len(np.unique(fi)) == len(ps)     # pool has no dead rows
+    f = np.arange(1001)[None, :]
+    pos_want = start[:, None] + 480 * f                      # centre sample of each frame
+    assert np.array_equal(ps[fi] + 480 * pf[fi], np.broadcast_to(pos_want, fi.shape))
+    clip_end_want = (start + valid)[:, None]                 # zero padding starts at the end of the clip
+    inner = (f >= 2) & (f <= 998)
+    # a shared frame never reaches the end of its source window unless that is the end of the clip
+    src_end = ps[fi] + pv[fi]
+    reach = pos_want + 512
+    ok = np.where(inner, (src_end == clip_end_want) | ((reach <= src_end) & (reach <= clip_end_want)), True)
+    assert ok.all()
+    assert ((pf[fi] >= 2) & (pf[fi] <= 998))[np.broadcast_to(inner, fi.shape)].all()
+    edge = ~np.broadcast_to(inner, fi.shape)
+    assert np.array_equal(ps[fi][edge], np.broadcast_to(start[:, None], fi.shape)[edge])
+    assert np.array_equal(pf[fi][edge], np.broadcast_to(f, fi.shape)[edge])
+    n_win = len(start)
+    assert len(ps) < 0.3 * n_win * 1001                      # ~5x fewer frames than windows x 1001 here
+
+
 def test_packing_shapes_and_padding():
     sd = weights_clap.synthetic_clap_state(0)
     pk = weights_clap.pack_clap(sd)
@@ -49,10 +78,13 @@ def clap_engine(engine):
 def test_logmel_batchnorm_stage_matches_oracle(clap_engine):
     clips = _clips()
     off = np.concatenate([[0], np.cumsum([len(c) for c in clips])]).astype(np.int64)
-    start, valid, rows = clap_engine.clap_plan(off)
+    plan = clap_engine.clap_plan_frames(off)
+    rows = plan["rows_per_clip"]
+    # a 10-s clip has 1897 shared interior frames + 4 edge frames per window instead of 10 x 1001
+    assert plan["pool_start"].shape[0] == (1897 + 40) + (200 + 997 + 12)
     dev = clap_engine.torch_device
-    got = clap_engine.clap_logmel(torch.from_numpy(np.concatenate(clips)).to(dev), torch.from_numpy(start).to(dev),
-                                  torch.from_numpy(valid).to(dev)).cpu()
+    got = clap_engine.clap_logmel(torch.from_numpy(np.concatenate(clips)).to(dev),
+                                  clap_engine.clap_plan_to_device(plan)).cpu()
     sd = co.synthetic_state(0)
     want = []
     for c in clips:
