@@ -215,7 +215,8 @@ def main():
     d = spec["d"]
     zero_mu, eye = torch.zeros(d, dtype=torch.float64), torch.eye(d, dtype=torch.float64)
     helper = EvalSetFAD(eng, zero_mu, eye, clip_samples, clips_per_chunk=args.chunk_clips, model=args.model)
-    base_pcm = synth.musiclike_device(args.baseline_clips, CLIP_SECONDS, sr, seed=30_000, device=dev)
+    base_pcm = synth.musiclike_device(args.baseline_clips, CLIP_SECONDS, sr, seed=30_000, device=dev,
+                                      fmax=1500.0, noise=0.08)
     base_emb = torch.cat([helper.embed(base_pcm[s:s + args.chunk_clips]) for s in range(0, args.baseline_clips, args.chunk_clips)])
     shift = base_emb[:4096].float().mean(0).to(torch.float16)
     acc = eng.stats_accumulate(base_emb, shift, eng.stats_new(d))

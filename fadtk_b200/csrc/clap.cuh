@@ -198,49 +198,59 @@ clap_patch_embed_kernel(const float* __restrict__ lm, const int* __restrict__ fr
                         float* __restrict__ x)
 {
     const int lane = threadIdx.x & 31;
-    const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tok >= (long long)n_chunks * 4096) return;
-    const int b = (int)(tok >> 12), p = (int)(tok & 4095);
-    const int ph = p >> 6, pwid = p & 63;                          // image row block / col block
-    const int j = ph >> 4, f0 = (ph & 15) * 4;                     // time block, first mel bin
-    // lanes 0..15: pixel (r = lane / 4 -> mel f0 + r, c = lane % 4 -> time)
-    float pix = 0.f;
-    if (lane < 16) {
-        const int r = lane >> 2, c = lane & 3;
-        const int t = j * 256 + pwid * 4 + c;                      // 0..1023 on the resized time axis
-        const float s = (float)t * (float)(kClFrames - 1) / 1023.0f;     // align_corners=True
-        const int i0 = (int)floorf(s);
-        float cf[4];
-        cubic_coeffs(s - (float)i0, cf);
-        const int* fidx = frame_index + (size_t)b * kClFrames;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int ti = i0 - 1 + k;
-            ti = ti < 0 ? 0 : (ti > kClFrames - 1 ? kClFrames - 1 : ti);
-            pix = fmaf(cf[k], lm[(size_t)fidx[ti] * kClMel + f0 + r], pix);
-        }
-    }
-    float o[3];
-#pragma unroll
-    for (int u = 0; u < 3; ++u) o[u] = bias[lane + 32 * u];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const float v = __shfl_sync(0xffffffffu, pix, q);
-#pragma unroll
-        for (int u = 0; u < 3; ++u) o[u] = fmaf(w[(lane + 32 * u) * 16 + q], v, o[u]);
-    }
-    float s1 = o[0] + o[1] + o[2];
-    for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-    const float mean = s1 / 96.0f;
-    float s2 = 0.f;
-#pragma unroll
-    for (int u = 0; u < 3; ++u) { const float dlt = o[u] - mean; s2 += dlt * dlt; }
-    for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-    const float rstd = rsqrtf(s2 / 96.0f + 1e-5f);
+    // the 96x16 filter bank, bias and LayerNorm affine live in registers (3 channels per lane) and are
+    // reused for every token this warp handles
+    float wr[3][16], br[3], gr[3], ber[3];
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
         const int ch = lane + 32 * u;
-        x[tok * 96 + ch] = (o[u] - mean) * rstd * gamma[ch] + beta[ch];
+        br[u] = bias[ch]; gr[u] = gamma[ch]; ber[u] = beta[ch];
+        const float4* wp = reinterpret_cast<const float4*>(w + ch * 16);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 t4 = wp[q4];
+            wr[u][4 * q4] = t4.x; wr[u][4 * q4 + 1] = t4.y; wr[u][4 * q4 + 2] = t4.z; wr[u][4 * q4 + 3] = t4.w;
+        }
+    }
+    const long long total = (long long)n_chunks * 4096;
+    for (long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); tok < total; tok += (long long)gridDim.x * 8) {
+        const int b = (int)(tok >> 12), p = (int)(tok & 4095);
+        const int ph = p >> 6, pwid = p & 63;                          // image row block / col block
+        const int j = ph >> 4, f0 = (ph & 15) * 4;                     // time block, first mel bin
+        // lanes 0..15: pixel (r = lane / 4 -> mel f0 + r, c = lane % 4 -> time)
+        float pix = 0.f;
+        if (lane < 16) {
+            const int r = lane >> 2, c = lane & 3;
+            const int t = j * 256 + pwid * 4 + c;                      // 0..1023 on the resized time axis
+            const float s = (float)t * (float)(kClFrames - 1) / 1023.0f;     // align_corners=True
+            const int i0 = (int)floorf(s);
+            float cf[4];
+            cubic_coeffs(s - (float)i0, cf);
+            const int* fidx = frame_index + (size_t)b * kClFrames;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int ti = i0 - 1 + k;
+                ti = ti < 0 ? 0 : (ti > kClFrames - 1 ? kClFrames - 1 : ti);
+                pix = fmaf(cf[k], lm[(size_t)fidx[ti] * kClMel + f0 + r], pix);
+            }
+        }
+        float o[3] = {br[0], br[1], br[2]};
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float v = __shfl_sync(0xffffffffu, pix, q);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) o[u] = fmaf(wr[u][q], v, o[u]);
+        }
+        float s1 = o[0] + o[1] + o[2];
+        for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        const float mean = s1 / 96.0f;
+        float s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) { const float dlt = o[u] - mean; s2 += dlt * dlt; }
+        for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+        const float rstd = rsqrtf(s2 / 96.0f + 1e-5f);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) x[tok * 96 + lane + 32 * u] = (o[u] - mean) * rstd * gr[u] + ber[u];
     }
 }
 

@@ -51,12 +51,13 @@ struct ConvGemmParams {
 
 // token index (b*res*res + y*res + x) of window-ordered row o (8x8 windows, cyclic shift)
 __device__ __forceinline__ long long window_row_to_token(long long o, int res, int shift) {
+    const int lg_nw = 28 - __clz(res);                 // res is a power of two >= 8: log2(res / 8)
     const int nw = res >> 3;
     const int in = (int)(o & 63);
-    long long wi = o >> 6;
-    const int wx = (int)(wi % nw); wi /= nw;
-    const int wy = (int)(wi % nw);
-    const long long b = wi / nw;
+    const long long wi = o >> 6;
+    const int wx = (int)wi & (nw - 1);
+    const int wy = (int)(wi >> lg_nw) & (nw - 1);
+    const long long b = wi >> (2 * lg_nw);
     int y = wy * 8 + (in >> 3) + shift, xx = wx * 8 + (in & 7) + shift;
     if (y >= res) y -= res;
     if (xx >= res) xx -= res;
@@ -69,6 +70,7 @@ constexpr int kConvGemmThreads = 384;
 constexpr int kEpilogueWarps = 8;
 constexpr int kChunkSteps = 8;                     // k-steps (of 64) per TMEM accumulation chunk
 constexpr uint32_t kABytes = kTileM * kBlockK * 2; // 16 KiB per stage
+constexpr uint32_t kStagingBytes = 32 * 128;       // per epilogue warp: 32 rows x 128 B output staging
 
 // SPLIT_W: the weights are an fp16 hi/lo pair (W = Wh + Wl, 22 bits).  fp16 rounding of the
 // weights is a fixed perturbation of the model that does not average out over samples: it alone
@@ -83,13 +85,31 @@ __host__ __device__ constexpr uint32_t conv_gemm_stage_bytes() {
 
 template <int N_TILE, int STAGES, bool SPLIT_W>
 __host__ __device__ constexpr uint32_t conv_gemm_smem_bytes() {
-    return STAGES * conv_gemm_stage_bytes<N_TILE, SPLIT_W>() + 1024 /*align slack*/ + 256 /*barriers*/;
+    return STAGES * conv_gemm_stage_bytes<N_TILE, SPLIT_W>() + 1024 /*align slack*/ + 256 /*barriers*/
+         + kEpilogueWarps * kStagingBytes;
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// GELU(x) = x/2 (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below the fp16 rounding of the value this feeds): 2 MUFU (rcp/ex2.approx) + ~12 FMA-pipe
+// instructions, about half of erff's.  torch.nn.GELU() (exact erf form) is what HTSAT uses.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+    const float erf_abs = fmaf(-poly, e, 1.0f);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
@@ -117,6 +137,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint8_t* staging = smem + STAGES * kStageBytes + 256;            // kEpilogueWarps x kStagingBytes
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -213,13 +234,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
         const int phh = (r / bw) % bh;
         const int pn = r / (bw * bh);
         int buf = 0; uint32_t buf_ph = 0;
+        // plain row-major GEMM (1x1 "image", 128 rows per tile): no per-tile divisions
+        const bool plain = p.tiles_w == 1 && p.tiles_h == 1 && bw == 1 && bh == 1;
+        int nt = blockIdx.x % p.n_tiles, m = blockIdx.x / p.n_tiles;
+        const int step_nt = gridDim.x % p.n_tiles, step_m = gridDim.x / p.n_tiles;
+        // residual rows are read-modify-written in the epilogue: pull the NEXT tile's rows into L2
+        // while this tile is computed, so the loads do not pay HBM latency on the critical path
+        auto prefetch_resid = [&](int nt_, int m_) {
+            if (p.resid == nullptr || !plain) return;
+            const int n_ = m_ * kTileM + r;
+            if (n_ >= p.NB) return;
+            const long long tok = p.resid_res ? window_row_to_token((long long)n_, p.resid_res, p.resid_shift) : (long long)n_;
+            const int c0 = nt_ * N_TILE + half * kColsPerWarp;
+            for (int c = c0; c < c0 + kColsPerWarp && c < p.resid_C; c += 32)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p.resid + tok * p.resid_C + c));
+        };
+        if (blockIdx.x < total_tiles) prefetch_resid(nt, m);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles;
-            const int m = tile / p.n_tiles;
-            const int w = (m % p.tiles_w) * bw + pw;
-            const int h = ((m / p.tiles_w) % p.tiles_h) * bh + phh;
-            const int n = (m / (p.tiles_w * p.tiles_h)) * p.box_n + pn;
+            int w, h, n;
+            if (plain) { w = 0; h = 0; n = m * kTileM + r; }
+            else {
+                w = (m % p.tiles_w) * bw + pw;
+                h = ((m / p.tiles_w) % p.tiles_h) * bh + phh;
+                n = (m / (p.tiles_w * p.tiles_h)) * p.box_n + pn;
+            }
             const bool valid = n < p.NB;
+            int nt_next = nt + step_nt, m_next = m + step_m;
+            if (nt_next >= p.n_tiles) { nt_next -= p.n_tiles; ++m_next; }
+            if (tile + (int)gridDim.x < total_tiles) prefetch_resid(nt_next, m_next);
 
             // sum the K chunks in registers (round-to-nearest adds)
             float acc[kColsPerWarp];
@@ -247,9 +289,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             }
 
             const int ch0 = nt * N_TILE + half * kColsPerWarp;
-            long long resid_row = 0;
-            if (p.resid != nullptr && valid)
-                resid_row = p.resid_res ? window_row_to_token((long long)n, p.resid_res, p.resid_shift) : (long long)n;
+            // Destination of this lane's row (element offsets, -1 = row beyond the batch).  Stores go
+            // through a per-warp staging tile (32 rows x 128 B, 16-B chunks XOR-swizzled by row) so a
+            // warp writes whole 128-B lines of 4 rows per instruction instead of 16 B into 32
+            // different rows: the direct pattern made the small-K GEMMs LSU-bound (ncu: 32 sectors
+            // per store request, stall_lg/long_scoreboard on the bias loads queued behind them).
+            long long out_off = -1, res_off = -1;
+            if (valid && !p.pool) {
+                out_off = (long long)((size_t(n) * p.H + h) * p.W + w) * p.Cout;
+                if (p.resid != nullptr)
+                    res_off = (p.resid_res ? window_row_to_token((long long)n, p.resid_res, p.resid_shift) : (long long)n)
+                              * p.resid_C;
+            }
+            uint8_t* stg = staging + (warp - 4) * kStagingBytes;
+            uint8_t* stg_mine = stg + lane * 128;
+            const int sw = lane & 7;
+            const int cq = lane & 7, rq = lane >> 3;      // flush role: 16-B chunk cq of rows it*4 + rq
+            const bool f32_path = p.out_f32 != nullptr || p.resid != nullptr;
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
                 const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ch0 + g * 32);
@@ -267,35 +323,78 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
                 } else if (p.relu == 2) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
                 }
                 uint32_t h2[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) h2[j] = pack_half2(f[2 * j], f[2 * j + 1]);
 
                 if (!p.pool) {
-                    if (valid) {
-                        const size_t pix = (size_t(n) * p.H + h) * p.W + w;
-                        if (p.out) {
-                            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + g * 32);
+                    if (f32_path) {
+                        // fp32 outputs: this group's 32 columns = one 128-B row segment per row
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(stg_mine + ((j ^ sw) << 4)) =
+                                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        __syncwarp();
+                        float4 v[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + rq;
+                            v[it] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+                        }
+                        const int col = ch0 + g * 32 + cq * 4;
+                        if (p.out_f32 != nullptr) {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const long long off = __shfl_sync(0xffffffffu, out_off, it * 4 + rq);
+                                if (off >= 0) *reinterpret_cast<float4*>(p.out_f32 + off + col) = v[it];
+                            }
+                        }
+                        if (p.resid != nullptr && ch0 + g * 32 < p.resid_C) {     // resid_C is a multiple of 32
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {               // 4 loads in flight, then 4 stores
+                                long long offs[4];
+                                float4 xv[4];
+#pragma unroll
+                                for (int it = 0; it < 4; ++it) {
+                                    offs[it] = __shfl_sync(0xffffffffu, res_off, (hf * 4 + it) * 4 + rq);
+                                    if (offs[it] >= 0) xv[it] = *reinterpret_cast<const float4*>(p.resid + offs[it] + col);
+                                }
+#pragma unroll
+                                for (int it = 0; it < 4; ++it) {
+                                    if (offs[it] >= 0) {
+                                        const float4 a = v[hf * 4 + it];
+                                        xv[it].x += a.x; xv[it].y += a.y; xv[it].z += a.z; xv[it].w += a.w;
+                                        *reinterpret_cast<float4*>(p.resid + offs[it] + col) = xv[it];
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (p.out != nullptr && out_off >= 0) {   // rare (last VGGish layer): both precisions, direct
+                            uint4* dst = reinterpret_cast<uint4*>(p.out + out_off + ch0 + g * 32);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 dst[j] = make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
                         }
-                        if (p.out_f32) {
-                            float4* d32 = reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + ch0 + g * 32);
+                    } else if (p.out != nullptr) {
+                        // fp16 output: two groups (64 columns) fill the 128-B row segment, then flush
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                d32[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                        }
-                        if (p.resid != nullptr && ch0 + g * 32 < p.resid_C) {     // resid_C is a multiple of 32
-                            float4* xr = reinterpret_cast<float4*>(p.resid + resid_row * p.resid_C + ch0 + g * 32);
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(stg_mine + ((((g & 1) * 4 + j) ^ sw) << 4)) =
+                                make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+                        if (g & 1) {
+                            __syncwarp();
+                            const int col = ch0 + (g - 1) * 32 + cq * 8;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float4 v = xr[j];
-                                v.x += f[4 * j]; v.y += f[4 * j + 1]; v.z += f[4 * j + 2]; v.w += f[4 * j + 3];
-                                xr[j] = v;
+                            for (int it = 0; it < 8; ++it) {
+                                const int rr = it * 4 + rq;
+                                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+                                const long long off = __shfl_sync(0xffffffffu, out_off, rr);
+                                if (off >= 0) *reinterpret_cast<uint4*>(p.out + off + col) = v;
                             }
+                            __syncwarp();
                         }
                     }
                 } else {
@@ -320,6 +419,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     }
                 }
             }
+            nt = nt_next; m = m_next;
         }
     }
 

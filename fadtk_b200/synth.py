@@ -44,12 +44,15 @@ def clip_set(kind: str, count: int, seconds: float, sr: int, start: int = 0) -> 
     return np.stack([gen(start + i, seconds, sr) for i in range(count)])
 
 
-def musiclike_device(count: int, seconds: float, sr: int, seed: int, device, chunk: int = 512):
+def musiclike_device(count: int, seconds: float, sr: int, seed: int, device, chunk: int = 512,
+                     fmax: float = 4000.0, noise: float = 0.02):
     """Large music-like set generated on the GPU (bench only): [count, samples] int16.
 
     Same recipe as ``musiclike_clip`` (4 sines 80-4000 Hz, amplitude 0.05-0.25, plus
     N(0, 0.02^2)) but drawn from a torch generator so 10 000 x 10 s clips take a
-    fraction of a second.  The CPU baseline leg reads the same tensor back.
+    fraction of a second.  The CPU baseline leg reads the same tensor back.  ``fmax`` / ``noise``
+    change the timbre (the bench draws its baseline set darker and noisier than the eval set, so
+    the FAD it reports is a distance between different distributions, as in real use).
     """
     import torch
     n = int(round(seconds * sr))
@@ -59,9 +62,9 @@ def musiclike_device(count: int, seconds: float, sr: int, seed: int, device, chu
     t = torch.arange(n, device=device, dtype=torch.float32) / sr
     for s in range(0, count, chunk):
         c = min(chunk, count - s)
-        freqs = 80.0 + 3920.0 * torch.rand((c, 4), generator=g, device=device)
+        freqs = 80.0 + (fmax - 80.0) * torch.rand((c, 4), generator=g, device=device)
         amps = 0.05 + 0.20 * torch.rand((c, 4), generator=g, device=device)
-        x = 0.02 * torch.randn((c, n), generator=g, device=device)
+        x = noise * torch.randn((c, n), generator=g, device=device)
         for k in range(4):
             x += amps[:, k:k + 1] * torch.sin(2 * np.pi * freqs[:, k:k + 1] * t[None, :])
         out[s:s + c] = torch.round(32767.0 * x.clamp_(-1.0, 1.0)).to(torch.int16)
