@@ -330,23 +330,31 @@ clap_copy_rows_kernel(float* __restrict__ x, const float* __restrict__ y, long l
         x[e] = y[(e / C) * ld_y + (e % C)];
 }
 
-// Window attention on the warp-level tensor-core path (mma.sync m16n8k16, fp16 in / fp32 accumulate):
-// a 64 x 64 x 24 problem per (window, head) is far too small for a tcgen05/TMEM tile, but maps
-// exactly onto 16x8x16 fragments.  One warp per (window, head):
-//   S = Q K^T            4 m-tiles x 8 n-tiles x 2 k-steps (head dim 24 zero-padded to 32)
+// Window attention on the warp-level tensor-core path (mma.sync m16n8k16 / m16n8k8, fp16 in / fp32
+// accumulate): a 64 x 64 x 24 problem per (window, head) is far too small for a tcgen05/TMEM tile,
+// but maps exactly onto 16x8 fragments.  One warp per (window, head):
+//   staging  Q, K, V rows (24 halves = 48 B each) with 16-B cp.async into warp-private smem, row
+//            stride 48 B: conflict-free for the fragment loads below and for ldmatrix
+//   S = Q K^T            4 m-tiles x 8 n-tiles, head dim 24 = one k16 + one k8 step
 //   S = S/sqrt(24) + relative-position bias (+ -100 across shift regions); row softmax in registers
-//   O = P V              per m-tile 3 n-tiles x 4 k-steps, P re-used straight from the S accumulators
+//   O = P V              per m-tile 3 n-tiles x 4 k-steps, P re-used straight from the S accumulators,
+//                        V fragments by ldmatrix.trans from the row-major tile
 // qkv: fp16 [rows, ld] with q | k | v at column offsets 0, C, 2C and head h at h*24.
 // relbias: fp32 [heads][64][64].  out: fp16 [rows, ld_out] (head h at h*24).
-constexpr int kAttWarps = 3;
-constexpr int kQStride = 40;      // halves per Q/K smem row (32 used): conflict-free fragment loads
-constexpr int kVStride = 72;      // halves per V^T smem row (64 keys used)
+constexpr int kAttWarps = 4;
+constexpr int kAttRow = 24;       // halves per staged row
+constexpr int kAttMat = 64 * kAttRow;
 
 __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                              uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_m16n8k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
 }
 __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
     __half2 h = __floats2half2_rn(x, y);
@@ -358,39 +366,36 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                              const float* __restrict__ relbias, int res, int shift, long long n_windows,
                              __half* __restrict__ out, int ld_out)
 {
-    __shared__ __align__(16) __half Qs[kAttWarps][64 * kQStride];
-    __shared__ __align__(16) __half Ks[kAttWarps][64 * kQStride];
-    __shared__ __align__(16) __half Vt[kAttWarps][24 * kVStride];
+    __shared__ __align__(16) __half tiles[kAttWarps][3 * kAttMat];     // Q | K | V, row-major [64][24]
     __shared__ int rid[kAttWarps][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const long long units = n_windows * heads;
+    const int lg_nw = 28 - __clz(res);
     const int nw = res >> 3;
     const float scale = 0.20412414523193151f;                      // 1 / sqrt(24)
-    __half* q_s = Qs[warp]; __half* k_s = Ks[warp]; __half* v_t = Vt[warp];
+    const __half* q_s = tiles[warp];
+    const __half* k_s = q_s + kAttMat;
+    const uint32_t tile_u32 = (uint32_t)__cvta_generic_to_shared(tiles[warp]);
+    // ldmatrix.trans row addresses for the V fragments: lanes 0-7 / 8-15 give the key rows of the
+    // two 8x8 blocks of one n-tile (b0, b1), lanes 16-31 the same rows of the next n-tile
+    const uint32_t v_ld = tile_u32 + 2 * kAttMat * 2 + ((lane & 15) * kAttRow + (lane >> 4) * 8) * 2;
     for (long long u = (long long)blockIdx.x * kAttWarps + warp; u < units; u += (long long)gridDim.x * kAttWarps) {
         const long long win = u / heads;
-        const int h = (int)(u % heads);
+        const int h = (int)(u - win * heads);
         const __half* base = qkv + win * 64 * ld + h * 24;
-        // stage Q, K (rows padded with zeros to 32 dims) and V^T
-        for (int i = lane; i < 64 * 16; i += 32) {                 // 16 half2 slots per row
-            const int r = i >> 4, d2 = (i & 15) * 2;
-            uint32_t qv = 0, kv = 0;
-            if (d2 < 24) {
-                qv = *reinterpret_cast<const uint32_t*>(base + (size_t)r * ld + d2);
-                kv = *reinterpret_cast<const uint32_t*>(base + (size_t)r * ld + C + d2);
-            }
-            *reinterpret_cast<uint32_t*>(q_s + r * kQStride + d2) = qv;
-            *reinterpret_cast<uint32_t*>(k_s + r * kQStride + d2) = kv;
-        }
-        for (int i = lane; i < 64 * 12; i += 32) {
-            const int r = i / 12, d2 = (i % 12) * 2;
-            const __half2 vv = *reinterpret_cast<const __half2*>(base + (size_t)r * ld + 2 * C + d2);
-            v_t[d2 * kVStride + r] = __low2half(vv);
-            v_t[(d2 + 1) * kVStride + r] = __high2half(vv);
+        // 3 matrices x 64 rows x 3 vectors of 16 B = 18 cp.async per lane
+#pragma unroll
+        for (int it = 0; it < 18; ++it) {
+            const int i = it * 32 + lane;
+            const int mtx = i / 192, rem = i - mtx * 192;
+            const int r = rem / 3, v = rem - r * 3;
+            const uint32_t dst = tile_u32 + ((mtx * 64 + r) * kAttRow + v * 8) * 2;
+            const __half* src = base + (size_t)r * ld + mtx * C + v * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src));
         }
         if (shift) {
-            const int wx = (int)(win % nw), wy = (int)((win / nw) % nw);
+            const int wx = (int)win & (nw - 1), wy = (int)(win >> lg_nw) & (nw - 1);
             for (int i = lane; i < 64; i += 32) {
                 const int y = wy * 8 + (i >> 3), xx = wx * 8 + (i & 7);   // coordinates in the SHIFTED image
                 const int ry = y < res - 8 ? 0 : (y < res - shift ? 1 : 2);
@@ -398,6 +403,7 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                 rid[warp][i] = ry * 3 + rx;
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
         const float* bias_h = relbias + (size_t)h * 64 * 64;
 #pragma unroll 1
@@ -406,18 +412,21 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
             float sacc[8][4];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f; }
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const int k0 = ks * 16 + 2 * t;
-                const uint32_t a0 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kQStride + k0);
-                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kQStride + k0);
-                const uint32_t a2 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kQStride + k0 + 8);
-                const uint32_t a3 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kQStride + k0 + 8);
+            {
+                const uint32_t a0 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kAttRow + 2 * t);
+                const uint32_t a1 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kAttRow + 2 * t);
+                const uint32_t a2 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kAttRow + 2 * t + 8);
+                const uint32_t a3 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kAttRow + 2 * t + 8);
+                const uint32_t a4 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kAttRow + 2 * t + 16);
+                const uint32_t a5 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kAttRow + 2 * t + 16);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(k_s + (j * 8 + g) * kQStride + k0);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(k_s + (j * 8 + g) * kQStride + k0 + 8);
+                    const __half* kr = k_s + (j * 8 + g) * kAttRow + 2 * t;
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
+                    const uint32_t b2 = *reinterpret_cast<const uint32_t*>(kr + 16);
                     mma_m16n8k16(sacc[j], a0, a1, a2, a3, b0, b1);
+                    mma_m16n8k8(sacc[j], a4, a5, b2);
                 }
             }
             // scale + bias + mask, row max
@@ -426,8 +435,8 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = j * 8 + 2 * t;
-                const float2 b0v = *reinterpret_cast<const float2*>(bias_h + r0 * 64 + c);
-                const float2 b1v = *reinterpret_cast<const float2*>(bias_h + r1 * 64 + c);
+                const float2 b0v = __ldg(reinterpret_cast<const float2*>(bias_h + r0 * 64 + c));
+                const float2 b1v = __ldg(reinterpret_cast<const float2*>(bias_h + r1 * 64 + c));
                 sacc[j][0] = sacc[j][0] * scale + b0v.x; sacc[j][1] = sacc[j][1] * scale + b0v.y;
                 sacc[j][2] = sacc[j][2] * scale + b1v.x; sacc[j][3] = sacc[j][3] * scale + b1v.y;
                 if (shift) {
@@ -463,12 +472,14 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                 const uint32_t a1 = pack_h2(sacc[2 * kk][2] * inv1, sacc[2 * kk][3] * inv1);
                 const uint32_t a2 = pack_h2(sacc[2 * kk + 1][0] * inv0, sacc[2 * kk + 1][1] * inv0);
                 const uint32_t a3 = pack_h2(sacc[2 * kk + 1][2] * inv1, sacc[2 * kk + 1][3] * inv1);
+                uint32_t b[6];
+                const uint32_t va = v_ld + kk * 16 * kAttRow * 2;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(va));
+                asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                             : "=r"(b[4]), "=r"(b[5]) : "r"(va + ((lane >> 4) ? -16 : 32)));   // dims 16..23 (lanes >= 16: address unused but valid)
 #pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(v_t + (n * 8 + g) * kVStride + kk * 16 + 2 * t);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(v_t + (n * 8 + g) * kVStride + kk * 16 + 2 * t + 8);
-                    mma_m16n8k16(oacc[n], a0, a1, a2, a3, b0, b1);
-                }
+                for (int n = 0; n < 3; ++n) mma_m16n8k16(oacc[n], a0, a1, a2, a3, b[2 * n], b[2 * n + 1]);
             }
             __half* d0 = out + (win * 64 + r0) * ld_out + h * 24;
             __half* d1 = out + (win * 64 + r1) * ld_out + h * 24;
@@ -477,11 +488,6 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                 *reinterpret_cast<uint32_t*>(d0 + n * 8 + 2 * t) = pack_h2(oacc[n][0], oacc[n][1]);
                 *reinterpret_cast<uint32_t*>(d1 + n * 8 + 2 * t) = pack_h2(oacc[n][2], oacc[n][3]);
             }
-            if (h == 0 && t == 0)                                   // keep the GEMM's K padding columns at zero
-                for (int cpad = C; cpad < ld_out; ++cpad) {
-                    out[(win * 64 + r0) * ld_out + cpad] = __float2half_rn(0.f);
-                    out[(win * 64 + r1) * ld_out + cpad] = __float2half_rn(0.f);
-                }
         }
         __syncwarp();
     }

@@ -39,6 +39,8 @@ struct ConvGemmParams {
     int img_groups;            // ceil(NB / box_n)
     int n_tiles;               // Cout / N_TILE
     int H, W, NB, Cout;
+    int ld_out, n_valid;       // un-pooled outputs: row stride and number of columns actually stored
+                               // (Cout is padded to the tile width; columns >= n_valid are dropped)
     int relu, pool;            // relu: 0 = none, 1 = ReLU, 2 = GELU (erf form)
     const float* bias;         // [Cout]
     __half* out;               // NHWC fp16 [NB, H(/2), W(/2), Cout]; may be null when out_f32 is set
@@ -296,7 +298,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             // per store request, stall_lg/long_scoreboard on the bias loads queued behind them).
             long long out_off = -1, res_off = -1;
             if (valid && !p.pool) {
-                out_off = (long long)((size_t(n) * p.H + h) * p.W + w) * p.Cout;
+                out_off = (long long)((size_t(n) * p.H + h) * p.W + w) * p.ld_out;
                 if (p.resid != nullptr)
                     res_off = (p.resid_res ? window_row_to_token((long long)n, p.resid_res, p.resid_shift) : (long long)n)
                               * p.resid_C;
@@ -348,7 +350,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
                             for (int it = 0; it < 8; ++it) {
                                 const long long off = __shfl_sync(0xffffffffu, out_off, it * 4 + rq);
-                                if (off >= 0) *reinterpret_cast<float4*>(p.out_f32 + off + col) = v[it];
+                                if (off >= 0 && col < p.n_valid) *reinterpret_cast<float4*>(p.out_f32 + off + col) = v[it];
                             }
                         }
                         if (p.resid != nullptr && ch0 + g * 32 < p.resid_C) {     // resid_C is a multiple of 32
@@ -372,7 +374,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                             }
                         }
                         __syncwarp();
-                        if (p.out != nullptr && out_off >= 0) {   // rare (last VGGish layer): both precisions, direct
+                        if (p.out != nullptr && out_off >= 0 && ch0 + g * 32 + 32 <= p.n_valid) {   // rare (last VGGish layer): both precisions, direct
                             uint4* dst = reinterpret_cast<uint4*>(p.out + out_off + ch0 + g * 32);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
@@ -392,7 +394,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                                 const int rr = it * 4 + rq;
                                 const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
                                 const long long off = __shfl_sync(0xffffffffu, out_off, rr);
-                                if (off >= 0) *reinterpret_cast<uint4*>(p.out + off + col) = v;
+                                if (off >= 0 && col < p.n_valid) *reinterpret_cast<uint4*>(p.out + off + col) = v;
                             }
                             __syncwarp();
                         }

@@ -168,10 +168,13 @@ int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw
     return 0;
 }
 
+// a_cols: channels actually stored per pixel/row of the activation (<= g.Cin); the TMA box reads
+// zeros beyond it, so a K that is not a multiple of 64 needs no padding columns in HBM.
 int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const void* w,
-                      CUtensorMap* mx, CUtensorMap* mw) {
-    const uint64_t xd[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)nb_dim};
-    const uint64_t xs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.W * g.Cin * 2, (uint64_t)g.H * g.W * g.Cin * 2};
+                      CUtensorMap* mx, CUtensorMap* mw, int a_cols = 0) {
+    const uint64_t ac = a_cols > 0 ? (uint64_t)a_cols : (uint64_t)g.Cin;
+    const uint64_t xd[4] = {ac, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)nb_dim};
+    const uint64_t xs[3] = {ac * 2, (uint64_t)g.W * ac * 2, (uint64_t)g.H * g.W * ac * 2};
     const uint32_t xb[4] = {64, (uint32_t)g.box_w, (uint32_t)g.box_h, (uint32_t)g.box_n};
     if (encode_f16_map(mx, x, 4, xd, xs, xb)) return 1;
     const uint64_t K = (uint64_t)g.taps * g.Cin;
@@ -184,7 +187,7 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
 
 int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CUtensorMap& mw,
               int NB, const float* bias, void* out, float* out_f32, cudaStream_t st,
-              float* resid = nullptr, int resid_C = 0, int resid_res = 0, int resid_shift = 0) {
+              float* resid = nullptr, int resid_C = 0, int resid_res = 0, int resid_shift = 0, int n_valid = 0) {
     fad::ConvGemmParams p;
     p.taps = g.taps; p.cblks = g.Cin / 64;
     p.box_w = g.box_w; p.box_h = g.box_h; p.box_n = g.box_n;
@@ -192,6 +195,8 @@ int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CU
     p.img_groups = (NB + g.box_n - 1) / g.box_n;
     p.n_tiles = g.Cout / g.n_tile;
     p.H = g.H; p.W = g.W; p.NB = NB; p.Cout = g.Cout;
+    p.n_valid = n_valid > 0 ? n_valid : g.Cout;
+    p.ld_out = p.n_valid;
     p.relu = g.relu; p.pool = g.pool;
     p.bias = bias; p.out = reinterpret_cast<__half*>(out); p.out_f32 = out_f32;
     p.resid = resid; p.resid_C = resid_C; p.resid_res = resid_res; p.resid_shift = resid_shift;
