@@ -95,21 +95,23 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-// GELU(x) = x/2 (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
-// far below the fp16 rounding of the value this feeds): 2 MUFU (rcp/ex2.approx) + ~12 FMA-pipe
-// instructions, about half of erff's.  torch.nn.GELU() (exact erf form) is what HTSAT uses.
+// GELU(x) = x/2 (1 + erf(x / sqrt 2)), the exact-erf form torch.nn.GELU() / HTSAT use, with
+//   erf(z) = 1 - 2^(z q(z)),  z = |x| / sqrt 2 clamped to 4.3   (erfc(4.3) = 1.2e-9)
+// q = degree-6 weighted-minimax fit of log2(erfc(z)) / z (oracle/fit_gelu.py): |erf error| <= 1.4e-7
+// in fp32, far below the fp16 rounding of the value this feeds.  One MUFU (ex2) + ~13 FMA-pipe
+// instructions per element - erff costs ~30, and two MUFUs made the fc1 epilogue MUFU-bound.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    float t, e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    poly *= t;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-    const float erf_abs = fmaf(-poly, e, 1.0f);
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float z = fminf(fabsf(x) * 0.70710678118654752f, 4.3f);
+    float q = 1.04899843e-04f;
+    q = fmaf(q, z, -4.92790774e-04f);
+    q = fmaf(q, z, -2.22368206e-03f);
+    q = fmaf(q, z, 2.93586859e-02f);
+    q = fmaf(q, z, -1.48908889e-01f);
+    q = fmaf(q, z, -9.18342944e-01f);
+    q = fmaf(q, z, -1.62791250e+00f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * z));
+    return 0.5f * x * (1.0f + copysignf(1.0f - e, x));
 }
 
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {

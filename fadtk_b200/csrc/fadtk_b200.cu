@@ -604,7 +604,7 @@ int newton_schulz(fad_handle* h, const double* A, int d, int iters, double* Y, d
     if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
     static const float dev_init[3] = {0.0f, 0.0f, 1.0e30f};            // slot (k-1)%3 for k = 0 is slot 2
     CK(cudaMemcpyAsync(dev, dev_init, sizeof dev_init, cudaMemcpyHostToDevice, st));
-    fad::norm_trace_kernel<<<1, 256, 0, st>>>(A, d, scal);
+    fad::norm_trace_kernel<<<1, 1024, 0, st>>>(A, d, scal);
     fad::ns_init_kernel<<<eb, 256, 0, st>>>(A, d, scal, Y, Z);
     CK(cudaGetLastError());
     h->launches += 2;
@@ -683,7 +683,7 @@ int fad_frechet_presqrt(fad_handle* h, const double* mu1, const double* sqrt1, c
     unsigned eb = (unsigned)((total + 255) / 256);
     if (eb > (unsigned)h->num_sms * 8) eb = h->num_sms * 8;
     const size_t ev_fr = prof_begin(h, st);
-    fad::norm_trace_kernel<<<1, 256, 0, st>>>(cov2, d, scalB);
+    fad::norm_trace_kernel<<<1, 1024, 0, st>>>(cov2, d, scalB);
     CK(cudaGetLastError());
     h->launches++;
     if (launch_dgemm(h, sqrt1, cov2, P, d, 1.0, 0.0, nullptr, st)) return 1;     // M = S C2 S

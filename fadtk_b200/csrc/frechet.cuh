@@ -118,19 +118,22 @@ __global__ void trace_kernel(const double* __restrict__ A, int d, double* __rest
     if (threadIdx.x == 0) out[0] = r[0];
 }
 
-// scal[0] = |A|_F, scal[1] = tr A     (single block)
-__global__ void norm_trace_kernel(const double* __restrict__ A, int d, double* __restrict__ scal)
+// scal[0] = |A|_F, scal[1] = tr A     (single block of 1024 threads: fixed summation order)
+__global__ void __launch_bounds__(1024) norm_trace_kernel(const double* __restrict__ A, int d, double* __restrict__ scal)
 {
-    __shared__ double r1[256], r2[256];
-    double s = 0.0, t = 0.0;
-    for (size_t e = threadIdx.x; e < (size_t)d * d; e += 256) {
-        const double v = A[e];
-        s += v * v;
-        if (e / d == e % d) t += v;
+    __shared__ double r1[1024], r2[1024];
+    double s0 = 0.0, s1 = 0.0, t = 0.0;
+    const size_t total = (size_t)d * d;
+    size_t e = threadIdx.x;
+    for (; e + 1024 < total; e += 2048) {                      // two independent chains per thread
+        const double v0 = A[e], v1 = A[e + 1024];
+        s0 += v0 * v0; s1 += v1 * v1;
     }
-    r1[threadIdx.x] = s; r2[threadIdx.x] = t;
+    if (e < total) { const double v = A[e]; s0 += v * v; }
+    for (int i = threadIdx.x; i < d; i += 1024) t += A[(size_t)i * d + i];
+    r1[threadIdx.x] = s0 + s1; r2[threadIdx.x] = t;
     __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
+    for (int k = 512; k > 0; k >>= 1) {
         if (threadIdx.x < k) { r1[threadIdx.x] += r1[threadIdx.x + k]; r2[threadIdx.x] += r2[threadIdx.x + k]; }
         __syncthreads();
     }
