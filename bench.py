@@ -264,9 +264,19 @@ def main():
     per_layer = {k: {"ms_per_launch": prof[k][0] / prof[k][1], "tflops": UMMA_LAYER_FLOP[k] * rows / (prof[k][0] / 1000.0) / 1e12}
                  for k in UMMA_LAYER_FLOP if k in prof and prof[k][0] > 0} if args.model == "vggish" else None
     other = {k: {"ms_total": v[0], "launches": v[1]} for k, v in prof.items() if k not in gemm_keys}
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/), scaled
+    # to this run's rows per launch; None when no capture exists for the model
+    traffic, traffic_src = None, None
+    tf = ROOT / "profiles" / "roofline_traffic.json"
+    if tf.exists() and umma_launch:
+        t = json.loads(tf.read_text()).get(args.model)
+        if t:
+            traffic = t["dram_gb_per_row"] * rows / umma_launch
+            traffic_src = t["source"]
     roofline = {"kernel": "fad::conv_gemm_kernel<128,4,SPLIT_W> (tcgen05 kind::f16, hi/lo split fp16 weights: 2 MMAs per K step)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": None,
+                "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": traffic, "traffic_unit": "GB per launch",
+                "traffic_source": traffic_src,
                 "issued_tflops": 2.0 * achieved, "issued_frac": 2.0 * achieved / peak_tf,
                 "note": "achieved counts ALGORITHMIC FLOPs (2*M*N*K once); the kernel issues twice that (W = Wh + Wl) to keep FAD within 1e-4",
                 "launches": umma_launch, "avg_launch_ms": umma_ms / max(1, umma_launch),
