@@ -55,6 +55,7 @@ SIGNATURES = {
     "fad_frechet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_sqrt_psd": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_presqrt": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "fad_frechet_batched": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_launch_count": (c_ll, [c_vp]),
     "fad_profile_enable": (C.c_int, [c_vp, C.c_int]),
     "fad_profile_collect": (C.c_int, [c_vp, c_vp, c_vp, C.c_int]),
@@ -323,6 +324,17 @@ class Baseline:
         out = torch.zeros(8, dtype=torch.float64, device=self.mu.device)
         _check(lib().fad_frechet_presqrt(self.eng._h, self.mu.data_ptr(), self.sqrt.data_ptr(), self.scal.data_ptr(),
                                          mu2.data_ptr(), cov2.data_ptr(), self.d, 0, out.data_ptr(), _stream()))
+        return out
+
+    def frechet_batched(self, emb: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+        """emb fp16 [N, d], offsets int64 [n_items + 1] (both cuda) -> fp64 [n_items, 8]: every item's
+        FAD against this baseline in one lock-step launch sequence (fad_frechet_batched)."""
+        assert emb.dtype == torch.float16 and emb.is_cuda and emb.is_contiguous() and emb.shape[1] == self.d
+        assert offsets.dtype == torch.int64 and offsets.is_cuda
+        n_items = offsets.shape[0] - 1
+        out = torch.zeros((n_items, 8), dtype=torch.float64, device=emb.device)
+        _check(lib().fad_frechet_batched(self.eng._h, self.mu.data_ptr(), self.sqrt.data_ptr(), self.scal.data_ptr(),
+                                         emb.data_ptr(), offsets.data_ptr(), n_items, self.d, 0, out.data_ptr(), _stream()))
         return out
 
 

@@ -16,6 +16,7 @@
 #include "frontend.cuh"
 #include "stats.cuh"
 #include "frechet.cuh"
+#include "frechet_batched.cuh"
 #include "clap.cuh"
 
 namespace {
@@ -133,6 +134,8 @@ struct fad_handle {
     // Frechet workspace (fp64 d x d matrices)
     double* fr_buf = nullptr;
     size_t fr_cap = 0;
+    unsigned char* frb_buf = nullptr;   // fad_frechet_batched workspace
+    size_t frb_cap = 0;
     double* fr_scal = nullptr;   // 32 doubles
 
     void* clap_state = nullptr;  // ClapState (clap_host.inc)
@@ -347,7 +350,7 @@ int fad_destroy(fad_handle* h) {
     cudaSetDevice(h->device);
     clap_free_state(h->clap_state);
     void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
-                    h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal};
+                    h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal, h->frb_buf};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; ++i) { if (h->conv_w[i]) cudaFree(h->conv_w[i]); if (h->conv_b[i]) cudaFree(h->conv_b[i]); }
     for (int i = 0; i < 3; ++i) { if (h->fc_w[i]) cudaFree(h->fc_w[i]); if (h->fc_b[i]) cudaFree(h->fc_b[i]); }
@@ -710,6 +713,87 @@ int fad_frechet(fad_handle* h, const double* mu1, const double* cov1, const doub
     double* scal1 = h->fr_scal + 12;
     if (fad_sqrt_psd(h, cov1, d, iters, S, scal1, stream)) return 1;
     return fad_frechet_presqrt(h, mu1, S, scal1, mu2, cov2, d, iters, out, stream);
+}
+
+// Ragged-batched FAD of n_items eval sets against one cached baseline (see frechet_batched.cuh).
+int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, const double* scal1,
+                        const void* emb_f16, const long long* offsets, long long n_items, int d, int iters,
+                        double* out, void* stream) {
+    if (!h) return fail("null handle");
+    if (d <= 0 || n_items < 0) return fail("bad dimension");
+    if (n_items == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iters <= 0) iters = 60;
+    if (iters & 1) ++iters;
+    const size_t total = (size_t)d * d;
+    long long G = (long long)((size_t(1) << 31) / (64 * total));          // 8 matrices of d*d doubles per item in 2 GiB
+    if (G < 1) G = 1;
+    if (G > 32767) G = 32767;                                              // two families share gridDim.z
+    if (G > n_items) G = n_items;
+    const size_t per_item = 8 * total * 8 + (size_t)d * 8 + 4 * 8 + 3 * 4 + 4;
+    if (ensure((void**)&h->frb_buf, &h->frb_cap, per_item * (size_t)G + 256)) return 1;
+    double* cov = reinterpret_cast<double*>(h->frb_buf);
+    double* P = cov + G * total;   double* M = P + G * total;
+    double* Y = M + G * total;     double* Z = Y + G * total;   double* W = Z + G * total;
+    double* Yn = W + G * total;    double* Zn = Yn + G * total;
+    double* mu = Zn + G * total;
+    double* scalC = mu + G * d;    double* scalM = scalC + 2 * G;
+    float* flags = reinterpret_cast<float*>(scalM + 2 * G);
+    int* ok = reinterpret_cast<int*>(flags + 3 * G);
+    const int dt = (d + 31) / 32;
+    const bool small = d <= 768;
+    const int gt = small ? dt : (d + 63) / 64;
+    auto gemm = [&](const fad::DgemmStrided& p, int families) -> int {
+        dim3 grid(gt, gt, (unsigned)(p.items * families));
+        if (small) fad::dgemm_strided_kernel<32><<<grid, 256, 0, st>>>(p, d);
+        else       fad::dgemm_strided_kernel<64><<<grid, 256, 0, st>>>(p, d);
+        CK(cudaGetLastError());
+        h->launches++;
+        return 0;
+    };
+    const float tol = 1e-12f;
+    const size_t ev = prof_begin(h, st);
+    for (long long g0 = 0; g0 < n_items; g0 += G) {
+        const int g = (int)((n_items - g0) < G ? (n_items - g0) : G);
+        fad::song_stats_kernel<<<dim3(dt, dt, g), 256, 0, st>>>(reinterpret_cast<const __half*>(emb_f16), offsets + g0, d, mu, cov, ok);
+        fad::norm_trace_batched_kernel<<<g, 256, 0, st>>>(cov, d, scalC);
+        CK(cudaGetLastError());
+        fad::DgemmStrided p = {};
+        p.items = g; p.flags = nullptr; p.in_slot = p.out_slot = p.clear_slot = -1; p.tol = tol;
+        p.f[0] = {sqrt1, cov, P, 0, (long long)total, (long long)total, 1.0, 0.0};          // P = S C_z
+        if (gemm(p, 1)) return 1;
+        p.f[0] = {P, sqrt1, M, (long long)total, 0, (long long)total, 1.0, 0.0};            // M = P S
+        if (gemm(p, 1)) return 1;
+        fad::norm_trace_batched_kernel<<<g, 256, 0, st>>>(M, d, scalM);
+        unsigned eb = (unsigned)((total + 255) / 256);
+        if (eb > 64) eb = 64;
+        fad::ns_init_batched_kernel<<<dim3(eb, g), 256, 0, st>>>(M, d, scalM, Y, Z, flags);
+        CK(cudaGetLastError());
+        h->launches += 4;
+        double* Yc = Y; double* Zc = Z; double* Yx = Yn; double* Zx = Zn;
+        for (int it = 0; it < iters; ++it) {
+            fad::DgemmStrided w = {};
+            w.items = g; w.flags = flags; w.tol = tol;
+            w.in_slot = (it + 2) % 3; w.out_slot = it % 3; w.clear_slot = -1;
+            w.f[0] = {Zc, Yc, W, (long long)total, (long long)total, (long long)total, -0.5, 1.5};   // W = 1.5 I - 0.5 Z Y
+            if (gemm(w, 1)) return 1;
+            fad::DgemmStrided yz = {};
+            yz.items = g; yz.flags = flags; yz.tol = tol;
+            yz.in_slot = (it + 2) % 3; yz.out_slot = -1; yz.clear_slot = (it + 1) % 3;
+            yz.f[0] = {Yc, W, Yx, (long long)total, (long long)total, (long long)total, 1.0, 0.0};   // Y <- Y W
+            yz.f[1] = {W, Zc, Zx, (long long)total, (long long)total, (long long)total, 1.0, 0.0};   // Z <- W Z
+            if (gemm(yz, 2)) return 1;
+            double* t = Yc; Yc = Yx; Yx = t;
+            t = Zc; Zc = Zx; Zx = t;
+        }
+        fad::frechet_assemble_batched_kernel<<<g, 256, 0, st>>>(mu1, mu, d, scal1, scalC, scalM, Y, Z, ok, offsets + g0,
+                                                                iters, out + g0 * 8);
+        CK(cudaGetLastError());
+        h->launches++;
+    }
+    prof_end(h, FAD_PROF_FRECHET, ev, st);
+    return 0;
 }
 
 }  // extern "C"

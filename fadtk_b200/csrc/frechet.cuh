@@ -33,17 +33,14 @@ struct DgemmBatch {
     const float* dev_in; float* dev_out; float* dev_clear; float tol;
 };
 
+// one TM x TM tile of C = alpha A B + beta_diag I; returns max |C - I| over this thread's outputs and
+// its share of tr C
 template <int TM>
-__global__ void __launch_bounds__(256)
-dgemm_kernel(const DgemmBatch batch, int d)
+__device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, const double* __restrict__ B,
+                                           double* __restrict__ C, int d, double alpha, double beta_diag,
+                                           float& dev, double& tr)
 {
     constexpr int R = TM / 16;                                 // outputs per thread per dimension
-    if (batch.dev_in != nullptr && *batch.dev_in < batch.tol) return;      // already converged
-    if (batch.dev_clear != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
-        *batch.dev_clear = 0.0f;
-    const DgemmProblem pr = batch.p[blockIdx.z];
-    const double* __restrict__ A = pr.A;
-    const double* __restrict__ B = pr.B;
     __shared__ double As[16][TM + 1], Bs[16][TM + 1];
     const int bi = blockIdx.y * TM, bj = blockIdx.x * TM;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -72,25 +69,38 @@ dgemm_kernel(const DgemmBatch batch, int d)
         }
         __syncthreads();
     }
-    double tr = 0.0;
-    float dev = 0.0f;
+    tr = 0.0;
+    dev = 0.0f;
 #pragma unroll
     for (int u = 0; u < R; ++u)
 #pragma unroll
         for (int v = 0; v < R; ++v) {
             const int gi = bi + ty * R + u, gj = bj + tx * R + v;
             if (gi < d && gj < d) {
-                double val = pr.alpha * c[u][v];
-                if (gi == gj) { val += pr.beta_diag; tr += val; }
-                pr.C[(size_t)gi * d + gj] = val;
+                double val = alpha * c[u][v];
+                if (gi == gj) { val += beta_diag; tr += val; }
+                C[(size_t)gi * d + gj] = val;
                 dev = fmaxf(dev, (float)fabs(val - (gi == gj ? 1.0 : 0.0)));
             }
         }
+}
+
+template <int TM>
+__global__ void __launch_bounds__(256)
+dgemm_kernel(const DgemmBatch batch, int d)
+{
+    if (batch.dev_in != nullptr && *batch.dev_in < batch.tol) return;      // already converged
+    if (batch.dev_clear != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+        *batch.dev_clear = 0.0f;
+    const DgemmProblem pr = batch.p[blockIdx.z];
+    float dev;
+    double tr;
+    dgemm_tile<TM>(pr.A, pr.B, pr.C, d, pr.alpha, pr.beta_diag, dev, tr);
     if (batch.dev_out != nullptr) {
         for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
         if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(batch.dev_out), __float_as_uint(dev));
     }
-    if (pr.trace_out != nullptr && bi == bj) {
+    if (pr.trace_out != nullptr && blockIdx.x == blockIdx.y) {
         // diagonal blocks only; reduce inside the block, one atomic per block
         __shared__ double red[256];
         red[threadIdx.x] = tr;

@@ -306,22 +306,50 @@ class FrechetAudioDistance:
         base = _native.Baseline(eng, mu, cov)          # C1^(1/2) once, reused for every song
         base.mu_host = np.asarray(mu, dtype=np.float64)
 
-        def _find_z_helper(f):
-            try:
-                embd = self.read_embedding_file(f)
-                if embd.dtype != np.float16:
-                    mu_eval, cov_eval = calc_embd_statistics(embd)
-                    return calc_frechet_distance(mu, cov, mu_eval, cov_eval)
-                assert embd.shape[0] >= 2, (f"FAD requires at least two embedding window frames, you have {embd.shape}."
-                    " (This probably means that your audio is too short)")
-                return _device_score(base, torch.from_numpy(np.ascontiguousarray(embd)).to(eng.torch_device), eng)
+        def _report(f, e):
+            log.error(f"An error occurred calculating individual FAD using model {self.ml.name} on file {f}")
+            log.error(e)
+
+        def _find_z_helper(f, embd):
+            try:                                           # non-fp16 caches: the generic per-item path
+                mu_eval, cov_eval = calc_embd_statistics(embd)
+                return calc_frechet_distance(mu, cov, mu_eval, cov_eval)
             except Exception as e:
                 traceback.print_exc()
-                log.error(f"An error occurred calculating individual FAD using model {self.ml.name} on file {f}")
-                log.error(e)
+                _report(f, e)
 
         _files = list(Path(eval_dir).glob("*.*"))
-        scores = [_find_z_helper(f) for f in _files]      # one GPU, one stream: no thread fan-out
+        scores: list = [None] * len(_files)
+        # fp16 caches (what the reference writes, model_loader.py:47-48): one ragged batch, every song's
+        # statistics and Frechet chain in lock-step on the device (fad_frechet_batched)
+        batch_idx, batch_rows = [], []
+        for i, f in enumerate(_files):
+            try:
+                embd = self.read_embedding_file(f)
+            except Exception as e:
+                traceback.print_exc()
+                _report(f, e)
+                continue
+            if embd.dtype == np.float16 and embd.ndim == 2 and embd.shape[1] == len(mu):
+                batch_idx.append(i)
+                batch_rows.append(np.ascontiguousarray(embd))
+            else:
+                scores[i] = _find_z_helper(f, embd)
+        if batch_idx:
+            offs = np.zeros(len(batch_rows) + 1, dtype=np.int64)
+            offs[1:] = np.cumsum([len(r) for r in batch_rows])
+            flat = torch.from_numpy(np.concatenate(batch_rows)).to(eng.torch_device)
+            out = base.frechet_batched(flat, torch.from_numpy(offs).to(eng.torch_device)).cpu().numpy()
+            for k, i in enumerate(batch_idx):
+                n_rows, fad_k = int(out[k, 7]), float(out[k, 0])
+                if n_rows < 2:
+                    _report(_files[i], AssertionError(
+                        f"FAD requires at least two embedding window frames, you have {batch_rows[k].shape}."
+                        " (This probably means that your audio is too short)"))
+                elif not np.isfinite(fad_k):
+                    _report(_files[i], ValueError("non-finite covariance statistics (NaN/Inf input)"))
+                else:
+                    scores[i] = fad_k
 
         pairs = [p for p in zip(_files, scores) if p[1] is not None]
         pairs = sorted(pairs, key=lambda x: np.abs(x[1]))

@@ -150,6 +150,16 @@ int fad_sqrt_psd(fad_handle* h, const double* cov, int d, int iters, double* sqr
 int fad_frechet_presqrt(fad_handle* h, const double* mu1, const double* sqrt1, const double* scal1,
                         const double* mu2, const double* cov2, int d, int iters, double* out, void* stream);
 
+/* Ragged-batched form for per-file scoring: replaces the loop of FrechetAudioDistance.score_individual
+ * (fadtk/fad.py:353-395; per file calc_embd_statistics fad.py:42-48 + calc_frechet_distance :51-120).
+ * emb_f16: fp16 [N, d] (device); offsets: int64 [n_items + 1] (device), item z = rows
+ * [offsets[z], offsets[z+1]).  Per item the mean is rounded to fp16 (np.mean dtype rule) and the
+ * covariance is the exact fp64 ddof=1 Gram.  out: fp64 [n_items][8] in fad_frechet's layout with
+ * [7] = row count; an item with fewer than two rows gets NaN in [0], [1] (the reference asserts). */
+int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, const double* scal1,
+                        const void* emb_f16, const long long* offsets, long long n_items, int d, int iters,
+                        double* out, void* stream);
+
 /* ---- measurement ----------------------------------------------------------------------
  * When enabled, CUDA events are recorded on the launching stream around every kernel group;
  * fad_profile_collect synchronises the device and returns accumulated milliseconds and launch

@@ -112,6 +112,30 @@ def test_score_individual_matches_reference_csv(engine, golden_dir, tmp_path):
     assert np.allclose(scores, g["scores"], rtol=1e-4)
 
 
+@pytest.mark.parametrize("d,lens", [(128, [750, 2, 1, 130, 40, 750, 333]), (512, [300, 700, 17])])
+def test_frechet_batched_matches_oracle_per_item(engine, d, lens):
+    """fad_frechet_batched == per-item reference arithmetic (fad.py:42-48 + :51-120), ragged items,
+    rank-deficient items (n < d), and an item with a single row (reference: AssertionError -> NaN here)."""
+    from fadtk_b200 import _native
+    rng = np.random.default_rng(5)
+    mix = rng.standard_normal((d, d)) * (1.0 / np.sqrt(d))
+    base_rows = (rng.standard_normal((4 * d, d)) @ mix).astype(np.float16)
+    mu_b, cov_b = fo.embd_statistics(base_rows)
+    mu_b = mu_b.astype(np.float64)        # load_stats returns fp64 baselines (fad.py:286-288); fp16 - fp16 would stay fp16 (fad.py:83)
+    items = [((rng.standard_normal((n, d)) @ mix) * (0.5 + 0.3 * i) + 0.1 * i).astype(np.float16) for i, n in enumerate(lens)]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    base = _native.Baseline(engine, mu_b, cov_b)
+    dev = engine.torch_device
+    out = base.frechet_batched(torch.from_numpy(np.concatenate(items)).to(dev), torch.from_numpy(offs).to(dev)).cpu().numpy()
+    assert out.shape == (len(lens), 8) and [int(v) for v in out[:, 7]] == lens
+    for k, rows in enumerate(items):
+        if len(rows) < 2:
+            assert np.isnan(out[k, 0])
+            continue
+        want = fo.frechet_distance(mu_b, cov_b, *fo.embd_statistics(rows))
+        assert out[k, 0] == pytest.approx(want, rel=2e-6, abs=1e-7 * (out[k, 5] + out[k, 6])), (k, len(rows), out[k, 0], want)
+
+
 def _make_dir(root, kind, count, seconds):
     root.mkdir(parents=True)
     clips = []
