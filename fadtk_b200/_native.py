@@ -55,6 +55,10 @@ SIGNATURES = {
     "fad_frechet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_sqrt_psd": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_presqrt": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "fad_resample_geometry": (C.c_int, [C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "fad_resample_length": (c_ll, [C.c_int, C.c_int, c_ll]),
+    "fad_resample_bank": (C.c_int, [C.c_int, C.c_int, c_vp]),
+    "fad_resample": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_batched": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_launch_count": (c_ll, [c_vp]),
     "fad_profile_enable": (C.c_int, [c_vp, C.c_int]),
@@ -260,6 +264,42 @@ class Engine:
                                      plan_dev["pool_valid"].data_ptr(), plan_dev["pool_frame"].data_ptr(), n_pool,
                                      pool.data_ptr(), _stream()))
         return pool[plan_dev["frame_index"].long()]
+
+    # -------------------------------------------------------------- audio conversion
+    @staticmethod
+    def resample_geometry(sr_in: int, sr_out: int):
+        """-> (orig, new, width, taps) of torchaudio's polyphase resampler for this rate pair."""
+        v = [C.c_int() for _ in range(4)]
+        _check(lib().fad_resample_geometry(int(sr_in), int(sr_out), *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    @staticmethod
+    def resample_bank(sr_in: int, sr_out: int) -> np.ndarray:
+        """float32 [new, taps] filter bank (host only; what fad_resample uploads)."""
+        _, new, _, taps = Engine.resample_geometry(sr_in, sr_out)
+        bank = np.empty((new, taps), dtype=np.float32)
+        _check(lib().fad_resample_bank(int(sr_in), int(sr_out), bank.ctypes.data))
+        return bank
+
+    def resample(self, x: torch.Tensor, sr_in: int, sr_out: int, return_float: bool = False):
+        """x: int16 [length, channels] / [length] (PCM16, cuda) or float32 [channels, length] (cuda)
+        -> int16 [ceil(new*length/orig)] mono at sr_out (and the un-quantised float32 if asked)."""
+        assert x.is_cuda
+        if x.dtype == torch.int16:
+            x = x.contiguous()
+            length, channels = x.shape[0], (1 if x.ndim == 1 else x.shape[1])
+            pi, pf = x.data_ptr(), None
+        else:
+            assert x.dtype == torch.float32 and x.ndim == 2
+            x = x.contiguous()
+            channels, length = x.shape
+            pi, pf = None, x.data_ptr()
+        n_out = int(lib().fad_resample_length(int(sr_in), int(sr_out), length))
+        out = torch.empty(n_out, dtype=torch.int16, device=x.device)
+        outf = torch.empty(n_out, dtype=torch.float32, device=x.device) if return_float else None
+        _check(lib().fad_resample(self._h, pi, pf, channels, length, int(sr_in), int(sr_out), out.data_ptr(),
+                                  outf.data_ptr() if outf is not None else None, _stream()))
+        return (out, outf) if return_float else out
 
     # -------------------------------------------------------------- statistics
     @staticmethod

@@ -18,6 +18,7 @@
 #include "frechet.cuh"
 #include "frechet_batched.cuh"
 #include "clap.cuh"
+#include "resample.cuh"
 
 namespace {
 
@@ -136,6 +137,8 @@ struct fad_handle {
     size_t fr_cap = 0;
     unsigned char* frb_buf = nullptr;   // fad_frechet_batched workspace
     size_t frb_cap = 0;
+    float* rs_bank = nullptr;  size_t rs_bank_cap = 0;  int rs_in = 0, rs_out = 0;     // resampler filter bank
+    float* rs_mono = nullptr;  size_t rs_mono_cap = 0;
     double* fr_scal = nullptr;   // 32 doubles
 
     void* clap_state = nullptr;  // ClapState (clap_host.inc)
@@ -350,7 +353,7 @@ int fad_destroy(fad_handle* h) {
     cudaSetDevice(h->device);
     clap_free_state(h->clap_state);
     void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
-                    h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal, h->frb_buf};
+                    h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal, h->frb_buf, h->rs_bank, h->rs_mono};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < 5; ++i) { if (h->conv_w[i]) cudaFree(h->conv_w[i]); if (h->conv_b[i]) cudaFree(h->conv_b[i]); }
     for (int i = 0; i < 3; ++i) { if (h->fc_w[i]) cudaFree(h->fc_w[i]); if (h->fc_b[i]) cudaFree(h->fc_b[i]); }
@@ -798,6 +801,7 @@ int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, c
 
 }  // extern "C"
 
+#include "resample_host.inc"
 #include "clap_host.inc"
 
 static void clap_free_state(void* p) { clap_free(reinterpret_cast<ClapState*>(p)); }

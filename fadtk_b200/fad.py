@@ -140,25 +140,21 @@ class FrechetAudioDistance:
             return synth.read_wav(new)[0]
         new.parent.mkdir(parents=True, exist_ok=True)
         if f.suffix.lower() == ".wav":
-            pcm, sr = synth.read_wav(f)
+            pcm, sr = synth.read_wav(f)          # int16 [T] or [T, channels]
             x = None
         else:
-            import torchaudio                    # needs a decoding backend (absent in this image)
-            x, sr = torchaudio.load(str(f))
+            import torchaudio                    # container decode only (needs a backend; absent in this image)
+            x, sr = torchaudio.load(str(f))      # float32 [channels, T]
             pcm = None
         if pcm is not None and pcm.ndim == 1 and sr == self.ml.sr:
             out = pcm                            # already mono PCM16 at the model rate: bit-exact copy
         else:
-            if x is None:
-                x = torch.from_numpy((pcm if pcm.ndim > 1 else pcm[:, None]).T.astype(np.float32) / 32768.0)
-            x = torch.mean(x, 0).unsqueeze(0)
-            if sr != self.ml.sr:
-                import torchaudio
-                resampler = torchaudio.transforms.Resample(
-                    sr, self.ml.sr, lowpass_filter_width=64, rolloff=0.9475937167399596,
-                    resampling_method="sinc_interp_kaiser", beta=14.769656459379492)
-                x = resampler(x)
-            out = torch.clamp(torch.round(x[0] * 32768.0), -32768, 32767).to(torch.int16).numpy()
+            # mono mix + Kaiser-sinc polyphase resampling + PCM16 quantisation on the GPU
+            # (fad_resample; same filter bank as the reference's torchaudio Resample, fad.py:150-160)
+            from . import _native
+            eng = _native.engine()
+            src = torch.from_numpy(np.array(pcm, copy=True)) if pcm is not None else x.to(torch.float32).contiguous()
+            out = eng.resample(src.to(eng.torch_device), int(sr), int(self.ml.sr)).cpu().numpy()
         synth.write_wav(new, out, self.ml.sr)
         return out
 

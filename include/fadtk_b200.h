@@ -160,6 +160,21 @@ int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, c
                         const void* emb_f16, const long long* offsets, long long n_items, int d, int iters,
                         double* out, void* stream);
 
+/* ---- audio conversion: replaces the torchaudio branch of FrechetAudioDistance.load_audio
+ * (fadtk/fad.py:147-160): mono mix (:150), Resample(lowpass_filter_width=64, rolloff=0.9475937167399596,
+ * sinc_interp_kaiser, beta=14.769656459379492) (:151-158), PCM16 quantisation (:160).
+ * fad_resample_geometry / _length / _bank are host-only (no GPU): reduced rates orig/new, filter
+ * half-width, taps = 2*width + orig; output length ceil(new*length/orig); the [new][taps] float32
+ * filter bank exactly as torchaudio builds it.
+ * fad_resample: exactly one of in_i16 (interleaved [length][channels], scaled by 1/32768) and in_f32
+ * (planar [channels][length]) is given (device); out_pcm int16 [fad_resample_length] (device);
+ * out_f32 optional un-quantised copy (device) or NULL. */
+int fad_resample_geometry(int sr_in, int sr_out, int* orig, int* new_, int* width, int* taps);
+long long fad_resample_length(int sr_in, int sr_out, long long length);
+int fad_resample_bank(int sr_in, int sr_out, float* bank_host);
+int fad_resample(fad_handle* h, const int16_t* in_i16, const float* in_f32, int channels, long long length,
+                 int sr_in, int sr_out, int16_t* out_pcm, float* out_f32, void* stream);
+
 /* ---- measurement ----------------------------------------------------------------------
  * When enabled, CUDA events are recorded on the launching stream around every kernel group;
  * fad_profile_collect synchronises the device and returns accumulated milliseconds and launch
