@@ -39,12 +39,14 @@ struct ConvGemmParams {
     int img_groups;            // ceil(NB / box_n)
     int n_tiles;               // Cout / N_TILE
     int H, W, NB, Cout;
+    float lo_scale;            // WMODE 2: 2^-s of the E4M3 low parts
     int ld_out, n_valid;       // un-pooled outputs: row stride and number of columns actually stored
                                // (Cout is padded to the tile width; columns >= n_valid are dropped)
     int relu, pool;            // relu: 0 = none, 1 = ReLU, 2 = GELU (erf form)
     const float* bias;         // [Cout]
     __half* out;               // NHWC fp16 [NB, H(/2), W(/2), Cout]; may be null when out_f32 is set
     float* out_f32;            // optional fp32 copy of the un-pooled output (may be null)
+    uint8_t* out8;             // optional E4M3 copy of `out` (same layout) for a WMODE 2 consumer (may be null)
     // optional fused residual update (transformer blocks): resid[token(row)][0:resid_C] += result,
     // where row -> token undoes the (shifted-)window ordering of the rows (resid_res = 0: identity)
     float* resid;
@@ -80,14 +82,20 @@ constexpr uint32_t kStagingBytes = 32 * 128;       // per epilogue warp: 32 rows
 // whereas fp16 activations cost 2e-5.  The hi and lo rows of one N tile are stored back to back
 // ([Wh: N_TILE rows | Wl: N_TILE rows] per tile), so ONE TMA box brings both and the MMA warp
 // issues A x Wh and A x Wl into the same TMEM accumulator.
-template <int N_TILE, bool SPLIT_W>
+// WMODE 0: fp16 weights.  1: fp16 hi/lo pair, two kind::f16 MMAs per K step.  2: fp16 hi + E4M3 lo:
+// the low part (|Wl| <= 2^-11 |W|, needed to ~4 bits) is applied by a kind::f8f6f4 MMA - twice the
+// rate and half the operand bytes of a second fp16 MMA - against an E4M3 copy of the activation
+// (written next to the fp16 one by the producing kernel, fetched by its own TMA box), into its own
+// TMEM accumulator that the epilogue adds with the power-of-two scale of the E4M3 weights.
+template <int N_TILE, int WMODE>
 __host__ __device__ constexpr uint32_t conv_gemm_stage_bytes() {
-    return kABytes + (SPLIT_W ? 2 : 1) * N_TILE * kBlockK * 2;
+    return WMODE == 2 ? kABytes + N_TILE * kBlockK * 2 + N_TILE * kBlockK + kTileM * kBlockK
+                      : kABytes + (WMODE == 1 ? 2 : 1) * N_TILE * kBlockK * 2;
 }
 
-template <int N_TILE, int STAGES, bool SPLIT_W>
+template <int N_TILE, int STAGES, int WMODE>
 __host__ __device__ constexpr uint32_t conv_gemm_smem_bytes() {
-    return STAGES * conv_gemm_stage_bytes<N_TILE, SPLIT_W>() + 1024 /*align slack*/ + 256 /*barriers*/
+    return STAGES * conv_gemm_stage_bytes<N_TILE, WMODE>() + 1024 /*align slack*/ + 256 /*barriers*/
          + kEpilogueWarps * kStagingBytes;
 }
 
@@ -114,22 +122,42 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + copysignf(1.0f - e, x));
 }
 
+// 8 halves -> 8 E4M3 bytes (round to nearest, saturate)
+__device__ __forceinline__ uint32_t f16x4_to_e4m3x4(uint32_t a, uint32_t b) {
+    __half2_raw h0, h1;
+    h0.x = (unsigned short)(a & 0xffffu); h0.y = (unsigned short)(a >> 16);
+    h1.x = (unsigned short)(b & 0xffffu); h1.y = (unsigned short)(b >> 16);
+    return (uint32_t)__nv_cvt_halfraw2_to_fp8x2(h0, __NV_SATFINITE, __NV_E4M3)
+         | ((uint32_t)__nv_cvt_halfraw2_to_fp8x2(h1, __NV_SATFINITE, __NV_E4M3) << 16);
+}
+__device__ __forceinline__ uint2 f16x8_to_e4m3x8(uint4 v) {
+    return make_uint2(f16x4_to_e4m3x4(v.x, v.y), f16x4_to_e4m3x4(v.z, v.w));
+}
+
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int N_TILE, int STAGES, bool SPLIT_W>
+template <int N_TILE, int STAGES, int WMODE>
 __global__ void __launch_bounds__(kConvGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                  const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_wl8,       // WMODE 2: E4M3 low parts [Cout, K]
+                 const __grid_constant__ CUtensorMap map_x8,        // WMODE 2: E4M3 copy of the activation
                  const ConvGemmParams p)
 {
     using namespace sm100;
-    constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE, SPLIT_W>();
-    constexpr int kBRows = (SPLIT_W ? 2 : 1) * N_TILE;              // rows of the weight box per tile
-    constexpr uint32_t kTmemCols = 2 * N_TILE;          // two chunk buffers
+    constexpr bool SPLIT_W = WMODE == 1;
+    constexpr bool LO8 = WMODE == 2;
+    constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE, WMODE>();
+    constexpr int kBRows = (WMODE != 0 ? 2 : 1) * N_TILE;           // rows of the packed weight tensor per N tile
+    constexpr uint32_t kTmemCols = (LO8 ? 4 : 2) * N_TILE;          // two chunk buffers (+ two low-part buffers)
     constexpr uint32_t kIdesc = make_idesc(FMT_F16, kTileM, N_TILE);
+    constexpr uint32_t kIdesc8 = make_idesc(FMT_E4M3, kTileM, N_TILE);
+    constexpr uint32_t kWhBytes = N_TILE * kBlockK * 2;
+    constexpr uint32_t kOffWl8 = kABytes + kWhBytes;                // stage layout (LO8): A16 | Wh | Wl8 | A8
+    constexpr uint32_t kOffA8 = kOffWl8 + N_TILE * kBlockK;
     constexpr int kColsPerWarp = N_TILE / 2;            // each lane quarter is shared by two warps
     constexpr int kGroups = kColsPerWarp / 32;
 
@@ -140,7 +168,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     uint64_t* empty = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* corr_empty = bars + 2 * STAGES + 4;                    // LO8: low-part accumulator drained
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
     uint8_t* staging = smem + STAGES * kStageBytes + 256;            // kEpilogueWarps x kStagingBytes
 
     const int warp = threadIdx.x >> 5;
@@ -154,10 +183,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
+        if (LO8) { tma_prefetch_desc(&map_wl8); tma_prefetch_desc(&map_x8); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpilogueWarps); }
+        for (int a = 0; a < 2; ++a) mbar_init(&corr_empty[a], kEpilogueWarps);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_base_slot);
@@ -190,6 +221,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     uint8_t* st = smem + s * kStageBytes;
                     tma_load_4d(st, &map_x, &full[s], cb * kBlockK, w0 + dw, h0 + dh, n0);
                     tma_load_2d(st + kABytes, &map_w, &full[s], ks * kBlockK, nt * kBRows);
+                    if (LO8) {
+                        tma_load_2d(st + kOffWl8, &map_wl8, &full[s], ks * kBlockK, nt * N_TILE);
+                        tma_load_4d(st + kOffA8, &map_x8, &full[s], cb * kBlockK, w0 + dw, h0 + dh, n0);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -199,7 +234,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
         if (elect_one()) {
             int s = 0; uint32_t ph = 0;
             int buf = 0; uint32_t buf_ph = 0;
+            int cpar = 0; uint32_t cpar_ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const uint32_t d_corr = tmem_base + 2 * N_TILE + cpar * N_TILE;
+                if (LO8) { mbar_wait(&corr_empty[cpar], cpar_ph ^ 1); tc_fence_after_sync(); }
                 for (int ks0 = 0; ks0 < ksteps; ks0 += chunk_len) {
                     const int ks1 = min(ks0 + chunk_len, ksteps);
                     mbar_wait(&tmem_empty[buf], buf_ph ^ 1);
@@ -218,12 +256,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                             if (SPLIT_W)      // lo half of the weights: N_TILE rows (x 128 B) further down the stage
                                 umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k + (N_TILE * 128 / 16), kIdesc, 1);
                         }
+                        if (LO8) {
+                            const uint64_t a8_desc = kmajor_sw64_desc(a_addr + kOffA8);
+                            const uint64_t w8_desc = kmajor_sw64_desc(a_addr + kOffWl8);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 32; ++k)   // K = 32 per kind::f8f6f4 MMA, +32 B inside the 64-B atom
+                                umma_f8(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, (ks > 0) || (k > 0));
+                        }
                         umma_commit(&empty[s]);           // smem slot free once these MMAs retire
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                     umma_commit(&tmem_full[buf]);         // chunk complete -> epilogue warps
                     if (++buf == 2) { buf = 0; buf_ph ^= 1; }
                 }
+                if (++cpar == 2) { cpar = 0; cpar_ph ^= 1; }
             }
         }
       }
@@ -238,6 +284,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
         const int phh = (r / bw) % bh;
         const int pn = r / (bw * bh);
         int buf = 0; uint32_t buf_ph = 0;
+        int cpar = 0;
         // plain row-major GEMM (1x1 "image", 128 rows per tile): no per-tile divisions
         const bool plain = p.tiles_w == 1 && p.tiles_h == 1 && bw == 1 && bh == 1;
         int nt = blockIdx.x % p.n_tiles, m = blockIdx.x / p.n_tiles;
@@ -285,12 +332,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(v[j]);
                     }
+                    if (LO8 && c == n_chunks - 1) {           // + A8 * Wl8^T / 2^s: complete once the last chunk is
+                        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + 2 * N_TILE + cpar * N_TILE + half * kColsPerWarp + g * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = fmaf(__uint_as_float(v[j]), p.lo_scale, acc[g * 32 + j]);
+                    }
                 }
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                if (lane == 0) {
+                    mbar_arrive(&tmem_empty[buf]);
+                    if (LO8 && c == n_chunks - 1) mbar_arrive(&corr_empty[cpar]);
+                }
                 if (++buf == 2) { buf = 0; buf_ph ^= 1; }
             }
+            cpar ^= 1;
 
             const int ch0 = nt * N_TILE + half * kColsPerWarp;
             // Destination of this lane's row (element offsets, -1 = row beyond the batch).  Stores go
@@ -396,7 +453,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                                 const int rr = it * 4 + rq;
                                 const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
                                 const long long off = __shfl_sync(0xffffffffu, out_off, rr);
-                                if (off >= 0 && col < p.n_valid) *reinterpret_cast<uint4*>(p.out + off + col) = v;
+                                if (off >= 0 && col < p.n_valid) {
+                                    *reinterpret_cast<uint4*>(p.out + off + col) = v;
+                                    if (p.out8 != nullptr) *reinterpret_cast<uint2*>(p.out8 + off + col) = f16x8_to_e4m3x8(v);
+                                }
                             }
                             __syncwarp();
                         }
@@ -420,6 +480,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     if (valid) {
                         const size_t pix = (size_t(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
                         *reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch0 + g * 32 + sub * 8) = o;
+                        if (p.out8 != nullptr) *reinterpret_cast<uint2*>(p.out8 + pix * p.Cout + ch0 + g * 32 + sub * 8) = f16x8_to_e4m3x8(o);
                     }
                 }
             }

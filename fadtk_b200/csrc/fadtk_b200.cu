@@ -5,10 +5,13 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -74,12 +77,19 @@ int encode_f16_map(CUtensorMap* map, const void* base, int rank, const uint64_t*
 struct LayerGeom {
     int taps, Cin, Cout, H, W, relu, pool;
     int box_w, box_h, box_n, n_tile;
-    int split_w;      // weights are an fp16 hi/lo pair, interleaved per 128-row tile
+    int split_w;      // 0: fp16 weights; 1: fp16 hi/lo pair (interleaved per 128-row tile), two fp16 MMAs;
+                      // 2: same packed tensor, low part applied as E4M3 (kind::f8f6f4) - see conv_gemm.cuh
 };
+
+// how the low part of split weights is applied: FADTK_WLO=fp16 (two fp16 MMAs) | fp8 (E4M3 correction MMA)
+int wlo_mode() {
+    static const int mode = [] { const char* e = getenv("FADTK_WLO"); return (e && std::string(e) == "fp8") ? 2 : 1; }();
+    return mode;
+}
 
 int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu, int pool, int split_w) {
     g.taps = taps; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.relu = relu; g.pool = pool;
-    g.split_w = split_w ? 1 : 0;
+    g.split_w = split_w;                     // 0, 1 or 2 - the caller decides (wlo_mode() for the VGGish pipeline)
     if (Cin % 64 != 0) return fail("Cin must be a multiple of 64");
     if (taps != 1 && taps != 9) return fail("taps must be 1 or 9");
     if (H == 1 && W == 1) { g.box_w = 1; g.box_h = 1; g.box_n = 128; }
@@ -123,7 +133,9 @@ struct fad_handle {
     __half* act[9] = {};       // act[0]=conv1 out ... act[5]=conv6 out (flattened), act[6..7]=fc1, fc2 out
 
     // per-layer cached descriptors for the fixed VGGish pipeline
-    CUtensorMap map_x[8], map_w[8];
+    CUtensorMap map_x[8], map_w[8], map_x8[8];
+    uint8_t* act8[8] = {};     // E4M3 copies of act[0..7] (inputs of the 8 tensor-core layers) when the low parts run in fp8
+    uint8_t* x8_scratch = nullptr;  size_t x8_scratch_cap = 0;   // fad_umma_layer (stage test) only
     LayerGeom geom[8];
 
     // statistics workspace
@@ -139,6 +151,8 @@ struct fad_handle {
     size_t frb_cap = 0;
     float* rs_bank = nullptr;  size_t rs_bank_cap = 0;  int rs_in = 0, rs_out = 0;     // resampler filter bank
     float* rs_mono = nullptr;  size_t rs_mono_cap = 0;
+    struct Lo8 { uint8_t* w8; float inv_scale; };
+    std::map<const void*, Lo8> lo8;          // E4M3 low parts per packed weight tensor (built on first use)
     double* fr_scal = nullptr;   // 32 doubles
 
     void* clap_state = nullptr;  // ClapState (clap_host.inc)
@@ -155,12 +169,12 @@ struct fad_handle {
 
 namespace {
 
-template <int N_TILE, int STAGES, bool SPLIT_W>
-int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw,
-                     const fad::ConvGemmParams& p, cudaStream_t st) {
+template <int N_TILE, int STAGES, int WMODE>
+int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mw8,
+                     const CUtensorMap& mx8, const fad::ConvGemmParams& p, cudaStream_t st) {
     static bool attr_set = false;
-    constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES, SPLIT_W>();
-    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, SPLIT_W>;
+    constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES, WMODE>();
+    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, WMODE>;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -168,7 +182,7 @@ int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw
     const int total = p.img_groups * p.tiles_h * p.tiles_w * p.n_tiles;
     if (total == 0) return 0;
     const int grid = total < h->num_sms ? total : h->num_sms;
-    kern<<<grid, fad::kConvGemmThreads, smem, st>>>(mx, mw, p);
+    kern<<<grid, fad::kConvGemmThreads, smem, st>>>(mx, mw, mw8, mx8, p);
     CK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -187,13 +201,35 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
     const uint64_t rows_mul = g.split_w ? 2 : 1;
     const uint64_t wd[2] = {K, (uint64_t)g.Cout * rows_mul};
     const uint64_t ws[1] = {K * 2};
-    const uint32_t wb[2] = {64, (uint32_t)(g.n_tile * rows_mul)};
+    const uint32_t wb[2] = {64, (uint32_t)(g.n_tile * (g.split_w == 1 ? 2 : 1))};   // mode 2 fetches the hi rows only
     return encode_f16_map(mw, w, 2, wd, ws, wb);
 }
 
-int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CUtensorMap& mw,
+int lo8_for(fad_handle* h, const LayerGeom& g, const void* w, CUtensorMap* mw8, float* inv_scale, cudaStream_t st);
+// the E4M3 low parts are cached per weight POINTER: drop the entry whenever that memory is rewritten
+void lo8_forget(fad_handle* h, const void* w) {
+    auto it = h->lo8.find(w);
+    if (it != h->lo8.end()) { cudaFree(it->second.w8); h->lo8.erase(it); }
+}
+
+// E4M3 copy of an NHWC activation: same box geometry as the fp16 map, 64-B rows, SWIZZLE_64B
+int encode_x8_map(const LayerGeom& g, const void* x8, long long nb_dim, CUtensorMap* mx8) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)nb_dim};
+    cuuint64_t gstr[3] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W * g.Cin, (cuuint64_t)g.H * g.W * g.Cin};
+    cuuint32_t bdim[4] = {64, (cuuint32_t)g.box_w, (cuuint32_t)g.box_h, (cuuint32_t)g.box_n}, estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(mx8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x8), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (E4M3 activation) failed");
+    return 0;
+}
+
+int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CUtensorMap& mw, const void* w,
               int NB, const float* bias, void* out, float* out_f32, cudaStream_t st,
-              float* resid = nullptr, int resid_C = 0, int resid_res = 0, int resid_shift = 0, int n_valid = 0) {
+              float* resid = nullptr, int resid_C = 0, int resid_res = 0, int resid_shift = 0, int n_valid = 0,
+              const CUtensorMap* mx8 = nullptr, uint8_t* out8 = nullptr) {
     fad::ConvGemmParams p;
     p.taps = g.taps; p.cblks = g.Cin / 64;
     p.box_w = g.box_w; p.box_h = g.box_h; p.box_n = g.box_n;
@@ -204,11 +240,83 @@ int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CU
     p.n_valid = n_valid > 0 ? n_valid : g.Cout;
     p.ld_out = p.n_valid;
     p.relu = g.relu; p.pool = g.pool;
-    p.bias = bias; p.out = reinterpret_cast<__half*>(out); p.out_f32 = out_f32;
+    p.bias = bias; p.out = reinterpret_cast<__half*>(out); p.out_f32 = out_f32; p.out8 = out8;
     p.resid = resid; p.resid_C = resid_C; p.resid_res = resid_res; p.resid_shift = resid_shift;
-    if (g.split_w) return launch_conv_gemm<128, 4, true>(h, mx, mw, p, st);
-    if (g.n_tile == 256) return launch_conv_gemm<256, 4, false>(h, mx, mw, p, st);
-    return launch_conv_gemm<128, 6, false>(h, mx, mw, p, st);
+    p.lo_scale = 0.0f;
+    if (g.split_w == 2) {
+        if (mx8 == nullptr) return fail("fp8 low-part mode needs the E4M3 copy of the activation");
+        CUtensorMap mw8;
+        if (lo8_for(h, g, w, &mw8, &p.lo_scale, st)) return 1;
+        return launch_conv_gemm<128, 4, 2>(h, mx, mw, mw8, *mx8, p, st);
+    }
+    if (g.split_w) return launch_conv_gemm<128, 4, 1>(h, mx, mw, mw, mx, p, st);
+    if (g.n_tile == 256) return launch_conv_gemm<256, 4, 0>(h, mx, mw, mw, mx, p, st);
+    return launch_conv_gemm<128, 6, 0>(h, mx, mw, mw, mx, p, st);
+}
+
+// E4M3 copy of the low parts of a packed hi/lo weight tensor, scaled by a power of two so the largest
+// |Wl| lands near 224 (E4M3 max 448), plus its tensor map (64-B rows, SWIZZLE_64B).  Built once per tensor.
+__global__ void wlo_absmax_kernel(const __half* __restrict__ w, long long n_tiles, long long K, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    const long long total = n_tiles * 128 * K;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / K, k = e - row * K;
+        const long long t = row >> 7, j = row & 127;
+        m = fmaxf(m, fabsf(__half2float(w[((t * 256 + 128 + j) * K) + k])));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+__global__ void wlo_to_e4m3_kernel(const __half* __restrict__ w, long long n_tiles, long long K, float scale, uint8_t* __restrict__ out) {
+    const long long total = n_tiles * 128 * K;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / K, k = e - row * K;
+        const long long t = row >> 7, j = row & 127;
+        const float v = __half2float(w[((t * 256 + 128 + j) * K) + k]) * scale;
+        out[e] = (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+    }
+}
+
+__global__ void f16_to_e4m3_kernel(const __half* __restrict__ x, size_t count, uint8_t* __restrict__ out) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x)
+        out[e] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(x[e]), __NV_SATFINITE, __NV_E4M3);
+}
+
+int lo8_for(fad_handle* h, const LayerGeom& g, const void* w, CUtensorMap* mw8, float* inv_scale, cudaStream_t st) {
+    const long long K = (long long)g.taps * g.Cin, n_tiles = g.Cout / 128;
+    auto it = h->lo8.find(w);
+    if (it == h->lo8.end()) {
+        unsigned int* d_max = nullptr;
+        uint8_t* w8 = nullptr;
+        CK(cudaMalloc(&d_max, 4));
+        CK(cudaMalloc(&w8, (size_t)(n_tiles * 128 * K)));
+        CK(cudaMemsetAsync(d_max, 0, 4, st));
+        const unsigned blocks = (unsigned)std::min<long long>((n_tiles * 128 * K + 255) / 256, (long long)h->num_sms * 16);
+        wlo_absmax_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(w), n_tiles, K, d_max);
+        float mx = 0.f;
+        CK(cudaMemcpyAsync(&mx, d_max, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int e = 0;
+        if (mx > 0.f) e = (int)std::floor(std::log2(224.0f / mx));
+        if (e > 100) e = 100;
+        const float scale = std::ldexp(1.0f, e);
+        wlo_to_e4m3_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(w), n_tiles, K, scale, w8);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        cudaFree(d_max);
+        it = h->lo8.emplace(w, fad_handle::Lo8{w8, 1.0f / scale}).first;
+    }
+    *inv_scale = it->second.inv_scale;
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)(n_tiles * 128)};
+    cuuint64_t gstr[1] = {(cuuint64_t)K};
+    cuuint32_t bdim[2] = {64, 128}, estr[2] = {1, 1};
+    CUresult r = fn(mw8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, it->second.w8, gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (E4M3 low parts) failed");
+    return 0;
 }
 
 // VGGish layer table: H, W are the conv's spatial size (input == un-pooled output)
@@ -355,9 +463,12 @@ int fad_destroy(fad_handle* h) {
     void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
                     h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal, h->frb_buf, h->rs_bank, h->rs_mono};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& kv : h->lo8) cudaFree(kv.second.w8);
     for (int i = 0; i < 5; ++i) { if (h->conv_w[i]) cudaFree(h->conv_w[i]); if (h->conv_b[i]) cudaFree(h->conv_b[i]); }
     for (int i = 0; i < 3; ++i) { if (h->fc_w[i]) cudaFree(h->fc_w[i]); if (h->fc_b[i]) cudaFree(h->fc_b[i]); }
     for (int i = 0; i < 9; ++i) if (h->act[i]) cudaFree(h->act[i]);
+    for (int i = 0; i < 8; ++i) if (h->act8[i]) cudaFree(h->act8[i]);
+    if (h->x8_scratch) cudaFree(h->x8_scratch);
     delete h;
     return 0;
 }
@@ -370,8 +481,9 @@ int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
     CK(cudaSetDevice(h->device));
     auto up = [&](void** dst, const void* src, size_t bytes) -> int {
         if (!src) return fail("missing weight pointer");
-        if (*dst) { cudaFree(*dst); *dst = nullptr; }          // sizes depend on split_mask
+        if (*dst) { lo8_forget(h, *dst); cudaFree(*dst); *dst = nullptr; }          // sizes depend on split_mask
         CK(cudaMalloc(dst, bytes));
+        lo8_forget(h, *dst);
         CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
         return 0;
     };
@@ -397,9 +509,13 @@ int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
     // batch are never scheduled and rows past it are masked in the epilogue)
     for (int i = 0; i < 8; ++i) {
         const VggLayer& L = kVgg[i];
-        if (make_geom(h->geom[i], L.H, L.W, L.Cin, L.Cout, L.taps, L.relu, L.pool, (w->split_mask >> i) & 1)) return 1;
+        if (make_geom(h->geom[i], L.H, L.W, L.Cin, L.Cout, L.taps, L.relu, L.pool, ((w->split_mask >> i) & 1) ? wlo_mode() : 0)) return 1;
         const void* wptr = i < 5 ? (const void*)h->conv_w[i] : (const void*)h->fc_w[i - 5];
         if (encode_layer_maps(h->geom[i], h->act[i], (long long)B, wptr, &h->map_x[i], &h->map_w[i])) return 1;
+        if (h->geom[i].split_w == 2) {
+            if (!h->act8[i]) CK(cudaMalloc(&h->act8[i], B * kActElems[i]));
+            if (encode_x8_map(h->geom[i], h->act8[i], (long long)B, &h->map_x8[i])) return 1;
+        }
     }
     h->vgg_loaded = true;
     return 0;
@@ -465,7 +581,7 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
         if (launch_logmel(h, pcm, ex_start + base, nb, h->logmel, fe_double, st)) return 1;
         prof_end(h, FAD_PROF_LOGMEL, ev, st);
         ev = prof_begin(h, st);
-        fad::conv1_kernel<<<dim3(6, nb), 256, 0, st>>>(h->logmel, h->conv1_w, h->conv1_b, h->act[0]);
+        fad::conv1_kernel<<<dim3(6, nb), 256, 0, st>>>(h->logmel, h->conv1_w, h->conv1_b, h->act[0], h->act8[0]);
         CK(cudaGetLastError());
         h->launches++;
         prof_end(h, FAD_PROF_CONV1, ev, st);
@@ -473,7 +589,8 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
             const float* bias = i < 5 ? h->conv_b[i] : h->fc_b[i - 5];
             void* out = (i == 7) ? (void*)((__half*)emb_out_f16 + (size_t)base * 128) : (void*)h->act[i + 1];
             ev = prof_begin(h, st);
-            if (run_layer(h, h->geom[i], h->map_x[i], h->map_w[i], nb, bias, out, nullptr, st)) return 1;
+            if (run_layer(h, h->geom[i], h->map_x[i], h->map_w[i], (i < 5 ? (const void*)h->conv_w[i] : (const void*)h->fc_w[i - 5]), nb, bias, out, nullptr, st,
+                          nullptr, 0, 0, 0, 0, h->geom[i].split_w == 2 ? &h->map_x8[i] : nullptr, i < 7 ? h->act8[i + 1] : nullptr)) return 1;
             prof_end(h, FAD_PROF_LAYER0 + i, ev, st);
         }
     }
@@ -488,9 +605,19 @@ int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int C
     LayerGeom g;
     if (make_geom(g, H, W, Cin, Cout, taps, relu, pool, split_w)) return 1;
     if (pool && out_f32_or_null) return fail("fp32 copy is only available for un-pooled layers");
-    CUtensorMap mx, mw;
+    CUtensorMap mx, mw, mx8;
     if (encode_layer_maps(g, x_f16, NB, w_f16, &mx, &mw)) return 1;
-    return run_layer(h, g, mx, mw, NB, bias, out_f16, out_f32_or_null, (cudaStream_t)stream);
+    if (g.split_w == 2) {                    // stage test entry: make the E4M3 copy a producer would have written
+        lo8_forget(h, w_f16);                // caller-owned weights: never trust a cached conversion
+        const size_t count = (size_t)NB * H * W * Cin;
+        if (ensure((void**)&h->x8_scratch, &h->x8_scratch_cap, count)) return 1;
+        f16_to_e4m3_kernel<<<(unsigned)std::min<size_t>((count / 8 + 255) / 256 + 1, (size_t)h->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const __half*>(x_f16), count, h->x8_scratch);
+        CK(cudaGetLastError());
+        if (encode_x8_map(g, h->x8_scratch, NB, &mx8)) return 1;
+    }
+    return run_layer(h, g, mx, mw, w_f16, NB, bias, out_f16, out_f32_or_null, (cudaStream_t)stream,
+                     nullptr, 0, 0, 0, 0, g.split_w == 2 ? &mx8 : nullptr, nullptr);
 }
 
 // -------------------------------------------------------------------------- statistics

@@ -15,6 +15,7 @@
 //                  for the tensor pipe); writes NHWC fp16 [B, 48, 32, 64] for the tcgen05 layers.
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace fad {
@@ -180,7 +181,8 @@ logmel_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ ex_
 // over pooled pixels of an 8-row strip; the fp32 input strip (with halo) sits in smem.
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ logmel /*[B,96,64]*/, const float* __restrict__ w /*[64,9]*/,
-             const float* __restrict__ bias, __half* __restrict__ out /*[B,48,32,64]*/)
+             const float* __restrict__ bias, __half* __restrict__ out /*[B,48,32,64]*/,
+             uint8_t* __restrict__ out8 /* optional E4M3 copy of `out` (fp8 low-part mode of conv2), may be null */)
 {
     __shared__ float tile[18][68];
     const int e = blockIdx.y, strip = blockIdx.x;          // strip: pooled rows [8*strip, 8*strip+8)
@@ -224,7 +226,11 @@ conv1_kernel(const float* __restrict__ logmel /*[B,96,64]*/, const float* __rest
             }
         m0 = fmaxf(m0 + b0, 0.f); m1 = fmaxf(m1 + b1, 0.f);
         const size_t pix = ((size_t)e * 48 + strip * 8 + py) * 32 + px;
-        *reinterpret_cast<__half2*>(out + pix * 64 + 2 * lane) = __floats2half2_rn(m0, m1);
+        const __half2 hv = __floats2half2_rn(m0, m1);
+        *reinterpret_cast<__half2*>(out + pix * 64 + 2 * lane) = hv;
+        if (out8 != nullptr)                               // E4M3 of the fp16 value the next layer sees
+            *reinterpret_cast<unsigned short*>(out8 + pix * 64 + 2 * lane) =
+                __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hv), __NV_SATFINITE, __NV_E4M3);
     }
 }
 

@@ -157,6 +157,10 @@ __device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t saddr) {
     return make_smem_desc(saddr, 16, 1024, SWZ_128B);
 }
 
+// K-major tile of 8-bit elements with 64-B rows (64 elements), SWIZZLE_64B: 8-row atoms of 512 B.
+__device__ __forceinline__ uint64_t kmajor_sw64_desc(uint32_t saddr) {
+    return make_smem_desc(saddr, 16, 512, SWZ_64B);
+}
 // MN-major operand tile, SWIZZLE_128B, 16-bit elements: each K row holds 64 contiguous
 // M/N elements (128 B); 8 K-rows form a 1024-B atom.  SBO = stride between 8-row K groups
 // (1024 B when the groups are dense), LBO = stride between successive 64-element blocks
@@ -174,6 +178,17 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint
                                                   uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16)
          | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// kind::f8f6f4 operand formats (instruction descriptor a_format / b_format)
+enum : uint32_t { FMT_E4M3 = 0, FMT_E5M2 = 1 };
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread for the whole CTA.

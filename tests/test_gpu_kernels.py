@@ -61,7 +61,7 @@ LAYERS = [
 ]
 
 
-@pytest.mark.parametrize("split_w", [False, True])
+@pytest.mark.parametrize("split_w", [0, 1, 2])          # fp16 weights | fp16 hi/lo | fp16 hi + E4M3 lo (kind::f8f6f4)
 @pytest.mark.parametrize("nb,hh,ww,cin,cout,taps,relu,pool", LAYERS)
 def test_umma_layer_matches_fp32_reference(engine, nb, hh, ww, cin, cout, taps, relu, pool, split_w):
     torch.backends.cudnn.allow_tf32 = False
