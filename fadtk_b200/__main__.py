@@ -41,7 +41,7 @@ def main():
     for d in [baseline, eval]:
         if Path(d).is_dir():
             cache_embedding_files(d, model, workers=args.workers)
-    if dist.rank() != 0:
+    if dist.rank() != 0 and not (args.inf or args.indiv):     # plain FAD: rank 0 scores; --inf / --indiv shard their work
         dist.shutdown()
         return
 
@@ -49,14 +49,19 @@ def main():
     fad = FrechetAudioDistance(model, audio_load_worker=args.workers, load_model=False)
     if args.inf:
         assert Path(eval).is_dir(), "FAD-inf requires a directory as the evaluation dataset"
-        score = fad.score_inf(baseline, list(Path(eval).glob('*.*')))
+        score = fad.score_inf(baseline, sorted(Path(eval).glob('*.*')))
+        if dist.rank() != 0:
+            dist.shutdown()
+            return
         print("FAD-inf Information:", score)
         score, inf_r2 = score.score, score.r2
     elif args.indiv:
         assert Path(eval).is_dir(), "Individual FAD requires a directory as the evaluation dataset"
         csv_path = Path(args.csv or 'fad-individual-results.csv')
         fad.score_individual(baseline, eval, csv_path)
-        log.info(f"Individual FAD scores saved to {csv_path}")
+        if dist.rank() == 0:
+            log.info(f"Individual FAD scores saved to {csv_path}")
+        dist.shutdown()
         exit(0)
     else:
         score = fad.score(baseline, eval)

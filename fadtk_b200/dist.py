@@ -71,6 +71,16 @@ def allgather_objects(obj):
     return out
 
 
+def broadcast_int64(arr, src: int = 0):
+    """numpy int64 array from rank ``src`` to every rank (FAD-inf bootstrap indices: one RNG stream)."""
+    if not is_distributed():
+        return arr
+    dev = torch.device("cuda", torch.cuda.current_device()) if td.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(dev)
+    td.broadcast(t, src=src)
+    return t.cpu().numpy()
+
+
 def barrier():
     if is_distributed():
         td.barrier()

@@ -270,15 +270,25 @@ class FrechetAudioDistance:
             base.mu_host = np.asarray(mu_base, dtype=np.float64)
             emb_dev = torch.from_numpy(np.ascontiguousarray(embeds)).to(eng.torch_device)
 
+        # Multi-GPU: the bootstrap sizes are independent.  Rank 0 owns the host RNG stream (so a seeded run
+        # reproduces the reference's np.random.choice sequence, fad.py:333) and broadcasts every index
+        # array; step i is evaluated by rank i mod world and the points are gathered.
+        from . import dist
+        world, me = dist.world_size(), dist.rank()
         results = []
-        for n in ns:
-            indices = np.random.choice(embeds.shape[0], size=n, replace=True)
+        for step, n in enumerate(ns):
+            indices = np.random.choice(embeds.shape[0], size=n, replace=True) if me == 0 else np.empty(n, dtype=np.int64)
+            indices = dist.broadcast_int64(indices)
+            if step % world != me:
+                continue
             if fp16_rows:
                 fad_score = _device_score(base, emb_dev, eng, torch.from_numpy(indices).to(eng.torch_device))
             else:
                 mu_eval, cov_eval = calc_embd_statistics(embeds[indices])
                 fad_score = calc_frechet_distance(mu_base, cov_base, mu_eval, cov_eval)
             results.append([n, fad_score])
+        if world > 1:
+            results = sorted((p for part in dist.allgather_objects(results) for p in part), key=lambda p: p[0])
 
         ys = np.array(results)
         xs = 1 / np.array(ns)
@@ -314,7 +324,9 @@ class FrechetAudioDistance:
                 traceback.print_exc()
                 _report(f, e)
 
-        _files = list(Path(eval_dir).glob("*.*"))
+        from . import dist
+        all_files = sorted(Path(eval_dir).glob("*.*"))
+        _files = list(dist.shard(all_files))               # multi-GPU: songs are independent, shard them
         scores: list = [None] * len(_files)
         # fp16 caches (what the reference writes, model_loader.py:47-48): one ragged batch, every song's
         # statistics and Frechet chain in lock-step on the device (fad_frechet_batched)
@@ -348,6 +360,10 @@ class FrechetAudioDistance:
                     scores[i] = fad_k
 
         pairs = [p for p in zip(_files, scores) if p[1] is not None]
+        if dist.is_distributed():
+            pairs = [p for part in dist.allgather_objects(pairs) for p in part]
+            if dist.rank() != 0:
+                return csv                                 # rank 0 writes the file
         pairs = sorted(pairs, key=lambda x: np.abs(x[1]))
         csv.parent.mkdir(parents=True, exist_ok=True)
         csv.write_text("\n".join([",".join([str(x).replace(',', '_') for x in row]) for row in pairs]))
