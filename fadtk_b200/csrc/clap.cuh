@@ -256,53 +256,75 @@ clap_patch_embed_kernel(const float* __restrict__ lm, const int* __restrict__ fr
 
 // mode 0: rows in (shifted-)window order; mode 1: patch-merge gather (output row = (b, i, j) on the
 // res/2 grid, features = [x(2i,2j), x(2i+1,2j), x(2i,2j+1), x(2i+1,2j+1)], LayerNorm over 4C).
-// One warp per output row, the row lives in registers (EPL = width / 32 values per lane, read once).
+// L lanes per row, 32 / L rows per warp; every lane keeps CHUNKS float4 pieces of its row in registers
+// (piece j of lane l = elements 4 (l + L j) ...), so loads are 16-B and stores 8-B per lane, fully
+// coalesced, and a warp has 32/L rows in flight (width = 4 L CHUNKS: 96 -> <3,8>, 192 -> <3,16>, ...).
 // out: fp16 [rows, ld_out] (columns >= width zero filled).
-template <int EPL>
+template <int CHUNKS, int L>
 __global__ void __launch_bounds__(256)
 clap_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                long long n_rows, int C, int ld_out, int res, int shift, int mode, __half* __restrict__ out)
 {
+    constexpr int R = 32 / L;                                      // rows per warp
+    constexpr int width = 4 * L * CHUNKS;
     const int lane = threadIdx.x & 31;
-    const long long o = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (o >= n_rows) return;
-    constexpr int width = EPL * 32;
-    float v[EPL];
-    if (mode == 0) {
-        const float* src = x + window_row_to_token(o, res, shift) * C;
+    const int li = lane % L;
+    const long long o = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R + lane / L;
+    const bool live = o < n_rows;
+    float4 v[CHUNKS];
+    if (live) {
+        if (mode == 0) {
+            const float4* src = reinterpret_cast<const float4*>(x + window_row_to_token(o, res, shift) * C);
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) v[k] = src[lane + 32 * k];
-    } else {
-        const int half = res >> 1;
-        const int jx = (int)(o % half);
-        const int iy = (int)((o / half) % half);
-        const long long b = o / ((long long)half * half);
-        const float* base = x + ((b * res + 2 * iy) * res + 2 * jx) * C;
-        // concat order x0 | x1 | x2 | x3 = (2i,2j) (2i+1,2j) (2i,2j+1) (2i+1,2j+1); C is a multiple of 32
+            for (int j = 0; j < CHUNKS; ++j) v[j] = src[li + L * j];
+        } else {
+            const int half = res >> 1;
+            const int jx = (int)(o % half);
+            const int iy = (int)((o / half) % half);
+            const long long b = o / ((long long)half * half);
+            const float* base = x + ((b * res + 2 * iy) * res + 2 * jx) * C;
+            // concat order x0 | x1 | x2 | x3 = (2i,2j) (2i+1,2j) (2i,2j+1) (2i+1,2j+1); C is a multiple of 4
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) {
-            const int i = lane + 32 * k;
-            const int part = i / C, c = i - part * C;
-            v[k] = base[(size_t)((part & 1) ? res * C : 0) + ((part & 2) ? C : 0) + c];
+            for (int j = 0; j < CHUNKS; ++j) {
+                const int i = 4 * (li + L * j);
+                const int part = i / C, c = i - part * C;
+                v[j] = *reinterpret_cast<const float4*>(base + (size_t)((part & 1) ? res * C : 0) + ((part & 2) ? C : 0) + c);
+            }
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CHUNKS; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float s1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) s1 += v[k];
-    for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+    for (int j = 0; j < CHUNKS; ++j) s1 += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int m = L / 2; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
     const float mean = s1 / (float)width;
     float s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) { const float dlt = v[k] - mean; s2 += dlt * dlt; }
-    for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    for (int j = 0; j < CHUNKS; ++j) {
+        const float a = v[j].x - mean, b2 = v[j].y - mean, c2 = v[j].z - mean, d2 = v[j].w - mean;
+        s2 += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+    }
+#pragma unroll
+    for (int m = L / 2; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
     const float rstd = rsqrtf(s2 / (float)width + 1e-5f);
+    if (!live) return;
     __half* dst = out + o * ld_out;
 #pragma unroll
-    for (int k = 0; k < EPL; ++k) {
-        const int i = lane + 32 * k;
-        dst[i] = __float2half_rn((v[k] - mean) * rstd * gamma[i] + beta[i]);
+    for (int j = 0; j < CHUNKS; ++j) {
+        const int i = 4 * (li + L * j);
+        const float4 g4 = *reinterpret_cast<const float4*>(gamma + i);
+        const float4 b4 = *reinterpret_cast<const float4*>(beta + i);
+        const __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd * g4.x + b4.x, (v[j].y - mean) * rstd * g4.y + b4.y);
+        const __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd * g4.z + b4.z, (v[j].w - mean) * rstd * g4.w + b4.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(dst + i) = pk;
     }
-    for (int i = width + lane; i < ld_out; i += 32) dst[i] = __float2half_rn(0.f);
+    for (int i = width + li; i < ld_out; i += L) dst[i] = __float2half_rn(0.f);
 }
 
 // x[token(o)][0:C] += y[o][0:C]   (windowed = 1: o is a window-ordered row)
