@@ -364,6 +364,8 @@ clap_copy_rows_kernel(float* __restrict__ x, const float* __restrict__ y, long l
 // qkv: fp16 [rows, ld] with q | k | v at column offsets 0, C, 2C and head h at h*24.
 // relbias: fp32 [heads][64][64].  out: fp16 [rows, ld_out] (head h at h*24).
 constexpr int kAttWarps = 4;
+constexpr int kAttStages = 1;     // 2 = prefetch the next unit into a second warp-private buffer: measured SLOWER
+                                  // (12 instead of 20 resident warps per SM: 122 vs 110 ms per 3 steps), kept for reference
 constexpr int kAttRow = 24;       // halves per staged row
 constexpr int kAttMat = 64 * kAttRow;
 
@@ -388,7 +390,8 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                              const float* __restrict__ relbias, int res, int shift, long long n_windows,
                              __half* __restrict__ out, int ld_out)
 {
-    __shared__ __align__(16) __half tiles[kAttWarps][3 * kAttMat];     // Q | K | V, row-major [64][24]
+    extern __shared__ __align__(16) unsigned char att_smem[];           // [warps][stages][Q | K | V], row-major [64][24] each
+    __half* tiles_base = reinterpret_cast<__half*>(att_smem);
     __shared__ int rid[kAttWarps][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -396,25 +399,42 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
     const int lg_nw = 28 - __clz(res);
     const int nw = res >> 3;
     const float scale = 0.20412414523193151f;                      // 1 / sqrt(24)
-    const __half* q_s = tiles[warp];
-    const __half* k_s = q_s + kAttMat;
-    const uint32_t tile_u32 = (uint32_t)__cvta_generic_to_shared(tiles[warp]);
-    // ldmatrix.trans row addresses for the V fragments: lanes 0-7 / 8-15 give the key rows of the
-    // two 8x8 blocks of one n-tile (b0, b1), lanes 16-31 the same rows of the next n-tile
-    const uint32_t v_ld = tile_u32 + 2 * kAttMat * 2 + ((lane & 15) * kAttRow + (lane >> 4) * 8) * 2;
-    for (long long u = (long long)blockIdx.x * kAttWarps + warp; u < units; u += (long long)gridDim.x * kAttWarps) {
-        const long long win = u / heads;
-        const int h = (int)(u - win * heads);
-        const __half* base = qkv + win * 64 * ld + h * 24;
-        // 3 matrices x 64 rows x 3 vectors of 16 B = 18 cp.async per lane
+    __half* my_tiles = tiles_base + (size_t)warp * kAttStages * 3 * kAttMat;
+    const uint32_t tiles_u32 = (uint32_t)__cvta_generic_to_shared(my_tiles);
+    // 3 matrices x 64 rows x 3 vectors of 16 B = 18 cp.async per lane
+    auto fetch = [&](long long unit, int stage) {
+        const long long w_ = unit / heads;
+        const int h_ = (int)(unit - w_ * heads);
+        const __half* base = qkv + w_ * 64 * ld + h_ * 24;
+        const uint32_t t32 = tiles_u32 + stage * 3 * kAttMat * 2;
 #pragma unroll
         for (int it = 0; it < 18; ++it) {
             const int i = it * 32 + lane;
             const int mtx = i / 192, rem = i - mtx * 192;
             const int r = rem / 3, v = rem - r * 3;
-            const uint32_t dst = tile_u32 + ((mtx * 64 + r) * kAttRow + v * 8) * 2;
+            const uint32_t dst = t32 + ((mtx * 64 + r) * kAttRow + v * 8) * 2;
             const __half* src = base + (size_t)r * ld + mtx * C + v * 8;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const long long stride = (long long)gridDim.x * kAttWarps;
+    long long u = (long long)blockIdx.x * kAttWarps + warp;
+    if (kAttStages == 2 && u < units) fetch(u, 0);
+    for (int stage = 0; u < units; u += stride, stage ^= (kAttStages - 1)) {
+        const long long win = u / heads;
+        const int h = (int)(u - win * heads);
+        const __half* q_s = my_tiles + stage * 3 * kAttMat;
+        const __half* k_s = q_s + kAttMat;
+        const uint32_t tile_u32 = tiles_u32 + stage * 3 * kAttMat * 2;
+        // ldmatrix.trans row addresses for the V fragments: lanes 0-7 / 8-15 give the key rows of the
+        // two 8x8 blocks of one n-tile (b0, b1), lanes 16-31 the same rows of the next n-tile
+        const uint32_t v_ld = tile_u32 + 2 * kAttMat * 2 + ((lane & 15) * kAttRow + (lane >> 4) * 8) * 2;
+        if (kAttStages == 2) {                      // next unit -> other buffer (free: its reader finished an iteration ago)
+            if (u + stride < units) fetch(u + stride, stage ^ 1);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            fetch(u, 0);
         }
         if (shift) {
             const int wx = (int)win & (nw - 1), wy = (int)(win >> lg_nw) & (nw - 1);
@@ -425,12 +445,21 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                 rid[warp][i] = ry * 3 + rx;
             }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (kAttStages == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
         const float* bias_h = relbias + (size_t)h * 64 * 64;
 #pragma unroll 1
         for (int mt = 0; mt < 4; ++mt) {
             const int r0 = mt * 16 + g, r1 = r0 + 8;
+            // relative-position bias of this m-tile: issue the 16 loads before the MMAs so their latency
+            // is hidden (ncu: the scale+bias FFMAs were the top long-scoreboard stall)
+            float2 bias0[8], bias1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bias0[j] = __ldg(reinterpret_cast<const float2*>(bias_h + r0 * 64 + j * 8 + 2 * t));
+                bias1[j] = __ldg(reinterpret_cast<const float2*>(bias_h + r1 * 64 + j * 8 + 2 * t));
+            }
             float sacc[8][4];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f; }
@@ -457,8 +486,7 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = j * 8 + 2 * t;
-                const float2 b0v = __ldg(reinterpret_cast<const float2*>(bias_h + r0 * 64 + c));
-                const float2 b1v = __ldg(reinterpret_cast<const float2*>(bias_h + r1 * 64 + c));
+                const float2 b0v = bias0[j], b1v = bias1[j];
                 sacc[j][0] = sacc[j][0] * scale + b0v.x; sacc[j][1] = sacc[j][1] * scale + b0v.y;
                 sacc[j][2] = sacc[j][2] * scale + b1v.x; sacc[j][3] = sacc[j][3] * scale + b1v.y;
                 if (shift) {
