@@ -581,7 +581,11 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
         if (launch_logmel(h, pcm, ex_start + base, nb, h->logmel, fe_double, st)) return 1;
         prof_end(h, FAD_PROF_LOGMEL, ev, st);
         ev = prof_begin(h, st);
-        fad::conv1_kernel<<<dim3(6, nb), 256, 0, st>>>(h->logmel, h->conv1_w, h->conv1_b, h->act[0], h->act8[0]);
+        {
+            static const bool simt = []() { const char* e = getenv("FADTK_CONV1"); return !(e && std::string(e) == "mma"); }();   // default: CUDA-core stencil
+            if (simt) fad::conv1_kernel<<<dim3(6, nb), 256, 0, st>>>(h->logmel, h->conv1_w, h->conv1_b, h->act[0], h->act8[0]);
+            else      fad::conv1_mma_kernel<<<nb, 256, 0, st>>>(h->logmel, h->conv1_w, h->conv1_b, h->act[0], h->act8[0]);
+        }
         CK(cudaGetLastError());
         h->launches++;
         prof_end(h, FAD_PROF_CONV1, ev, st);
