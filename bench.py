@@ -40,8 +40,13 @@ UMMA_LAYER_FLOP = {
     "fc1": 2 * 12288 * 4096, "fc2": 2 * 4096 * 4096, "fc3": 2 * 4096 * 128,
 }
 # HTSAT-tiny GEMMs per 10-s window: 24 T C^2 per Swin block + 3 patch-merging reductions
-CLAP_GEMM_FLOP = sum(d * 24 * t * c * c for d, t, c in ((2, 4096, 96), (2, 1024, 192), (6, 256, 384), (2, 64, 768))) \
-    + sum(2 * t * 4 * c * 2 * c for t, c in ((1024, 96), (256, 192), (64, 384)))
+def _htsat_gemm_flop(embed, depths):
+    dims = [(d, 4096 >> (2 * i), embed << i) for i, d in enumerate(depths)]
+    return sum(d * 24 * t * c * c for d, t, c in dims) + sum(2 * (t // 4) * 4 * c * 2 * c for _, t, c in dims[:3])
+
+
+CLAP_GEMM_FLOP = _htsat_gemm_flop(96, (2, 2, 6, 2))
+CLAP_MUSIC_GEMM_FLOP = _htsat_gemm_flop(128, (2, 2, 12, 2))
 
 MODELS = {
     "vggish": dict(sr=16000, clips=10000, baseline_clips=1000, chunk_clips=1000, d=128,
@@ -51,6 +56,9 @@ MODELS = {
                              workload="clap-laion-audio (HTSAT-tiny) FAD, {clips} x 10 s synthetic 48 kHz clips per GPU vs {base}-clip "
                                       "baseline (BASELINE.json configs[2] at single-GPU size)",
                              rows_flop=CLAP_GEMM_FLOP),
+    "clap-laion-music": dict(sr=48000, clips=250, baseline_clips=50, chunk_clips=25, d=512,
+                             workload="clap-laion-music (HTSAT-base) FAD, {clips} x 10 s synthetic 48 kHz clips per GPU vs {base}-clip baseline",
+                             rows_flop=CLAP_MUSIC_GEMM_FLOP),
 }
 
 
@@ -170,7 +178,8 @@ def main():
               "l2": f"inputs ({pcm_gb:.1f} GB PCM per GPU) exceed L2; no explicit flush", "parallelism": f"dp{world}"}
 
     from fadtk_b200 import synth, weights, weights_clap
-    state = weights.synthetic_vggish_state(0) if args.model == "vggish" else weights_clap.synthetic_clap_state(0)
+    state = weights.synthetic_vggish_state(0) if args.model == "vggish" else \
+        weights_clap.synthetic_clap_state(0, "base" if args.model == "clap-laion-music" else "tiny")
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":

@@ -191,6 +191,7 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
 
 // one warp per token (patch).  lm: frame pool [n_pool,64] (already BatchNorm-ed), addressed through
 // frame_index [B][1001]; w: [96][16]; x out: [B,4096,96]
+template <int CPL>                                              // channels per lane: embed dim = 32 CPL (96 tiny, 128 base)
 __global__ void __launch_bounds__(256)
 clap_patch_embed_kernel(const float* __restrict__ lm, const int* __restrict__ frame_index,
                         const float* __restrict__ w, const float* __restrict__ bias,
@@ -200,9 +201,9 @@ clap_patch_embed_kernel(const float* __restrict__ lm, const int* __restrict__ fr
     const int lane = threadIdx.x & 31;
     // the 96x16 filter bank, bias and LayerNorm affine live in registers (3 channels per lane) and are
     // reused for every token this warp handles
-    float wr[3][16], br[3], gr[3], ber[3];
+    float wr[CPL][16], br[CPL], gr[CPL], ber[CPL];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
+    for (int u = 0; u < CPL; ++u) {
         const int ch = lane + 32 * u;
         br[u] = bias[ch]; gr[u] = gamma[ch]; ber[u] = beta[ch];
         const float4* wp = reinterpret_cast<const float4*>(w + ch * 16);
@@ -234,23 +235,27 @@ clap_patch_embed_kernel(const float* __restrict__ lm, const int* __restrict__ fr
                 pix = fmaf(cf[k], lm[(size_t)fidx[ti] * kClMel + f0 + r], pix);
             }
         }
-        float o[3] = {br[0], br[1], br[2]};
+        float o[CPL];
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) o[u] = br[u];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const float v = __shfl_sync(0xffffffffu, pix, q);
 #pragma unroll
-            for (int u = 0; u < 3; ++u) o[u] = fmaf(wr[u][q], v, o[u]);
+            for (int u = 0; u < CPL; ++u) o[u] = fmaf(wr[u][q], v, o[u]);
         }
-        float s1 = o[0] + o[1] + o[2];
+        float s1 = 0.f;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) s1 += o[u];
         for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-        const float mean = s1 / 96.0f;
+        const float mean = s1 / (32.0f * CPL);
         float s2 = 0.f;
 #pragma unroll
-        for (int u = 0; u < 3; ++u) { const float dlt = o[u] - mean; s2 += dlt * dlt; }
+        for (int u = 0; u < CPL; ++u) { const float dlt = o[u] - mean; s2 += dlt * dlt; }
         for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-        const float rstd = rsqrtf(s2 / 96.0f + 1e-5f);
+        const float rstd = rsqrtf(s2 / (32.0f * CPL) + 1e-5f);
 #pragma unroll
-        for (int u = 0; u < 3; ++u) x[tok * 96 + lane + 32 * u] = (o[u] - mean) * rstd * gr[u] + ber[u];
+        for (int u = 0; u < CPL; ++u) x[tok * (32 * CPL) + lane + 32 * u] = (o[u] - mean) * rstd * gr[u] + ber[u];
     }
 }
 
@@ -366,8 +371,10 @@ clap_copy_rows_kernel(float* __restrict__ x, const float* __restrict__ y, long l
 constexpr int kAttWarps = 4;
 constexpr int kAttStages = 1;     // 2 = prefetch the next unit into a second warp-private buffer: measured SLOWER
                                   // (12 instead of 20 resident warps per SM: 122 vs 110 ms per 3 steps), kept for reference
-constexpr int kAttRow = 24;       // halves per staged row
-constexpr int kAttMat = 64 * kAttRow;
+// head dim 24 (HTSAT-tiny): rows of 48 B; head dim 32 (HTSAT-base): rows padded to 80 B - both strides keep the
+// 32-bit fragment loads and ldmatrix conflict-free and 16-B aligned for cp.async
+__host__ __device__ constexpr int att_row_halves(int hd) { return hd == 24 ? 24 : 40; }
+__host__ __device__ constexpr int att_smem_bytes(int hd, int warps, int stages) { return warps * stages * 3 * 64 * att_row_halves(hd) * 2; }
 
 __device__ __forceinline__ void mma_m16n8k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
@@ -379,11 +386,16 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <int HD>
 __global__ void __launch_bounds__(kAttWarps * 32)
 clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int heads,
                              const float* __restrict__ relbias, int res, int shift, long long n_windows,
                              __half* __restrict__ out, int ld_out)
 {
+    constexpr int kAttRow = att_row_halves(HD);
+    constexpr int kAttMat = 64 * kAttRow;
+    constexpr int kVec = HD / 8;                                   // 16-B vectors per row
+    constexpr int kNT = HD / 8;                                    // PV n-tiles
     extern __shared__ __align__(16) unsigned char att_smem[];           // [warps][stages][Q | K | V], row-major [64][24] each
     __half* tiles_base = reinterpret_cast<__half*>(att_smem);
     __shared__ int rid[kAttWarps][64];
@@ -392,20 +404,20 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
     const long long units = n_windows * heads;
     const int lg_nw = 28 - __clz(res);
     const int nw = res >> 3;
-    const float scale = 0.20412414523193151f;                      // 1 / sqrt(24)
+    const float scale = HD == 24 ? 0.20412414523193151f : 0.17677669529663689f;   // 1 / sqrt(head dim)
     __half* my_tiles = tiles_base + (size_t)warp * kAttStages * 3 * kAttMat;
     const uint32_t tiles_u32 = (uint32_t)__cvta_generic_to_shared(my_tiles);
-    // 3 matrices x 64 rows x 3 vectors of 16 B = 18 cp.async per lane
+    // 3 matrices x 64 rows x kVec vectors of 16 B = 6 kVec cp.async per lane
     auto fetch = [&](long long unit, int stage) {
         const long long w_ = unit / heads;
         const int h_ = (int)(unit - w_ * heads);
-        const __half* base = qkv + w_ * 64 * ld + h_ * 24;
+        const __half* base = qkv + w_ * 64 * ld + h_ * HD;
         const uint32_t t32 = tiles_u32 + stage * 3 * kAttMat * 2;
 #pragma unroll
-        for (int it = 0; it < 18; ++it) {
+        for (int it = 0; it < 6 * kVec; ++it) {
             const int i = it * 32 + lane;
-            const int mtx = i / 192, rem = i - mtx * 192;
-            const int r = rem / 3, v = rem - r * 3;
+            const int mtx = i / (64 * kVec), rem = i - mtx * (64 * kVec);
+            const int r = rem / kVec, v = rem - r * kVec;
             const uint32_t dst = t32 + ((mtx * 64 + r) * kAttRow + v * 8) * 2;
             const __half* src = base + (size_t)r * ld + mtx * C + v * 8;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src));
@@ -464,6 +476,11 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                 const uint32_t a3 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kAttRow + 2 * t + 8);
                 const uint32_t a4 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kAttRow + 2 * t + 16);
                 const uint32_t a5 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kAttRow + 2 * t + 16);
+                uint32_t a6 = 0, a7 = 0;
+                if (HD == 32) {
+                    a6 = *reinterpret_cast<const uint32_t*>(q_s + r0 * kAttRow + 2 * t + 24);
+                    a7 = *reinterpret_cast<const uint32_t*>(q_s + r1 * kAttRow + 2 * t + 24);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const __half* kr = k_s + (j * 8 + g) * kAttRow + 2 * t;
@@ -471,7 +488,8 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
                     const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
                     const uint32_t b2 = *reinterpret_cast<const uint32_t*>(kr + 16);
                     mma_m16n8k16(sacc[j], a0, a1, a2, a3, b0, b1);
-                    mma_m16n8k8(sacc[j], a4, a5, b2);
+                    if (HD == 24) mma_m16n8k8(sacc[j], a4, a5, b2);
+                    else mma_m16n8k16(sacc[j], a4, a5, a6, a7, b2, *reinterpret_cast<const uint32_t*>(kr + 24));
                 }
             }
             // scale + bias + mask, row max
@@ -507,28 +525,33 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
             sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
             const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
             // O = P V : P fragments come straight from the (normalised) S accumulators
-            float oacc[3][4];
+            float oacc[kNT][4];
 #pragma unroll
-            for (int n = 0; n < 3; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+            for (int n = 0; n < kNT; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const uint32_t a0 = pack_h2(sacc[2 * kk][0] * inv0, sacc[2 * kk][1] * inv0);
                 const uint32_t a1 = pack_h2(sacc[2 * kk][2] * inv1, sacc[2 * kk][3] * inv1);
                 const uint32_t a2 = pack_h2(sacc[2 * kk + 1][0] * inv0, sacc[2 * kk + 1][1] * inv0);
                 const uint32_t a3 = pack_h2(sacc[2 * kk + 1][2] * inv1, sacc[2 * kk + 1][3] * inv1);
-                uint32_t b[6];
+                uint32_t b[8];
                 const uint32_t va = v_ld + kk * 16 * kAttRow * 2;
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                              : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(va));
-                asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
-                             : "=r"(b[4]), "=r"(b[5]) : "r"(va + ((lane >> 4) ? -16 : 32)));   // dims 16..23 (lanes >= 16: address unused but valid)
+                if (HD == 24) {
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                                 : "=r"(b[4]), "=r"(b[5]) : "r"(va + ((lane >> 4) ? -16 : 32)));   // dims 16..23 (lanes >= 16: address unused but valid)
+                } else {
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]) : "r"(va + 32));   // dims 16..31
+                }
 #pragma unroll
-                for (int n = 0; n < 3; ++n) mma_m16n8k16(oacc[n], a0, a1, a2, a3, b[2 * n], b[2 * n + 1]);
+                for (int n = 0; n < kNT; ++n) mma_m16n8k16(oacc[n], a0, a1, a2, a3, b[2 * n], b[2 * n + 1]);
             }
-            __half* d0 = out + (win * 64 + r0) * ld_out + h * 24;
-            __half* d1 = out + (win * 64 + r1) * ld_out + h * 24;
+            __half* d0 = out + (win * 64 + r0) * ld_out + h * HD;
+            __half* d1 = out + (win * 64 + r1) * ld_out + h * HD;
 #pragma unroll
-            for (int n = 0; n < 3; ++n) {
+            for (int n = 0; n < kNT; ++n) {
                 *reinterpret_cast<uint32_t*>(d0 + n * 8 + 2 * t) = pack_h2(oacc[n][0], oacc[n][1]);
                 *reinterpret_cast<uint32_t*>(d1 + n * 8 + 2 * t) = pack_h2(oacc[n][2], oacc[n][3]);
             }
@@ -539,43 +562,45 @@ clap_window_attention_kernel(const __half* __restrict__ qkv, int ld, int C, int 
 
 // one block (256 threads) per chunk: LayerNorm(768) of the 64 tokens, mean over tokens,
 // 768 -> 512 ReLU -> 512, L2 normalise, fp16 out [B, 512]
+template <int D>                                                // final width: 768 (tiny) or 1024 (base)
 __global__ void __launch_bounds__(256)
-clap_head_kernel(const float* __restrict__ x /*[B,64,768]*/, const float* __restrict__ gamma,
+clap_head_kernel(const float* __restrict__ x /*[B,64,D]*/, const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ w1, const float* __restrict__ b1,
                  const float* __restrict__ w2, const float* __restrict__ b2, __half* __restrict__ out)
 {
-    __shared__ float pooled[768];
-    __shared__ float part[8][768];                                 // per-warp partial means (fixed-order reduce)
+    __shared__ float pooled[D];
+    __shared__ float part[8][D];                                 // per-warp partial means (fixed-order reduce)
     __shared__ float h1[512];
     __shared__ float h2[512];
     __shared__ float red[8];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float acc_tok[24];
+    constexpr int E = D / 32;
+    float acc_tok[E];
 #pragma unroll
-    for (int k = 0; k < 24; ++k) acc_tok[k] = 0.f;
+    for (int k = 0; k < E; ++k) acc_tok[k] = 0.f;
     for (int t = warp; t < 64; t += 8) {
-        const float* row = x + ((size_t)b * 64 + t) * 768;
-        float v[24];
+        const float* row = x + ((size_t)b * 64 + t) * D;
+        float v[E];
         float s1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 24; ++k) { v[k] = row[lane + 32 * k]; s1 += v[k]; }
+        for (int k = 0; k < E; ++k) { v[k] = row[lane + 32 * k]; s1 += v[k]; }
         for (int m = 16; m > 0; m >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-        const float mean = s1 / 768.0f;
+        const float mean = s1 / (float)D;
         float s2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 24; ++k) { const float dlt = v[k] - mean; s2 += dlt * dlt; }
+        for (int k = 0; k < E; ++k) { const float dlt = v[k] - mean; s2 += dlt * dlt; }
         for (int m = 16; m > 0; m >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-        const float rstd = rsqrtf(s2 / 768.0f + 1e-5f);
+        const float rstd = rsqrtf(s2 / (float)D + 1e-5f);
 #pragma unroll
-        for (int k = 0; k < 24; ++k) {
+        for (int k = 0; k < E; ++k) {
             const int c = lane + 32 * k;
             acc_tok[k] += (v[k] - mean) * rstd * gamma[c] + beta[c];
         }
     }
 #pragma unroll
-    for (int k = 0; k < 24; ++k) part[warp][lane + 32 * k] = acc_tok[k];
+    for (int k = 0; k < E; ++k) part[warp][lane + 32 * k] = acc_tok[k];
     __syncthreads();
-    for (int i = threadIdx.x; i < 768; i += 256) {
+    for (int i = threadIdx.x; i < D; i += 256) {
         float sacc = 0.f;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) sacc += part[wv][i];
@@ -584,7 +609,7 @@ clap_head_kernel(const float* __restrict__ x /*[B,64,768]*/, const float* __rest
     __syncthreads();
     for (int o = warp; o < 512; o += 8) {
         float acc = 0.f;
-        for (int k = lane; k < 768; k += 32) acc = fmaf(w1[(size_t)o * 768 + k], pooled[k], acc);
+        for (int k = lane; k < D; k += 32) acc = fmaf(w1[(size_t)o * D + k], pooled[k], acc);
         for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
         if (lane == 0) h1[o] = fmaxf(acc + b1[o], 0.f);
     }

@@ -155,10 +155,12 @@ class VGGishModel(ModelLoader):
 
 
 class CLAPLaionModel(ModelLoader):
-    """CLAP from https://github.com/LAION-AI/CLAP, audio branch (HTSAT-tiny), B200-native.
+    """CLAP from https://github.com/LAION-AI/CLAP, audio branch, B200-native.
 
-    Same registry name, dimensionality and sample rate as the reference (model_loader.py:296-297).
-    ``type='audio'`` (HTSAT-tiny, 630k-audioset) is implemented; ``'music'`` (HTSAT-base) is not.
+    Same registry names, dimensionality and sample rate as the reference (model_loader.py:296-297):
+    ``type='audio'`` = HTSAT-tiny (630k-audioset-best), ``type='music'`` = HTSAT-base
+    (music_audioset_epoch_15_esc_90.14, model_loader.py:303,385) - same kernels, wider instantiations.
+    One engine holds one CLAP variant at a time (as one reference process holds one model).
     The reference's per-window loop at batch one (model_loader.py:402-407) becomes one batched
     launch sequence over all 10-s windows of all clips.
     """
@@ -177,11 +179,11 @@ class CLAPLaionModel(ModelLoader):
         return st
 
     def load_model(self):
-        if self.type != 'audio':
-            raise NotImplementedError("clap-laion-music (HTSAT-base) has no sm_100a forward pass yet")
+        if self.type not in ('audio', 'music'):
+            raise ValueError(f"unknown CLAP-LAION type {self.type!r}")
         from . import _native, weights_clap
         self._engine = _native.engine()
-        state = weights_clap.load_clap_state(self.checkpoint, self.seed)
+        state = weights_clap.load_clap_state(self.checkpoint, self.seed, "tiny" if self.type == 'audio' else "base")
         self._engine.clap_load(weights_clap.pack_clap(state))
         self.model = self._engine
         self.device = self._engine.torch_device

@@ -38,7 +38,7 @@ class EvalSetFAD:
         if model == "vggish":
             self.d = 128
             self.rows_per_clip = int(_native.lib().fad_vggish_num_examples(self.clip_samples))
-        elif model == "clap-laion-audio":
+        elif model in ("clap-laion-audio", "clap-laion-music"):
             self.d = 512
             self.rows_per_clip = -(-self.clip_samples // 48000)
         else:

@@ -15,16 +15,31 @@ import torch
 
 from .weights import split_hi_lo_tiles
 
-EMBED, DEPTHS, HEADS, WINDOW, N_MEL = 96, (2, 2, 6, 2), (4, 8, 16, 32), 8, 64
+HEADS, WINDOW, N_MEL = (4, 8, 16, 32), 8, 64
+# HTSAT-tiny = clap-laion-audio, HTSAT-base = clap-laion-music (model_loader.py:385): (embed dim, depths)
+VARIANTS = {"tiny": (96, (2, 2, 6, 2)), "base": (128, (2, 2, 12, 2))}
+EMBED, DEPTHS = VARIANTS["tiny"]
 N_TENSORS = 6 + 12 * 13 + 3 * 4 + 6
+
+
+def n_tensors(variant: str = "tiny") -> int:
+    return 6 + sum(VARIANTS[variant][1]) * 13 + 3 * 4 + 6
+
+
+def config_of(sd: dict):
+    """(embed dim, depths) read off a state dict."""
+    embed = sd["patch_embed.proj.weight"].shape[0]
+    depths = tuple(len({k.split(".")[3] for k in sd if k.startswith(f"layers.{i}.blocks.")}) for i in range(4))
+    return embed, depths
 
 
 def _pad_to(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
-def synthetic_clap_state(seed: int = 0) -> dict:
+def synthetic_clap_state(seed: int = 0, variant: str = "tiny") -> dict:
     """Seeded random parameters (float32, CPU); same recipe as oracle.clap_oracle.synthetic_state."""
+    EMBED, DEPTHS = VARIANTS[variant]
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -66,9 +81,9 @@ def synthetic_clap_state(seed: int = 0) -> dict:
     return sd
 
 
-def load_clap_state(path=None, seed: int = 0) -> dict:
-    """HF-format checkpoint if ``path`` (or $FADTK_CLAP_CKPT) exists, else synthetic."""
-    path = path or os.environ.get("FADTK_CLAP_CKPT")
+def load_clap_state(path=None, seed: int = 0, variant: str = "tiny") -> dict:
+    """HF-format checkpoint if ``path`` (or $FADTK_CLAP_CKPT / $FADTK_CLAP_MUSIC_CKPT) exists, else synthetic."""
+    path = path or os.environ.get("FADTK_CLAP_CKPT" if variant == "tiny" else "FADTK_CLAP_MUSIC_CKPT")
     if path and Path(path).exists():
         raw = torch.load(path, map_location="cpu")
         raw = raw.get("state_dict", raw)
@@ -79,7 +94,7 @@ def load_clap_state(path=None, seed: int = 0) -> dict:
                     and "relative_position_index" not in k and "num_batches_tracked" not in k:
                 out[k] = v.float().contiguous()
         return out
-    return synthetic_clap_state(seed)
+    return synthetic_clap_state(seed, variant)
 
 
 def _rel_pos_index(ws: int = WINDOW) -> torch.Tensor:
@@ -104,11 +119,13 @@ def _padded_vec(b: torch.Tensor, n: int) -> torch.Tensor:
 
 
 def pack_clap(sd: dict) -> list:
-    """-> the 180 contiguous CPU tensors fad_clap_load expects (order: csrc/clap_host.inc).
+    """-> the contiguous CPU tensors fad_clap_load expects (180 for HTSAT-tiny, 258 for HTSAT-base;
+    order: csrc/clap_host.inc).
 
     GEMM weights are zero padded to K % 64 == 0 / N % 128 == 0 and stored as fp16 hi/lo tiles
     (22-bit weights, see weights.split_hi_lo_tiles); everything else stays float32."""
     f = lambda t: t.float().contiguous()
+    EMBED, DEPTHS = config_of(sd)
     out = []
     scale = sd["batch_norm.weight"] / torch.sqrt(sd["batch_norm.running_var"] + 1e-5)
     out += [f(scale), f(sd["batch_norm.bias"] - sd["batch_norm.running_mean"] * scale)]
@@ -144,5 +161,5 @@ def pack_clap(sd: dict) -> list:
     out += [f(sd["norm.weight"]), f(sd["norm.bias"]),
             f(sd["audio_projection.linear1.weight"]), f(sd["audio_projection.linear1.bias"]),
             f(sd["audio_projection.linear2.weight"]), f(sd["audio_projection.linear2.bias"])]
-    assert len(out) == N_TENSORS
+    assert len(out) == 6 + sum(DEPTHS) * 13 + 3 * 4 + 6
     return out

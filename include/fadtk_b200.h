@@ -84,7 +84,9 @@ int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int C
 
 /* ---- CLAP-LAION audio embedder (HTSAT-tiny): replaces CLAPLaionModel.load_model/_get_embedding
  * (fadtk/model_loader.py:382-418 -> laion_clap.CLAP_Module + torchlibrosa front-end).
- * tensors_host: 180 host pointers in the order documented at the top of csrc/clap_host.inc
+ * tensors_host: 180 (HTSAT-tiny = clap-laion-audio) or 258 (HTSAT-base = clap-laion-music,
+ * model_loader.py:385) host pointers in the order documented at the top of csrc/clap_host.inc; the count
+ * selects the variant
  * (produced by fadtk_b200/weights_clap.py).  max_chunks bounds the 10-s windows per internal batch
  * (~12 MB of workspace each). */
 int fad_clap_load(fad_handle* h, const void* const* tensors_host, int n_tensors, int max_chunks);

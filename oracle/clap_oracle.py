@@ -36,9 +36,17 @@ CHUNK = 10 * SR
 FRAMES = CHUNK // HOP + 1          # 1001 (center=True)
 SPEC = 256
 WINDOW = 8
-EMBED = 96
-DEPTHS = (2, 2, 6, 2)
+# HTSAT-tiny (clap-laion-audio) / HTSAT-base (clap-laion-music, model_loader.py:385): (embed dim, depths)
+VARIANTS = {"tiny": (96, (2, 2, 6, 2)), "base": (128, (2, 2, 12, 2))}
+EMBED, DEPTHS = VARIANTS["tiny"]
 HEADS = (4, 8, 16, 32)
+
+
+def config_of(sd: dict):
+    """(embed dim, depths) read off a state dict."""
+    embed = sd["patch_embed.proj.weight"].shape[0]
+    depths = tuple(len({k.split(".")[3] for k in sd if k.startswith(f"layers.{i}.blocks.")}) for i in range(4))
+    return embed, depths
 OUT_DIM = 512
 
 
@@ -202,10 +210,11 @@ def network(lm: torch.Tensor, sd: dict) -> torch.Tensor:
     x = F.conv2d(img, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=4)
     x = _ln(x.flatten(2).transpose(1, 2), sd, "patch_embed.norm")      # [B, 4096, 96]
     res = SPEC // 4
-    for i, (depth, heads) in enumerate(zip(DEPTHS, HEADS)):
+    _, depths = config_of(sd)
+    for i, (depth, heads) in enumerate(zip(depths, HEADS)):
         for j in range(depth):
             x = swin_block(x, sd, f"layers.{i}.blocks.{j}.", res, heads, 0 if j % 2 == 0 else WINDOW // 2)
-        if i < len(DEPTHS) - 1:
+        if i < len(depths) - 1:
             x = patch_merge(x, sd, f"layers.{i}.downsample.", res)
             res //= 2
     x = _ln(x, sd, "norm").mean(1)                                     # token average -> [B, 768]
@@ -221,8 +230,9 @@ def embed(wave: np.ndarray, sd: dict, batch: int = 4) -> np.ndarray:
     return torch.cat(outs).numpy().astype(np.float16)
 
 
-def synthetic_state(seed: int = 0) -> dict:
-    """Seeded random HTSAT-tiny + projection parameters (float32), HF key names."""
+def synthetic_state(seed: int = 0, variant: str = "tiny") -> dict:
+    """Seeded random HTSAT (tiny | base) + projection parameters (float32), HF key names."""
+    EMBED, DEPTHS = VARIANTS[variant]
     g = torch.Generator().manual_seed(seed)
     sd = {}
 

@@ -140,3 +140,20 @@ def test_clap_fad_parity_on_identical_audio(clap_engine):
     assert abs(fad_gpu - fad_same) < 1e-4 * abs(fad_same) + 1e-6 * traces, (fad_gpu, fad_same)   # statistics + Frechet chain
     rel = abs(fad_gpu - fad_cpu) / abs(fad_cpu)
     assert rel < 1e-4, f"FAD gpu {fad_gpu} vs cpu reference path {fad_cpu}: rel {rel}"
+
+
+@pytest.mark.gpu
+def test_music_variant_htsat_base_matches_oracle(engine):
+    """clap-laion-music = HTSAT-base (embed 128, depths 2-2-12-2, head dim 32, final width 1024,
+    model_loader.py:385): same kernels, wider instantiations, checked against the HF-pinned oracle."""
+    clips = [synth.musiclike_clip(3, 3.2, 48000), synth.noise_clip(1, 1.0, 48000)]
+    ml = fk.CLAPLaionModel('music')
+    ml.load_model()
+    got = np.concatenate(ml.embed_pcm_batch(clips)).astype(np.float32)
+    sd = co.synthetic_state(0, "base")
+    want = np.concatenate([co.embed(c / 32768.0, sd) for c in clips]).astype(np.float32)
+    assert got.shape == want.shape == (5, 512)
+    cos = (got * want).sum(1)
+    assert cos.min() > 0.9999, cos
+    assert np.abs(got - want).max() < 3e-3, np.abs(got - want).max()
+    fk.CLAPLaionModel('audio').load_model()           # leave the engine with the tiny variant for later tests

@@ -11,7 +11,12 @@ from oracle import clap_oracle as co
 
 def _hf_model(sd):
     tr = pytest.importorskip("transformers")
-    cfg = tr.ClapAudioConfig()               # defaults == HTSAT-tiny (depths 2,2,6,2; heads 4,8,16,32)
+    embed, depths = co.config_of(sd)
+    if embed == 96:
+        cfg = tr.ClapAudioConfig()           # defaults == HTSAT-tiny (depths 2,2,6,2; heads 4,8,16,32)
+    else:                                    # HTSAT-base (clap-laion-music): embed 128, depths 2,2,12,2, final width 1024
+        cfg = tr.ClapAudioConfig(patch_embeds_hidden_size=embed, depths=list(depths), hidden_size=8 * embed)
+    assert cfg.patch_embeds_hidden_size == embed and list(cfg.depths) == list(depths)
     cfg.hidden_dropout_prob = 0.0
     model = tr.ClapAudioModelWithProjection(cfg).eval()
     hf = model.state_dict()
@@ -27,8 +32,9 @@ def _hf_model(sd):
     return model
 
 
-def test_network_matches_independent_hf_port():
-    sd = co.synthetic_state(1)
+@pytest.mark.parametrize("variant", ["tiny", "base"])
+def test_network_matches_independent_hf_port(variant):
+    sd = co.synthetic_state(1, variant)
     model = _hf_model(sd)
     g = torch.Generator().manual_seed(0)
     lm = -30.0 + 12.0 * torch.randn((2, co.FRAMES, co.N_MEL), generator=g)
