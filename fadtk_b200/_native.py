@@ -55,6 +55,9 @@ SIGNATURES = {
     "fad_frechet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_sqrt_psd": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_presqrt": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "fad_whisper_load": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),
+    "fad_whisper_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "fad_whisper_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_resample_geometry": (C.c_int, [C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "fad_resample_length": (c_ll, [C.c_int, C.c_int, c_ll]),
     "fad_resample_bank": (C.c_int, [C.c_int, C.c_int, c_vp]),
@@ -264,6 +267,34 @@ class Engine:
                                      plan_dev["pool_valid"].data_ptr(), plan_dev["pool_frame"].data_ptr(), n_pool,
                                      pool.data_ptr(), _stream()))
         return pool[plan_dev["frame_index"].long()]
+
+    # ------------------------------------------------------------------ Whisper
+    def whisper_load(self, cfg: tuple, tensors: list, max_clips: int = 16):
+        """cfg = (d_model, heads, enc_layers, dec_layers, ffn); tensors from weights_whisper.pack_whisper."""
+        keep = [t.contiguous() for t in tensors]
+        arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
+        c = (C.c_int * 5)(*[int(v) for v in cfg])
+        _check(lib().fad_whisper_load(self._h, c, arr, len(keep), int(max_clips)))
+        self._whisper_d = int(cfg[0])
+
+    def whisper_forward(self, pcm: torch.Tensor, clip_start: torch.Tensor, clip_len: torch.Tensor) -> torch.Tensor:
+        """pcm int16 (cuda, 16 kHz); clip_start int64 / clip_len int32 [n] (cuda) -> fp16 [n, 2, d_model]."""
+        assert pcm.dtype == torch.int16 and pcm.is_cuda and clip_start.dtype == torch.int64 and clip_len.dtype == torch.int32
+        n = clip_start.shape[0]
+        out = torch.empty((n, 2, self._whisper_d), dtype=torch.float16, device=pcm.device)
+        _check(lib().fad_whisper_forward(self._h, pcm.data_ptr(), clip_start.data_ptr(), clip_len.data_ptr(), n,
+                                         out.data_ptr(), _stream()))
+        return out
+
+    def whisper_features(self, pcm: torch.Tensor, clip_start: torch.Tensor, clip_len: torch.Tensor) -> torch.Tensor:
+        """-> fp32 [n, 3000, 80]: the feature extractor's input_features (time-major)."""
+        n = clip_start.shape[0]
+        buf = torch.empty(n * 3000 * 80 + n, dtype=torch.float32, device=pcm.device)
+        _check(lib().fad_whisper_logmel(self._h, pcm.data_ptr(), clip_start.data_ptr(), clip_len.data_ptr(), n,
+                                        buf.data_ptr(), _stream()))
+        raw = buf[: n * 3000 * 80].view(n, 3000, 80)
+        mx = buf[n * 3000 * 80:].view(n, 1, 1)
+        return (torch.maximum(raw, mx - 8.0) + 4.0) / 4.0
 
     # -------------------------------------------------------------- audio conversion
     @staticmethod

@@ -279,7 +279,7 @@ clap_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     float4 v[CHUNKS];
     if (live) {
         if (mode == 0) {
-            const float4* src = reinterpret_cast<const float4*>(x + window_row_to_token(o, res, shift) * C);
+            const float4* src = reinterpret_cast<const float4*>(x + (res ? window_row_to_token(o, res, shift) : o) * C);   // res = 0: rows as they are
 #pragma unroll
             for (int j = 0; j < CHUNKS; ++j) v[j] = src[li + L * j];
         } else {

@@ -22,6 +22,7 @@
 #include "frechet_batched.cuh"
 #include "clap.cuh"
 #include "resample.cuh"
+#include "whisper.cuh"
 
 namespace {
 
@@ -156,6 +157,7 @@ struct fad_handle {
     double* fr_scal = nullptr;   // 32 doubles
 
     void* clap_state = nullptr;  // ClapState (clap_host.inc)
+    void* whisper_state = nullptr;   // WhisperState (whisper_host.inc)
 
     // optional per-category timing with CUDA events recorded on the launching stream
     bool prof_on = false;
@@ -455,11 +457,13 @@ int fad_create(int device, int max_examples, fad_handle** out) {
 }
 
 static void clap_free_state(void* p);
+static void whisper_free_state(void* p);
 
 int fad_destroy(fad_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     clap_free_state(h->clap_state);
+    whisper_free_state(h->whisper_state);
     void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
                     h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal, h->frb_buf, h->rs_bank, h->rs_mono};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -936,3 +940,5 @@ int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, c
 #include "clap_host.inc"
 
 static void clap_free_state(void* p) { clap_free(reinterpret_cast<ClapState*>(p)); }
+
+#include "whisper_host.inc"

@@ -207,6 +207,59 @@ class CLAPLaionModel(ModelLoader):
         return list(torch.split(emb, [int(r) for r in plan["rows_per_clip"]]))
 
 
+class WhisperModel(ModelLoader):
+    """Whisper from https://huggingface.co/openai/whisper-<size>, B200-native (model_loader.py:636-672).
+
+    Same registry names (``whisper-tiny|base|small|medium|large``), dimensionality and sample rate.  The
+    reference's three transformers calls - feature extractor (clip padded / truncated to 30 s),
+    ``WhisperModel`` forward with ``decoder_input_ids = [[sot, sot]]`` and ``last_hidden_state`` - are one
+    batched launch sequence (fad_whisper_forward); every clip yields 2 rows of ``d_model`` features.
+    """
+
+    DIMS = {'tiny': 384, 'base': 512, 'small': 768, 'medium': 1024, 'large': 1280}
+
+    def __init__(self, size: str = 'small', checkpoint=None, seed: int = 0, max_clips: int = 16):
+        super().__init__(f"whisper-{size}", self.DIMS[size], 16000)
+        self.size = size
+        self.checkpoint = checkpoint
+        self.seed = seed
+        self.max_clips = max_clips
+        self._engine = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st["model"] = None
+        return st
+
+    def load_model(self):
+        from . import _native, weights_whisper
+        self._engine = _native.engine()
+        state, start = weights_whisper.load_whisper_state(self.checkpoint, self.seed, self.size)
+        self._engine.whisper_load(weights_whisper.config_of(state), weights_whisper.pack_whisper(state, start), self.max_clips)
+        self.model = self._engine
+        self.device = self._engine.torch_device
+
+    def _get_embedding(self, audio: np.ndarray):
+        return self._embed_flat([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
+
+    def embed_pcm_batch(self, clips):
+        return [t.cpu().numpy() for t in self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])]
+
+    def _embed_flat(self, clips):
+        if self._engine is None:
+            raise RuntimeError("load_model() has not been called")
+        eng = self._engine
+        lens = np.array([len(c) for c in clips], dtype=np.int32)
+        starts = np.zeros(len(clips), dtype=np.int64)
+        starts[1:] = np.cumsum(lens[:-1])
+        flat = torch.from_numpy(np.concatenate(clips)) if len(clips) > 1 else torch.from_numpy(np.ascontiguousarray(clips[0]))
+        dev = eng.torch_device
+        emb = eng.whisper_forward(flat.pin_memory().to(dev, non_blocking=True), torch.from_numpy(starts).to(dev),
+                                  torch.from_numpy(lens).to(dev))
+        return list(emb)                                   # [2, d_model] per clip
+
+
 class UnbuiltModel(ModelLoader):
     """Registry entry whose forward pass has no B200-native implementation yet.
 
@@ -239,8 +292,6 @@ def get_all_models() -> list[ModelLoader]:
         *_layered("hubert-base", 768, 12, 12), *_layered("hubert-large", 1024, 24, 24),
         *_layered("wavlm-base", 768, 12, 12), *_layered("wavlm-base-plus", 768, 12, 12),
         *_layered("wavlm-large", 1024, 24, 24),
-        UnbuiltModel("whisper-tiny", 384, 16000), UnbuiltModel("whisper-small", 768, 16000),
-        UnbuiltModel("whisper-base", 512, 16000), UnbuiltModel("whisper-medium", 1024, 16000),
-        UnbuiltModel("whisper-large", 1280, 16000),
+        WhisperModel('tiny'), WhisperModel('small'), WhisperModel('base'), WhisperModel('medium'), WhisperModel('large'),
     ]
     return ms

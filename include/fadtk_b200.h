@@ -115,6 +115,23 @@ int fad_clap_forward(fad_handle* h, const int16_t* pcm, const long long* pool_st
 int fad_clap_logmel(fad_handle* h, const int16_t* pcm, const long long* pool_start, const int* pool_valid,
                     const int* pool_frame, long long n_pool, float* out, void* stream);
 
+/* ---- Whisper: replaces WhisperModel.load_model / _get_embedding (fadtk/model_loader.py:657-669):
+ * WhisperFeatureExtractor (clip padded / truncated to 30 s, log-mel 80 x 3000) and
+ * transformers.WhisperModel(input_features, decoder_input_ids = [[sot, sot]]).last_hidden_state.
+ * cfg: {d_model, heads (= d_model / 64), encoder layers, decoder layers, ffn dim}; tensors_host: host pointers in
+ * the order documented at the top of csrc/whisper_host.inc (5 + 12 L_enc + 3 + 20 L_dec + 2), packed by
+ * fadtk_b200/weights_whisper.py.  max_clips bounds the clips per launch sequence (45 MB of workspace each at
+ * d_model = 768). */
+int fad_whisper_load(fad_handle* h, const int* cfg, const void* const* tensors_host, int n_tensors, int max_clips);
+/* pcm: int16 mono 16 kHz; clip_start int64 / clip_len int32 [n_clips] (all device).
+ * emb_out: fp16 [n_clips][2][d_model]. */
+int fad_whisper_forward(fad_handle* h, const int16_t* pcm, const long long* clip_start, const int* clip_len,
+                        long long n_clips, void* emb_out_f16, void* stream);
+/* stage entry point: out = fp32 [n_clips*3000*80] log10 mel (time-major) followed by [n_clips] per-clip maxima;
+ * the features are (max(x, max - 8) + 4) / 4. */
+int fad_whisper_logmel(fad_handle* h, const int16_t* pcm, const long long* clip_start, const int* clip_len,
+                       long long n_clips, float* out, void* stream);
+
 /* ---- statistics: replaces calc_embd_statistics (fadtk/fad.py:42-48) and
  * _process_file / calculate_embd_statistics_online (fadtk/utils.py:13-46) ----------------
  * Packed fp64 accumulator of length fad_stats_acc_len(d):
