@@ -45,7 +45,18 @@ def _htsat_gemm_flop(embed, depths):
     return sum(d * 24 * t * c * c for d, t, c in dims) + sum(2 * (t // 4) * 4 * c * 2 * c for _, t, c in dims[:3])
 
 
+def _whisper_gemm_flop(d, n_enc, n_dec):
+    """tensor-core GEMM FLOPs per clip (30-s padded input): conv stem (as 3-tap GEMMs), encoder layers,
+    cross-attention K/V projections; the 2-token decoder GEMMs are negligible."""
+    f = 4 * d
+    stem = 2 * 3000 * d * 240 + 2 * 1500 * d * 3 * d
+    enc = n_enc * 2 * 1500 * (4 * d * d + 2 * d * f)
+    ckv = n_dec * 2 * 1500 * 2 * d * d
+    return stem + enc + ckv
+
+
 CLAP_GEMM_FLOP = _htsat_gemm_flop(96, (2, 2, 6, 2))
+WHISPER_SMALL_GEMM_FLOP = _whisper_gemm_flop(768, 12, 12)
 CLAP_MUSIC_GEMM_FLOP = _htsat_gemm_flop(128, (2, 2, 12, 2))
 
 MODELS = {
@@ -59,6 +70,10 @@ MODELS = {
     "clap-laion-music": dict(sr=48000, clips=250, baseline_clips=50, chunk_clips=25, d=512,
                              workload="clap-laion-music (HTSAT-base) FAD, {clips} x 10 s synthetic 48 kHz clips per GPU vs {base}-clip baseline",
                              rows_flop=CLAP_MUSIC_GEMM_FLOP),
+    "whisper-small": dict(sr=16000, clips=256, baseline_clips=64, chunk_clips=32, d=768,
+                          workload="whisper-small FAD, {clips} x 10 s synthetic 16 kHz clips per GPU (each padded to 30 s, 2 rows per clip) "
+                                   "vs {base}-clip baseline (BASELINE.json configs[4] embedding stage)",
+                          rows_flop=WHISPER_SMALL_GEMM_FLOP),
 }
 
 
@@ -113,6 +128,11 @@ def oracle_embed_fn(model: str, state):
     if model == "vggish":
         from oracle import vggish_oracle as vo
         return lambda pcm: vo.embed(vo.load_wav_semantics(pcm), state)
+    if model.startswith("whisper-"):
+        from fadtk_b200 import weights_whisper
+        from oracle import whisper_oracle as wo
+        hf, fe = wo.build(state, weights_whisper.SYNTH_START)
+        return lambda pcm: wo.embed(pcm / 32768.0, hf, fe, weights_whisper.SYNTH_START)
     from oracle import clap_oracle as co
     return lambda pcm: co.embed(pcm / 32768.0, state)
 
@@ -142,8 +162,10 @@ def cpu_reference_leg(model, pcm_clips: np.ndarray, base_stats, state, budget_s:
     total = t_embed + t_stats + t_fr
     return {"value": used * CLIP_SECONDS / total, "unit": "audio-s/s", "cores": threads, "kind": "port",
             "sample": f"{used} of the eval clips ({used * CLIP_SECONDS:.0f} audio-s): embed {t_embed:.2f}s, "
-                      f"stats {t_stats:.3f}s, frechet {t_fr:.3f}s; oracle/ torch-CPU fp32 {model} + numpy/scipy "
-                      f"(reference third-party model is not installable offline)",
+                      f"stats {t_stats:.3f}s, frechet {t_fr:.3f}s; "
+                      + ("transformers WhisperFeatureExtractor + WhisperModel on CPU (the reference's own dependency, "
+                         "driven as model_loader.py:663-669) + numpy/scipy" if model.startswith("whisper-") else
+                         f"oracle/ torch-CPU fp32 {model} + numpy/scipy (reference third-party model is not installable offline)"),
             "fad": float(fad), "clips": used, "seconds": total}
 
 
@@ -178,8 +200,13 @@ def main():
               "l2": f"inputs ({pcm_gb:.1f} GB PCM per GPU) exceed L2; no explicit flush", "parallelism": f"dp{world}"}
 
     from fadtk_b200 import synth, weights, weights_clap
-    state = weights.synthetic_vggish_state(0) if args.model == "vggish" else \
-        weights_clap.synthetic_clap_state(0, "base" if args.model == "clap-laion-music" else "tiny")
+    if args.model == "vggish":
+        state = weights.synthetic_vggish_state(0)
+    elif args.model.startswith("whisper-"):
+        from fadtk_b200 import weights_whisper
+        state = weights_whisper.synthetic_whisper_state(0, args.model.split("-", 1)[1])
+    else:
+        state = weights_clap.synthetic_clap_state(0, "base" if args.model == "clap-laion-music" else "tiny")
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -217,6 +244,9 @@ def main():
     eng = _native.Engine(local_rank, max_examples=args.chunk_clips * ROWS_PER_CLIP)
     if args.model == "vggish":
         eng.vggish_load(weights.pack_vggish(state))
+    elif args.model.startswith("whisper-"):
+        eng.whisper_load(weights_whisper.config_of(state), weights_whisper.pack_whisper(state, weights_whisper.SYNTH_START),
+                         max_clips=args.chunk_clips)
     else:
         eng.clap_load(weights_clap.pack_clap(state), max_chunks=args.chunk_clips * ROWS_PER_CLIP)
 
@@ -264,7 +294,7 @@ def main():
 
     # ---- roofline of the dominant kernel: the tcgen05 conv/FC (GEMM) kernel
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    rows = args.clips * ROWS_PER_CLIP * args.steps                  # examples (VGGish) / 10-s windows (CLAP)
+    rows = args.clips * (1 if args.model.startswith("whisper-") else ROWS_PER_CLIP) * args.steps   # examples (VGGish) / 10-s windows (CLAP) / clips (Whisper)
     gemm_keys = list(UMMA_LAYER_FLOP) if args.model == "vggish" else ["clap_gemm"]
     umma_ms = sum(prof[k][0] for k in gemm_keys if k in prof)
     umma_launch = sum(prof[k][1] for k in gemm_keys if k in prof)

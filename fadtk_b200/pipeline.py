@@ -41,6 +41,10 @@ class EvalSetFAD:
         elif model in ("clap-laion-audio", "clap-laion-music"):
             self.d = 512
             self.rows_per_clip = -(-self.clip_samples // 48000)
+        elif model.startswith("whisper-"):
+            from .model_loader import WhisperModel
+            self.d = WhisperModel.DIMS[model.split("-", 1)[1]]
+            self.rows_per_clip = 2                           # last_hidden_state of the two start tokens
         else:
             raise ValueError(model)
         self.mirror = mirror_file_means
@@ -56,6 +60,9 @@ class EvalSetFAD:
             if self.model == "vggish":
                 ex, _ = self.eng.vggish_plan(off)
                 self._plans[n_clips] = (torch.from_numpy(ex).to(self.dev),)
+            elif self.model.startswith("whisper-"):
+                self._plans[n_clips] = (torch.from_numpy(off[:-1].copy()).to(self.dev),
+                                        torch.full((n_clips,), self.clip_samples, dtype=torch.int32, device=self.dev))
             else:
                 self._plans[n_clips] = (self.eng.clap_plan_to_device(self.eng.clap_plan_frames(off)),)
         return self._plans[n_clips]
@@ -66,7 +73,10 @@ class EvalSetFAD:
         flat = pcm_dev.reshape(-1)
         if self.model == "vggish":
             return self.eng.vggish_forward(flat, plan[0], out)
-        emb = self.eng.clap_forward(flat, plan[0])
+        if self.model.startswith("whisper-"):
+            emb = self.eng.whisper_forward(flat, plan[0], plan[1]).reshape(-1, self.d)
+        else:
+            emb = self.eng.clap_forward(flat, plan[0])
         if out is not None:
             out.copy_(emb)
             return out

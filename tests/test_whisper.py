@@ -80,3 +80,25 @@ def test_embeddings_match_transformers(engine, size):
     one = ml.get_embedding(clips[1] / 32768.0)           # plugin contract, single clip, batch-invariant
     assert one.dtype == np.float16 and one.shape == (2, ml.num_features)
     assert np.array_equal(one, got[1].astype(np.float16))
+
+
+@pytest.mark.gpu
+def test_whisper_fad_parity_on_identical_audio(engine):
+    """FAD (whisper-tiny embeddings, 2 rows per clip) on the same audio: CUDA path vs the reference's CPU path
+    (transformers forward + reference statistics / Frechet arithmetic)."""
+    from oracle import fad_oracle as fo
+    n = 40
+    sets = {"base": [synth.noise_clip(i, 4.0 + 0.1 * i, 16000) for i in range(n)],
+            "eval": [synth.musiclike_clip(i, 5.0 + 0.1 * i, 16000) for i in range(n)]}
+    ml = fk.WhisperModel("tiny", max_clips=8)
+    ml.load_model()
+    sd, start = ww.load_whisper_state(size="tiny")
+    model, fe = wo.build(sd, start)
+    gpu = {k: np.concatenate(ml.embed_pcm_batch(v)) for k, v in sets.items()}
+    cpu = {k: np.concatenate([wo.embed(c / 32768.0, model, fe, start) for c in v]) for k, v in sets.items()}
+    assert gpu["eval"].shape == cpu["eval"].shape == (2 * n, 384)
+    fad_gpu = fk.calc_frechet_distance(*fk.calc_embd_statistics(gpu["base"]), *fk.calc_embd_statistics(gpu["eval"]))
+    fad_cpu = fo.frechet_distance(*fo.embd_statistics(cpu["base"]), *fo.embd_statistics(cpu["eval"]))
+    rel = abs(fad_gpu - fad_cpu) / abs(fad_cpu)
+    print(f"whisper-tiny FAD gpu {fad_gpu:.6f} cpu reference path {fad_cpu:.6f} rel {rel:.2e}")
+    assert rel < 1e-4, (fad_gpu, fad_cpu, rel)
