@@ -58,6 +58,8 @@ SIGNATURES = {
     "fad_whisper_load": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),
     "fad_whisper_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_whisper_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "fad_encodec_load": (C.c_int, [c_vp, c_vp, C.c_int, c_ll]),
+    "fad_encodec_forward": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp]),
     "fad_resample_geometry": (C.c_int, [C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "fad_resample_length": (c_ll, [C.c_int, C.c_int, c_ll]),
     "fad_resample_bank": (C.c_int, [C.c_int, C.c_int, c_vp]),
@@ -295,6 +297,23 @@ class Engine:
         raw = buf[: n * 3000 * 80].view(n, 3000, 80)
         mx = buf[n * 3000 * 80:].view(n, 1, 1)
         return (torch.maximum(raw, mx - 8.0) + 4.0) / 4.0
+
+    # ------------------------------------------------------------------ Encodec
+    def encodec_load(self, tensors: list, max_chunk_samples: int = 16 * 240000):
+        keep = [t.contiguous() for t in tensors]
+        arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
+        _check(lib().fad_encodec_load(self._h, arr, len(keep), int(max_chunk_samples)))
+
+    def encodec_forward(self, pcm: torch.Tensor) -> torch.Tensor:
+        """pcm int16 [n_clips, T] (cuda, 24 kHz, equal lengths) -> fp16 [n_clips, ceil(T/320), 128]."""
+        assert pcm.dtype == torch.int16 and pcm.is_cuda and pcm.ndim == 2 and pcm.is_contiguous()
+        n, T = pcm.shape
+        frames = T
+        for r in (2, 4, 5, 8):
+            frames = -(-frames // r)
+        out = torch.empty((n, frames, 128), dtype=torch.float16, device=pcm.device)
+        _check(lib().fad_encodec_forward(self._h, pcm.data_ptr(), n, T, out.data_ptr(), _stream()))
+        return out
 
     # -------------------------------------------------------------- audio conversion
     @staticmethod

@@ -42,7 +42,7 @@ struct ConvGemmParams {
     float lo_scale;            // WMODE 2: 2^-s of the E4M3 low parts
     int ld_out, n_valid;       // un-pooled outputs: row stride and number of columns actually stored
                                // (Cout is padded to the tile width; columns >= n_valid are dropped)
-    int relu, pool;            // relu: 0 = none, 1 = ReLU, 2 = GELU (erf form)
+    int relu, pool;            // relu: 0 = none, 1 = ReLU, 2 = GELU (erf form), 3 = ELU
     const float* bias;         // [Cout]
     __half* out;               // NHWC fp16 [NB, H(/2), W(/2), Cout]; may be null when out_f32 is set
     float* out_f32;            // optional fp32 copy of the un-pooled output (may be null)
@@ -385,6 +385,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 } else if (p.relu == 2) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                } else if (p.relu == 3) {                           // ELU (alpha = 1): SEANet's activation
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
                 }
                 uint32_t h2[16];
 #pragma unroll

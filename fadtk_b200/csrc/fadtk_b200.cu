@@ -23,6 +23,7 @@
 #include "clap.cuh"
 #include "resample.cuh"
 #include "whisper.cuh"
+#include "encodec.cuh"
 
 namespace {
 
@@ -158,6 +159,7 @@ struct fad_handle {
 
     void* clap_state = nullptr;  // ClapState (clap_host.inc)
     void* whisper_state = nullptr;   // WhisperState (whisper_host.inc)
+    void* encodec_state = nullptr;   // EncodecState (encodec_host.inc)
 
     // optional per-category timing with CUDA events recorded on the launching stream
     bool prof_on = false;
@@ -458,12 +460,14 @@ int fad_create(int device, int max_examples, fad_handle** out) {
 
 static void clap_free_state(void* p);
 static void whisper_free_state(void* p);
+static void encodec_free_state(void* p);
 
 int fad_destroy(fad_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     clap_free_state(h->clap_state);
     whisper_free_state(h->whisper_state);
+    encodec_free_state(h->encodec_state);
     void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
                     h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal, h->frb_buf, h->rs_bank, h->rs_mono};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -942,3 +946,4 @@ int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, c
 static void clap_free_state(void* p) { clap_free(reinterpret_cast<ClapState*>(p)); }
 
 #include "whisper_host.inc"
+#include "encodec_host.inc"

@@ -260,6 +260,66 @@ class WhisperModel(ModelLoader):
         return list(emb)                                   # [2, d_model] per clip
 
 
+class EncodecEmbModel(ModelLoader):
+    """Encodec (https://github.com/facebookresearch/encodec) continuous encoder output, B200-native
+    (model_loader.py:111-176).  ``variant='24k'`` (registry name ``encodec-emb``): the causal SEANet encoder
+    of ``EncodecModel.encodec_model_24khz()`` on the whole file -> [T/320, 128].  The 48 kHz variant
+    (non-causal, time-group norm, 1-s segments) is not built.
+    """
+
+    def __init__(self, variant: str = '24k', checkpoint=None, seed: int = 0, max_chunk_samples: int = 16 * 240000):
+        super().__init__('encodec-emb' if variant == '24k' else f"encodec-emb-{variant}", 128,
+                         sr=24000 if variant == '24k' else 48000)
+        self.variant = variant
+        self.checkpoint = checkpoint
+        self.seed = seed
+        self.max_chunk_samples = max_chunk_samples
+        self._engine = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st["model"] = None
+        return st
+
+    def load_model(self):
+        if self.variant != '24k':
+            raise NotImplementedError("encodec-emb-48k has no sm_100a forward pass yet")
+        from . import _native, weights_encodec
+        self._engine = _native.engine()
+        self._engine.encodec_load(weights_encodec.pack_encodec(weights_encodec.load_encodec_state(self.checkpoint, self.seed)),
+                                  self.max_chunk_samples)
+        self.model = self._engine
+        self.device = self._engine.torch_device
+
+    def load_wav(self, wav_file):
+        """The reference cuts files longer than 3 minutes (model_loader.py:171-173)."""
+        wav = super().load_wav(wav_file)
+        return wav[: 3 * 60 * self.sr]
+
+    def _get_embedding(self, audio: np.ndarray):
+        return self.embed_equal_length([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
+
+    def embed_pcm_batch(self, clips):
+        """Clips of equal length share one launch sequence; others are embedded one length group at a time."""
+        clips = [np.asarray(c, dtype=np.int16) for c in clips]
+        out = [None] * len(clips)
+        groups = {}
+        for i, c in enumerate(clips):
+            groups.setdefault(len(c), []).append(i)
+        for _, idx in groups.items():
+            for i, e in zip(idx, self.embed_equal_length([clips[i] for i in idx])):
+                out[i] = e.cpu().numpy()
+        return out
+
+    def embed_equal_length(self, clips):
+        if self._engine is None:
+            raise RuntimeError("load_model() has not been called")
+        eng = self._engine
+        pcm = torch.from_numpy(np.stack(clips)).pin_memory().to(eng.torch_device, non_blocking=True)
+        return list(eng.encodec_forward(pcm))
+
+
 class UnbuiltModel(ModelLoader):
     """Registry entry whose forward pass has no B200-native implementation yet.
 
@@ -287,7 +347,7 @@ def get_all_models() -> list[ModelLoader]:
         CLAPLaionModel('audio'), CLAPLaionModel('music'),
         VGGishModel(),
         *[UnbuiltModel("MERT-v1-95M" + ("" if v == 12 else f"-{v}"), 768, 24000) for v in range(1, 13)],
-        UnbuiltModel("encodec-emb", 128, 24000), UnbuiltModel("encodec-emb-48k", 128, 48000),
+        EncodecEmbModel('24k'), EncodecEmbModel('48k'),
         *_layered("w2v2-base", 768, 12, 12), *_layered("w2v2-large", 1024, 24, 24),
         *_layered("hubert-base", 768, 12, 12), *_layered("hubert-large", 1024, 24, 24),
         *_layered("wavlm-base", 768, 12, 12), *_layered("wavlm-base-plus", 768, 12, 12),

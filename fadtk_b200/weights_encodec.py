@@ -1,0 +1,109 @@
+"""Encodec-24 kHz SEANet encoder parameters: seeded synthetic set, checkpoint loading, device packing.
+
+State-dict keys are those of ``transformers.EncodecModel(...).encoder`` (weight-normalised convs stored as
+``parametrizations.weight.original0`` = g and ``original1`` = v; LSTM ``weight_ih_l*`` ...), the HF port of
+facebookresearch/encodec's ``EncodecModel.encodec_model_24khz().encoder`` that the reference calls
+(model_loader.py:123-130, 160).  No checkpoint exists offline: tests and benches use seeded synthetic
+parameters with the real architecture.
+"""
+from __future__ import annotations
+
+import math
+import os
+from pathlib import Path
+
+import torch
+
+from .weights import split_hi_lo_tiles
+
+RATIOS = (2, 4, 5, 8)          # encoder order (upsampling_ratios reversed)
+N_FILTERS, DIM, LSTM_LAYERS = 32, 128, 2
+# (HF layer index, kind, Cin, Cout, kernel, stride) in execution order
+def conv_table():
+    t = [(0, "in", 1, N_FILTERS, 7, 1)]
+    ch, idx = N_FILTERS, 1
+    for r in RATIOS:
+        t += [(idx, "res", ch, ch, 3, 1), (idx + 2, "down", ch, 2 * ch, 2 * r, r)]
+        ch, idx = 2 * ch, idx + 3
+    t.append((idx + 2, "out", ch, DIM, 7, 1))       # idx = 13 (LSTM), 14 ELU, 15 conv
+    return t
+
+
+def _conv_keys(prefix):
+    return prefix + ".conv.parametrizations.weight.original0", prefix + ".conv.parametrizations.weight.original1", prefix + ".conv.bias"
+
+
+def synthetic_encodec_state(seed: int = 0) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(prefix, cout, cin, k):
+        kg, kv, kb = _conv_keys(prefix)
+        v = torch.randn((cout, cin, k), generator=g)
+        sd[kv] = v
+        sd[kg] = (math.sqrt(2.0) * (0.8 + 0.4 * torch.rand((cout, 1, 1), generator=g)))      # |w| ~ sqrt(2) per row: unit-gain-ish
+        sd[kb] = 0.02 * torch.randn((cout,), generator=g)
+
+    for idx, kind, cin, cout, k, s in conv_table():
+        if kind == "res":
+            conv(f"layers.{idx}.block.1", cin // 2, cin, 3)
+            conv(f"layers.{idx}.block.3", cin, cin // 2, 1)
+            conv(f"layers.{idx}.shortcut", cin, cin, 1)
+        else:
+            conv(f"layers.{idx}", cout, cin, k)
+    h = 16 * N_FILTERS
+    for l in range(LSTM_LAYERS):
+        for name, shape in (("weight_ih", (4 * h, h)), ("weight_hh", (4 * h, h)), ("bias_ih", (4 * h,)), ("bias_hh", (4 * h,))):
+            sd[f"layers.13.lstm.{name}_l{l}"] = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(h)
+    return sd
+
+
+def load_encodec_state(path=None, seed: int = 0) -> dict:
+    path = path or os.environ.get("FADTK_ENCODEC_CKPT")
+    if path and Path(path).exists():
+        raw = torch.load(path, map_location="cpu")
+        raw = raw.get("state_dict", raw)
+        return {k.removeprefix("encoder."): v.float().contiguous() for k, v in raw.items() if "layers." in k and not k.startswith(("decoder.", "quantizer."))}
+    return synthetic_encodec_state(seed)
+
+
+def effective_weight(sd: dict, prefix: str) -> torch.Tensor:
+    """weight_norm: w = g * v / ||v|| with the norm over (in, k) per output channel -> [Cout, Cin, k]"""
+    kg, kv, _ = _conv_keys(prefix)
+    v = sd[kv]
+    return sd[kg] * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)
+
+
+def _pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def _gemm_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, k] -> fp16 hi/lo tiles [2*Npad, Kpad], column = tap*Cin + c (the im2col order)"""
+    cout, cin, k = w.shape
+    m = torch.zeros((_pad_to(cout, 128), _pad_to(k * cin, 64)))
+    m[:cout, :k * cin] = w.permute(0, 2, 1).reshape(cout, k * cin)
+    return split_hi_lo_tiles(m)
+
+
+def _bias(b, n):
+    out = torch.zeros((_pad_to(n, 128),))
+    out[:b.shape[0]] = b
+    return out
+
+
+def pack_encodec(sd: dict) -> list:
+    """-> contiguous CPU tensors in the order fad_encodec_load expects (csrc/encodec_host.inc):
+    per conv (execution order; a residual block contributes conv3, conv1, shortcut): weight tiles, bias;
+    then per LSTM layer: W_ih tiles [2048, 512], W_hh tiles over [h_hi | h_lo] = [2048, 1024], bias_ih + bias_hh."""
+    out = []
+    for idx, kind, cin, cout, k, s in conv_table():
+        names = [f"layers.{idx}.block.1", f"layers.{idx}.block.3", f"layers.{idx}.shortcut"] if kind == "res" else [f"layers.{idx}"]
+        for p in names:
+            w = effective_weight(sd, p)
+            out += [_gemm_weight(w), _bias(sd[p + ".conv.bias"], w.shape[0])]
+    for l in range(LSTM_LAYERS):
+        wih, whh = sd[f"layers.13.lstm.weight_ih_l{l}"], sd[f"layers.13.lstm.weight_hh_l{l}"]
+        out += [split_hi_lo_tiles(wih.contiguous()), split_hi_lo_tiles(torch.cat([whh, whh], 1).contiguous()),
+                (sd[f"layers.13.lstm.bias_ih_l{l}"] + sd[f"layers.13.lstm.bias_hh_l{l}"]).float().contiguous()]
+    return out

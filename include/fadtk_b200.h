@@ -132,6 +132,16 @@ int fad_whisper_forward(fad_handle* h, const int16_t* pcm, const long long* clip
 int fad_whisper_logmel(fad_handle* h, const int16_t* pcm, const long long* clip_start, const int* clip_len,
                        long long n_clips, float* out, void* stream);
 
+/* ---- Encodec: replaces EncodecEmbModel.load_model / _get_frame for the 24 kHz variant
+ * (fadtk/model_loader.py:123-130, 155-166): EncodecModel.encodec_model_24khz().encoder(audio) -> [T/320, 128].
+ * tensors_host: 42 host pointers in the order documented at the top of csrc/encodec_host.inc, packed by
+ * fadtk_b200/weights_encodec.py (weight-norm folded, im2col column order, fp16 hi/lo tiles).
+ * max_chunk_samples bounds clips x samples per convolution chunk (0.55 KB of workspace per sample). */
+int fad_encodec_load(fad_handle* h, const void* const* tensors_host, int n_tensors, long long max_chunk_samples);
+/* pcm: int16 mono 24 kHz [n_clips][T] (device), all clips of one call have the same length T.
+ * emb_out: fp16 [n_clips][ceil(T/320)][128] (device). */
+int fad_encodec_forward(fad_handle* h, const int16_t* pcm, long long n_clips, int T, void* emb_out_f16, void* stream);
+
 /* ---- statistics: replaces calc_embd_statistics (fadtk/fad.py:42-48) and
  * _process_file / calculate_embd_statistics_online (fadtk/utils.py:13-46) ----------------
  * Packed fp64 accumulator of length fad_stats_acc_len(d):

@@ -1,0 +1,70 @@
+"""CPU restatement of the Encodec-24 kHz SEANet encoder as the reference uses it (test infrastructure only).
+
+Reference call sites: fadtk/model_loader.py:123-130 (EncodecModel.encodec_model_24khz(), bandwidth irrelevant
+for the encoder), :160-166 (``self.model.encoder(audio)`` -> [1, 128, T/320] -> transposed [T/320, 128]).
+The ``encodec`` package (0.1.1, uv.lock) is not installed here; this restates its SEANetEncoder (causal
+reflect-padded weight-normalised convs, ELU, residual blocks with conv shortcut, 2-layer LSTM with skip) and
+tests/test_encodec_oracle.py pins it to transformers' independent port (EncodecModel.encoder) with shared
+random weights.  Parity against the real facebook checkpoint is unpinned (no weights offline).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from fadtk_b200.weights_encodec import conv_table, effective_weight, LSTM_LAYERS
+
+
+def _causal_conv(x, w, b, stride):
+    """x [B, C, T]; causal SConv1d: pad (k - stride) on the left, extra on the right so the last window is full; reflect."""
+    k = w.shape[-1]
+    pad_total = k - stride
+    n_frames = (x.shape[-1] - k + pad_total) / stride + 1
+    ideal = (math.ceil(n_frames) - 1) * stride + (k - pad_total)
+    extra = ideal - x.shape[-1]
+    x = _reflect_pad(x, pad_total, extra)
+    return F.conv1d(x, w, b, stride=stride)
+
+
+def _reflect_pad(x, left, right):
+    length = x.shape[-1]
+    max_pad = max(left, right)
+    extra = 0
+    if length <= max_pad:                                      # encodec pad1d: tiny inputs get zeros first
+        extra = max_pad - length + 1
+        x = F.pad(x, (0, extra))
+    y = F.pad(x, (left, right), mode="reflect")
+    return y[..., : y.shape[-1] - extra] if extra else y
+
+
+@torch.no_grad()
+def encoder(x: torch.Tensor, sd: dict) -> torch.Tensor:
+    """[B, 1, T] float32 -> [B, 128, ceil(T / 320)]"""
+    conv = lambda t, p, s=1: _causal_conv(t, effective_weight(sd, p), sd[p + ".conv.bias"], s)
+    for idx, kind, cin, cout, k, s in conv_table():
+        if kind == "in":
+            x = conv(x, f"layers.{idx}")
+        elif kind == "res":
+            h = conv(F.elu(x), f"layers.{idx}.block.1")
+            h = conv(F.elu(h), f"layers.{idx}.block.3")
+            x = conv(x, f"layers.{idx}.shortcut") + h
+        elif kind == "down":
+            x = conv(F.elu(x), f"layers.{idx}", s)
+        else:                                                  # LSTM with skip, ELU, last conv
+            seq = x.permute(2, 0, 1)
+            hsz = seq.shape[-1]
+            lstm = torch.nn.LSTM(hsz, hsz, LSTM_LAYERS)
+            lstm.load_state_dict({k_.split("lstm.")[1]: v for k_, v in sd.items() if ".lstm." in k_})
+            y = lstm(seq)[0] + seq
+            x = conv(F.elu(y.permute(1, 2, 0)), f"layers.{idx}")
+    return x
+
+
+@torch.no_grad()
+def embed(wave: np.ndarray, sd: dict) -> np.ndarray:
+    """What ModelLoader.get_embedding returns for encodec-emb: fp16 [T/320, 128]."""
+    x = torch.from_numpy(np.asarray(wave, dtype=np.float32)).reshape(1, 1, -1)
+    return encoder(x, sd)[0].transpose(0, 1).numpy().astype(np.float16)

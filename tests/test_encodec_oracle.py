@@ -1,0 +1,40 @@
+"""Pin oracle/encodec_oracle.py to an independent implementation of the same architecture: transformers'
+EncodecModel.encoder (default config == encodec_24khz), with shared random weights.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from fadtk_b200 import weights_encodec as we
+from oracle import encodec_oracle as eo
+
+
+@pytest.mark.parametrize("length", [24000, 24000 * 3 + 137, 500])
+def test_encoder_matches_independent_hf_port(length):
+    tr = pytest.importorskip("transformers")
+    sd = we.synthetic_encodec_state(3)
+    cfg = tr.EncodecConfig()
+    assert list(cfg.upsampling_ratios)[::-1] == list(we.RATIOS) and cfg.use_causal_conv and cfg.norm_type == "weight_norm"
+    enc = tr.EncodecModel(cfg).eval().encoder
+    hf = enc.state_dict()
+    assert set(hf) == set(sd) and all(hf[k].shape == sd[k].shape for k in hf)
+    enc.load_state_dict(sd)
+    x = 0.3 * torch.randn((2, 1, length), generator=torch.Generator().manual_seed(length))
+    with torch.no_grad():
+        want = enc(x)
+    got = eo.encoder(x, sd)
+    assert got.shape == want.shape == (2, 128, -(-length // 320))
+    assert torch.allclose(got, want, atol=2e-5 * want.abs().max().item() + 1e-6), (got - want).abs().max()
+
+
+def test_embed_shape_and_packing():
+    sd = we.synthetic_encodec_state(0)
+    e = eo.embed(0.1 * np.random.default_rng(0).standard_normal(24000 * 2), sd)
+    assert e.shape == (150, 128) and e.dtype == np.float16                     # 75 frames per second
+    pk = we.pack_encodec(sd)
+    n_convs = 1 + 4 * 4 + 1
+    assert len(pk) == 2 * n_convs + 3 * 2
+    assert pk[0].shape == (2 * 128, 64) and pk[0].dtype == torch.float16       # conv0: 32 x (7 taps x 1 ch) -> [128 pad, 64 pad]
+    w = we.effective_weight(sd, "layers.3")                                     # first down conv [64, 32, 4]
+    assert torch.allclose(w.flatten(1).norm(dim=1), sd["layers.3.conv.parametrizations.weight.original0"].flatten())
+    g = pk[2 * 4]                                                               # its GEMM weight: column = tap * 32 + c
+    assert g.shape == (2 * 128, 128) and torch.equal(g[5, 2 * 32 + 7].float(), w[5, 7, 2].to(torch.float16).float())
