@@ -57,6 +57,22 @@ def _whisper_gemm_flop(d, n_enc, n_dec):
 
 CLAP_GEMM_FLOP = _htsat_gemm_flop(96, (2, 2, 6, 2))
 WHISPER_SMALL_GEMM_FLOP = _whisper_gemm_flop(768, 12, 12)
+
+
+def _encodec_gemm_flop(T=240000):
+    """algorithmic conv + LSTM FLOPs of the 24 kHz SEANet encoder per clip of T samples (2*M*N*K, no padding)"""
+    fl, ch, t = 2 * T * 32 * 7, 32, T
+    for r in (2, 4, 5, 8):
+        fl += 2 * t * (ch // 2) * 3 * ch + 2 * t * ch * (ch // 2) + 2 * t * ch * ch     # conv3, conv1, shortcut
+        t = -(-t // r)
+        fl += 2 * t * 2 * ch * 2 * r * ch                                               # down conv
+        ch *= 2
+    fl += 2 * (2 * t * 2048 * 512 * 2)                                                 # LSTM: input + recurrent, 2 layers
+    fl += 2 * t * 128 * 7 * 512
+    return fl
+
+
+ENCODEC_GEMM_FLOP = _encodec_gemm_flop()
 CLAP_MUSIC_GEMM_FLOP = _htsat_gemm_flop(128, (2, 2, 12, 2))
 
 MODELS = {
@@ -70,6 +86,10 @@ MODELS = {
     "clap-laion-music": dict(sr=48000, clips=250, baseline_clips=50, chunk_clips=25, d=512,
                              workload="clap-laion-music (HTSAT-base) FAD, {clips} x 10 s synthetic 48 kHz clips per GPU vs {base}-clip baseline",
                              rows_flop=CLAP_MUSIC_GEMM_FLOP),
+    "encodec-emb": dict(sr=24000, clips=512, baseline_clips=64, chunk_clips=128, d=128,
+                        workload="encodec-emb (24 kHz SEANet encoder) FAD, {clips} x 10 s synthetic 24 kHz clips per GPU (750 rows per clip) "
+                                 "vs {base}-clip baseline (BASELINE.json configs[3] embedding stage)",
+                        rows_flop=ENCODEC_GEMM_FLOP),
     "whisper-small": dict(sr=16000, clips=256, baseline_clips=64, chunk_clips=32, d=768,
                           workload="whisper-small FAD, {clips} x 10 s synthetic 16 kHz clips per GPU (each padded to 30 s, 2 rows per clip) "
                                    "vs {base}-clip baseline (BASELINE.json configs[4] embedding stage)",
@@ -128,6 +148,9 @@ def oracle_embed_fn(model: str, state):
     if model == "vggish":
         from oracle import vggish_oracle as vo
         return lambda pcm: vo.embed(vo.load_wav_semantics(pcm), state)
+    if model == "encodec-emb":
+        from oracle import encodec_oracle as eo
+        return lambda pcm: eo.embed(pcm / 32768.0, state)
     if model.startswith("whisper-"):
         from fadtk_b200 import weights_whisper
         from oracle import whisper_oracle as wo
@@ -202,6 +225,9 @@ def main():
     from fadtk_b200 import synth, weights, weights_clap
     if args.model == "vggish":
         state = weights.synthetic_vggish_state(0)
+    elif args.model == "encodec-emb":
+        from fadtk_b200 import weights_encodec
+        state = weights_encodec.synthetic_encodec_state(0)
     elif args.model.startswith("whisper-"):
         from fadtk_b200 import weights_whisper
         state = weights_whisper.synthetic_whisper_state(0, args.model.split("-", 1)[1])
@@ -244,6 +270,8 @@ def main():
     eng = _native.Engine(local_rank, max_examples=args.chunk_clips * ROWS_PER_CLIP)
     if args.model == "vggish":
         eng.vggish_load(weights.pack_vggish(state))
+    elif args.model == "encodec-emb":
+        eng.encodec_load(weights_encodec.pack_encodec(state), max_chunk_samples=16 * int(CLIP_SECONDS * sr))
     elif args.model.startswith("whisper-"):
         eng.whisper_load(weights_whisper.config_of(state), weights_whisper.pack_whisper(state, weights_whisper.SYNTH_START),
                          max_clips=args.chunk_clips)
@@ -294,7 +322,7 @@ def main():
 
     # ---- roofline of the dominant kernel: the tcgen05 conv/FC (GEMM) kernel
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    rows = args.clips * (1 if args.model.startswith("whisper-") else ROWS_PER_CLIP) * args.steps   # examples (VGGish) / 10-s windows (CLAP) / clips (Whisper)
+    rows = args.clips * (1 if args.model.startswith("whisper-") or args.model == "encodec-emb" else ROWS_PER_CLIP) * args.steps   # examples (VGGish) / 10-s windows (CLAP) / clips (Whisper)
     gemm_keys = list(UMMA_LAYER_FLOP) if args.model == "vggish" else ["clap_gemm"]
     umma_ms = sum(prof[k][0] for k in gemm_keys if k in prof)
     umma_launch = sum(prof[k][1] for k in gemm_keys if k in prof)

@@ -41,6 +41,12 @@ class EvalSetFAD:
         elif model in ("clap-laion-audio", "clap-laion-music"):
             self.d = 512
             self.rows_per_clip = -(-self.clip_samples // 48000)
+        elif model == "encodec-emb":
+            self.d = 128
+            r = self.clip_samples
+            for ratio in (2, 4, 5, 8):                       # ceil at every down-sampling conv
+                r = -(-r // ratio)
+            self.rows_per_clip = r
         elif model.startswith("whisper-"):
             from .model_loader import WhisperModel
             self.d = WhisperModel.DIMS[model.split("-", 1)[1]]
@@ -60,6 +66,8 @@ class EvalSetFAD:
             if self.model == "vggish":
                 ex, _ = self.eng.vggish_plan(off)
                 self._plans[n_clips] = (torch.from_numpy(ex).to(self.dev),)
+            elif self.model == "encodec-emb":
+                self._plans[n_clips] = ()
             elif self.model.startswith("whisper-"):
                 self._plans[n_clips] = (torch.from_numpy(off[:-1].copy()).to(self.dev),
                                         torch.full((n_clips,), self.clip_samples, dtype=torch.int32, device=self.dev))
@@ -73,7 +81,9 @@ class EvalSetFAD:
         flat = pcm_dev.reshape(-1)
         if self.model == "vggish":
             return self.eng.vggish_forward(flat, plan[0], out)
-        if self.model.startswith("whisper-"):
+        if self.model == "encodec-emb":
+            emb = self.eng.encodec_forward(pcm_dev.contiguous()).reshape(-1, self.d)
+        elif self.model.startswith("whisper-"):
             emb = self.eng.whisper_forward(flat, plan[0], plan[1]).reshape(-1, self.d)
         else:
             emb = self.eng.clap_forward(flat, plan[0])
