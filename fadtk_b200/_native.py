@@ -58,6 +58,8 @@ SIGNATURES = {
     "fad_whisper_load": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int]),
     "fad_whisper_forward": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_whisper_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "fad_w2v_load": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int]),
+    "fad_w2v_forward": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_encodec_load": (C.c_int, [c_vp, c_vp, C.c_int, c_ll]),
     "fad_encodec_forward": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp]),
     "fad_resample_geometry": (C.c_int, [C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -297,6 +299,30 @@ class Engine:
         raw = buf[: n * 3000 * 80].view(n, 3000, 80)
         mx = buf[n * 3000 * 80:].view(n, 1, 1)
         return (torch.maximum(raw, mx - 8.0) + 4.0) / 4.0
+
+    # ------------------------------------------------------- wav2vec 2.0 / HuBERT / MERT
+    def w2v_load(self, cfg: tuple, tensors: list, max_clips: int = 8, max_len: int = 16000 * 30):
+        """cfg = (d_model, heads, layers, ffn); tensors from weights_w2v.pack_w2v."""
+        keep = [t.contiguous() for t in tensors]
+        arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
+        c = (C.c_int * 4)(*[int(v) for v in cfg])
+        _check(lib().fad_w2v_load(self._h, c, arr, len(keep), int(max_clips), int(max_len)))
+        self._w2v_d = int(cfg[0])
+
+    @staticmethod
+    def w2v_frames(n_samples: int) -> int:
+        t = n_samples
+        for k, s in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
+            t = (t - k) // s + 1
+        return t
+
+    def w2v_forward(self, pcm: torch.Tensor, layer: int) -> torch.Tensor:
+        """pcm int16 [n_clips, L] (cuda, equal lengths) -> fp16 [n_clips, frames, d_model] = hidden_states[layer]."""
+        assert pcm.dtype == torch.int16 and pcm.is_cuda and pcm.ndim == 2 and pcm.is_contiguous()
+        n, L = pcm.shape
+        out = torch.empty((n, self.w2v_frames(L), self._w2v_d), dtype=torch.float16, device=pcm.device)
+        _check(lib().fad_w2v_forward(self._h, pcm.data_ptr(), n, L, int(layer), out.data_ptr(), _stream()))
+        return out
 
     # ------------------------------------------------------------------ Encodec
     def encodec_load(self, tensors: list, max_chunk_samples: int = 16 * 240000):

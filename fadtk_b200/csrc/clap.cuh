@@ -267,8 +267,9 @@ clap_patch_embed_kernel(const float* __restrict__ lm, const int* __restrict__ fr
 // out: fp16 [rows, ld_out] (columns >= width zero filled).
 template <int CHUNKS, int L>
 __global__ void __launch_bounds__(256)
-clap_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-               long long n_rows, int C, int ld_out, int res, int shift, int mode, __half* __restrict__ out)
+clap_ln_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
+               long long n_rows, int C, int ld_out, int res, int shift, int mode, __half* __restrict__ out,
+               float* out32 = nullptr /* optional fp32 copy of the normalised row (row order o, stride width); may alias x */)
 {
     constexpr int R = 32 / L;                                      // rows per warp
     constexpr int width = 4 * L * CHUNKS;
@@ -328,6 +329,10 @@ clap_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
         pk.x = *reinterpret_cast<const uint32_t*>(&h0);
         pk.y = *reinterpret_cast<const uint32_t*>(&h1);
         *reinterpret_cast<uint2*>(dst + i) = pk;
+        if (out32 != nullptr)                                      // post-LN transformers: the normalised row IS the new stream
+            *reinterpret_cast<float4*>(out32 + o * width + i) =
+                make_float4((v[j].x - mean) * rstd * g4.x + b4.x, (v[j].y - mean) * rstd * g4.y + b4.y,
+                            (v[j].z - mean) * rstd * g4.z + b4.z, (v[j].w - mean) * rstd * g4.w + b4.w);
     }
     for (int i = width + li; i < ld_out; i += L) dst[i] = __float2half_rn(0.f);
 }

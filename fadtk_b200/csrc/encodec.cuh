@@ -18,14 +18,15 @@ pcm_to_f32_kernel(const int16_t* __restrict__ pcm, long long n, float* __restric
         out[i] = (float)pcm[i] * (1.0f / 32768.0f);                // torchaudio.load normalisation (model_loader.py:168)
 }
 
-// a[(b*T_out + t)][tap*C + c] = act(x[b][t*stride + tap - (k - stride)][c]), causal SConv1d padding:
-// (k - stride) samples on the left, right padding so the last window is full, both by reflection.
+// a[(b*T_out + t)][tap*C + c] = act(x[b][t*stride + tap - pad_left][c]).  Encodec's causal SConv1d pads
+// pad_left = k - stride samples on the left and completes the last window on the right, both by reflection;
+// a "valid" convolution (wav2vec2 feature encoder) passes pad_left = 0 and never leaves the signal.
 // x: fp32 [B][T_in][C]; a: fp16 [B*T_out][Kpad] (columns >= k*C are zero).  One thread per 8 columns.
 __global__ void __launch_bounds__(256)
-encodec_im2col_kernel(const float* __restrict__ x, int T_in, int C, int k, int stride, int elu, int T_out, int Kpad,
+encodec_im2col_kernel(const float* __restrict__ x, int T_in, int C, int k, int stride, int pad_left, int elu, int T_out, int Kpad,
                       long long n_rows, __half* __restrict__ a)
 {
-    const int vecs = Kpad / 8, pad_left = k - stride, KC = k * C;
+    const int vecs = Kpad / 8, KC = k * C;
     for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n_rows * vecs; e += (long long)gridDim.x * 256) {
         const long long row = e / vecs;
         const int col0 = (int)(e - row * vecs) * 8;

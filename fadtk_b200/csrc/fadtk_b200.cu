@@ -24,6 +24,7 @@
 #include "resample.cuh"
 #include "whisper.cuh"
 #include "encodec.cuh"
+#include "wav2vec.cuh"
 
 namespace {
 
@@ -160,6 +161,7 @@ struct fad_handle {
     void* clap_state = nullptr;  // ClapState (clap_host.inc)
     void* whisper_state = nullptr;   // WhisperState (whisper_host.inc)
     void* encodec_state = nullptr;   // EncodecState (encodec_host.inc)
+    void* w2v_state = nullptr;       // W2vState (wav2vec_host.inc)
 
     // optional per-category timing with CUDA events recorded on the launching stream
     bool prof_on = false;
@@ -461,6 +463,7 @@ int fad_create(int device, int max_examples, fad_handle** out) {
 static void clap_free_state(void* p);
 static void whisper_free_state(void* p);
 static void encodec_free_state(void* p);
+static void w2v_free_state(void* p);
 
 int fad_destroy(fad_handle* h) {
     if (!h) return 0;
@@ -468,6 +471,7 @@ int fad_destroy(fad_handle* h) {
     clap_free_state(h->clap_state);
     whisper_free_state(h->whisper_state);
     encodec_free_state(h->encodec_state);
+    w2v_free_state(h->w2v_state);
     void* ptrs[] = {h->d_twiddle, h->d_hann, h->d_melw, h->d_mel_start, h->d_mel_count, h->conv1_w, h->conv1_b,
                     h->logmel, h->ws_tiles, h->ws_sums, h->gather_buf, h->fr_buf, h->fr_scal, h->frb_buf, h->rs_bank, h->rs_mono};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -947,3 +951,4 @@ static void clap_free_state(void* p) { clap_free(reinterpret_cast<ClapState*>(p)
 
 #include "whisper_host.inc"
 #include "encodec_host.inc"
+#include "wav2vec_host.inc"

@@ -320,6 +320,91 @@ class EncodecEmbModel(ModelLoader):
         return list(eng.encodec_forward(pcm))
 
 
+class Wav2VecFamilyModel(ModelLoader):
+    """wav2vec 2.0 / HuBERT / MERT hidden-state embedders, B200-native (model_loader.py:254-288, 525-596).
+
+    One class for the three reference loaders whose checkpoints share the "group-norm conv feature encoder +
+    post-LN transformer" architecture: ``w2v2-base[-k]`` (facebook/wav2vec2-base-960h), ``hubert-base[-k]``
+    (facebook/hubert-base-ls960) and ``MERT-v1-95M[-k]`` (24 kHz).  The reference's processor + model call +
+    ``hidden_states[layer]`` is one launch sequence that stops after ``layer`` transformer layers.
+    Files longer than ``limit_minutes`` are truncated like the reference does.
+    """
+
+    def __init__(self, family: str, name: str, layer: int, sr: int, checkpoint=None, seed: int = 0, limit_minutes: int = 6,
+                 max_clips: int = 8):
+        super().__init__(name, 768, sr)
+        self.family = family
+        self.layer = layer
+        self.limit = limit_minutes * 60 * sr
+        self.checkpoint = checkpoint
+        self.seed = seed
+        self.max_clips = max_clips
+        self._engine = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st["model"] = None
+        st["_packed"] = None
+        return st
+
+    def load_model(self):
+        from . import _native, weights_w2v
+        self._engine = _native.engine()
+        env = {"w2v2": "FADTK_W2V2_CKPT", "hubert": "FADTK_HUBERT_CKPT", "mert": "FADTK_MERT_CKPT"}[self.family]
+        state = weights_w2v.load_w2v_state(self.checkpoint, self.seed, env=env)
+        self._packed = (weights_w2v.config_of(state), weights_w2v.pack_w2v(state))
+        self._max_len = self.sr * 30                           # workspace: max_clips pieces of up to 30 s
+        self._engine.w2v_load(*self._packed, self.max_clips, max_len=self._max_len)
+        self.model = self._engine
+        self.device = self._engine.torch_device
+
+    def _get_embedding(self, audio: np.ndarray):
+        pcm = _as_pcm16(np.asarray(audio).reshape(-1))
+        if pcm.shape[0] > self.limit:
+            log.warning(f"Audio is too long ({pcm.shape[0] / self.sr / 60:.2f} minutes > {self.limit / self.sr / 60:.2f} minutes). Truncating.")
+            pcm = pcm[:self.limit]
+        return self.embed_equal_length([pcm])[0]
+
+    def embed_pcm_batch(self, clips):
+        clips = [np.asarray(c, dtype=np.int16)[:self.limit] for c in clips]
+        out = [None] * len(clips)
+        groups = {}
+        for i, c in enumerate(clips):
+            groups.setdefault(len(c), []).append(i)
+        for _, idx in groups.items():
+            for i, e in zip(idx, self.embed_equal_length([clips[i] for i in idx])):
+                out[i] = e.cpu().numpy()
+        return out
+
+    def embed_equal_length(self, clips):
+        if self._engine is None:
+            raise RuntimeError("load_model() has not been called")
+        eng = self._engine
+        L = len(clips[0])
+        if L > self._max_len:                                  # a long file (up to limit_minutes): one clip at a time
+            self._max_len = L
+            eng.w2v_load(*self._packed, 1, max_len=L)
+            self.max_clips = 1
+        pcm = torch.from_numpy(np.stack(clips)).pin_memory().to(eng.torch_device, non_blocking=True)
+        return list(eng.w2v_forward(pcm, self.layer))
+
+
+def W2V2Model(size: str, layer: int, **kw):
+    assert size == 'base', "w2v2-large has no sm_100a forward pass yet"
+    return Wav2VecFamilyModel("w2v2", "w2v2-base" + ("" if layer == 12 else f"-{layer}"), layer, 16000, **kw)
+
+
+def HuBERTModel(size: str, layer: int, **kw):
+    assert size == 'base', "hubert-large (stable layer norm) has no sm_100a forward pass yet"
+    return Wav2VecFamilyModel("hubert", "hubert-base" + ("" if layer == 12 else f"-{layer}"), layer, 16000, **kw)
+
+
+def MERTModel(size: str = 'v1-95M', layer: int = 12, **kw):
+    assert size == 'v1-95M', "only MERT-v1-95M is built"
+    return Wav2VecFamilyModel("mert", "MERT-v1-95M" + ("" if layer == 12 else f"-{layer}"), layer, 24000, **kw)
+
+
 class UnbuiltModel(ModelLoader):
     """Registry entry whose forward pass has no B200-native implementation yet.
 
@@ -346,10 +431,10 @@ def get_all_models() -> list[ModelLoader]:
         UnbuiltModel("clap-2023", 1024, 44100),
         CLAPLaionModel('audio'), CLAPLaionModel('music'),
         VGGishModel(),
-        *[UnbuiltModel("MERT-v1-95M" + ("" if v == 12 else f"-{v}"), 768, 24000) for v in range(1, 13)],
+        *[MERTModel('v1-95M', v) for v in range(1, 13)],
         EncodecEmbModel('24k'), EncodecEmbModel('48k'),
-        *_layered("w2v2-base", 768, 12, 12), *_layered("w2v2-large", 1024, 24, 24),
-        *_layered("hubert-base", 768, 12, 12), *_layered("hubert-large", 1024, 24, 24),
+        *[W2V2Model('base', v) for v in range(1, 13)], *_layered("w2v2-large", 1024, 24, 24),
+        *[HuBERTModel('base', v) for v in range(1, 13)], *_layered("hubert-large", 1024, 24, 24),
         *_layered("wavlm-base", 768, 12, 12), *_layered("wavlm-base-plus", 768, 12, 12),
         *_layered("wavlm-large", 1024, 24, 24),
         WhisperModel('tiny'), WhisperModel('small'), WhisperModel('base'), WhisperModel('medium'), WhisperModel('large'),

@@ -1,0 +1,115 @@
+"""wav2vec 2.0 / HuBERT / MERT parameters (group-norm feature encoder, post-LN transformer): seeded synthetic
+set, checkpoint loading, device packing.  State-dict keys are those of ``transformers.Wav2Vec2Model`` /
+``HubertModel`` (identical for these checkpoints), which is what the reference loads
+(model_loader.py:262-265, 540-544, 578-582).  No checkpoint exists offline."""
+from __future__ import annotations
+
+import math
+import os
+from pathlib import Path
+
+import torch
+
+from .weights import split_hi_lo_tiles
+
+CONV_KERNEL, CONV_STRIDE, CONV_DIM = (10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2), 512
+POS_K, POS_GROUPS = 128, 16
+BASE = dict(d=768, layers=12, ffn=3072)
+
+
+def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int = 3072) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def lin(key, out_f, in_f):
+        sd[key + ".weight"] = torch.randn((out_f, in_f), generator=g) * (1.0 / math.sqrt(in_f))
+        sd[key + ".bias"] = torch.randn((out_f,), generator=g) * 0.02
+
+    def ln(key, n):
+        sd[key + ".weight"] = 1.0 + 0.1 * torch.randn((n,), generator=g)
+        sd[key + ".bias"] = 0.05 * torch.randn((n,), generator=g)
+
+    cin = 1
+    for i, k in enumerate(CONV_KERNEL):
+        sd[f"feature_extractor.conv_layers.{i}.conv.weight"] = torch.randn((CONV_DIM, cin, k), generator=g) * math.sqrt(2.0 / (cin * k))
+        cin = CONV_DIM
+    ln("feature_extractor.conv_layers.0.layer_norm", CONV_DIM)
+    ln("feature_projection.layer_norm", CONV_DIM)
+    lin("feature_projection.projection", d, CONV_DIM)
+    cg = d // POS_GROUPS
+    sd["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = torch.randn((d, cg, POS_K), generator=g)
+    sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = 2.0 * (0.8 + 0.4 * torch.rand((1, 1, POS_K), generator=g))
+    sd["encoder.pos_conv_embed.conv.bias"] = 0.02 * torch.randn((d,), generator=g)
+    ln("encoder.layer_norm", d)
+    for i in range(layers):
+        p = f"encoder.layers.{i}."
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            lin(p + "attention." + n, d, d)
+        ln(p + "layer_norm", d)
+        lin(p + "feed_forward.intermediate_dense", ffn, d)
+        lin(p + "feed_forward.output_dense", d, ffn)
+        ln(p + "final_layer_norm", d)
+    return sd
+
+
+def load_w2v_state(path=None, seed: int = 0, env: str = "FADTK_W2V_CKPT", **cfg) -> dict:
+    path = path or os.environ.get(env)
+    if path and Path(path).exists():
+        raw = torch.load(path, map_location="cpu")
+        raw = raw.get("state_dict", raw)
+        drop = ("masked_spec_embed", "lm_head", "quantizer", "project_", "label_embs")
+        return {k.removeprefix("wav2vec2.").removeprefix("hubert."): v.float().contiguous() for k, v in raw.items()
+                if not any(x in k for x in drop)}
+    return synthetic_w2v_state(seed, **cfg)
+
+
+def config_of(sd: dict) -> tuple:
+    d = sd["feature_projection.projection.weight"].shape[0]
+    layers = len({k.split(".")[2] for k in sd if k.startswith("encoder.layers.")})
+    return d, d // 64, layers, sd["encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0]
+
+
+def pos_conv_weight(sd: dict) -> torch.Tensor:
+    """weight_norm(dim=2): w = g * v / ||v|| with the norm over (out, in) per tap -> [d, d/16, 128]"""
+    v = sd["encoder.pos_conv_embed.conv.parametrizations.weight.original1"]
+    g_ = sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"]
+    return g_ * v / v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
+
+
+def _pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def pack_w2v(sd: dict) -> list:
+    d, heads, layers, ffn = config_of(sd)
+    fl = lambda t: t.float().contiguous()
+    out = []
+    for i, k in enumerate(CONV_KERNEL):
+        w = sd[f"feature_extractor.conv_layers.{i}.conv.weight"]                      # [512, Cin, k]
+        cout, cin, _ = w.shape
+        m = torch.zeros((cout, _pad_to(k * cin, 64)))
+        m[:, :k * cin] = w.permute(0, 2, 1).reshape(cout, k * cin)                     # column = tap*Cin + c
+        b = sd.get(f"feature_extractor.conv_layers.{i}.conv.bias", torch.zeros(cout))
+        out += [split_hi_lo_tiles(m), fl(b)]
+    out += [fl(sd["feature_extractor.conv_layers.0.layer_norm.weight"]), fl(sd["feature_extractor.conv_layers.0.layer_norm.bias"]),
+            fl(sd["feature_projection.layer_norm.weight"]), fl(sd["feature_projection.layer_norm.bias"]),
+            split_hi_lo_tiles(fl(sd["feature_projection.projection.weight"])), fl(sd["feature_projection.projection.bias"])]
+    wp = pos_conv_weight(sd)
+    cg = d // POS_GROUPS
+    for g in range(POS_GROUPS):
+        wg = torch.zeros((128, POS_K * cg))
+        wg[:cg] = wp[g * cg:(g + 1) * cg].permute(0, 2, 1).reshape(cg, POS_K * cg)    # column = tap*cg + ci
+        out.append(split_hi_lo_tiles(wg))
+    out += [fl(sd["encoder.pos_conv_embed.conv.bias"]), fl(sd["encoder.layer_norm.weight"]), fl(sd["encoder.layer_norm.bias"])]
+    for i in range(layers):
+        p = f"encoder.layers.{i}."
+        a = p + "attention."
+        qkv_w = torch.cat([sd[a + "q_proj.weight"], sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]], 0)
+        qkv_b = torch.cat([sd[a + "q_proj.bias"], sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]], 0)
+        out += [split_hi_lo_tiles(qkv_w), fl(qkv_b), split_hi_lo_tiles(fl(sd[a + "out_proj.weight"])), fl(sd[a + "out_proj.bias"]),
+                fl(sd[p + "layer_norm.weight"]), fl(sd[p + "layer_norm.bias"]),
+                split_hi_lo_tiles(fl(sd[p + "feed_forward.intermediate_dense.weight"])), fl(sd[p + "feed_forward.intermediate_dense.bias"]),
+                split_hi_lo_tiles(fl(sd[p + "feed_forward.output_dense.weight"])), fl(sd[p + "feed_forward.output_dense.bias"]),
+                fl(sd[p + "final_layer_norm.weight"]), fl(sd[p + "final_layer_norm.bias"])]
+    assert len(out) == 14 + 6 + 17 + 2 + 12 * layers
+    return out

@@ -142,6 +142,16 @@ int fad_encodec_load(fad_handle* h, const void* const* tensors_host, int n_tenso
  * emb_out: fp16 [n_clips][ceil(T/320)][128] (device). */
 int fad_encodec_forward(fad_handle* h, const int16_t* pcm, long long n_clips, int T, void* emb_out_f16, void* stream);
 
+/* ---- wav2vec 2.0 / HuBERT / MERT: replaces W2V2Model, HuBERTModel, MERTModel load_model / _get_embedding
+ * (fadtk/model_loader.py:254-288, 525-596) for the "group-norm feature encoder + post-LN transformer" checkpoints
+ * (wav2vec2-base-960h, hubert-base-ls960, MERT-v1-95M): processor normalisation, Wav2Vec2Model / HubertModel
+ * forward with output_hidden_states, hidden_states[layer].
+ * cfg: {d_model, heads (= d_model / 64), layers, ffn}; tensors_host in the order of csrc/wav2vec_host.inc
+ * (39 + 12 layers), packed by fadtk_b200/weights_w2v.py. */
+int fad_w2v_load(fad_handle* h, const int* cfg, const void* const* tensors_host, int n_tensors, int max_clips, int max_len);
+/* pcm: int16 mono [n_clips][L] (device), equal lengths; emb_out: fp16 [n_clips][frames(L)][d_model]. */
+int fad_w2v_forward(fad_handle* h, const int16_t* pcm, long long n_clips, int L, int layer, void* emb_out_f16, void* stream);
+
 /* ---- statistics: replaces calc_embd_statistics (fadtk/fad.py:42-48) and
  * _process_file / calculate_embd_statistics_online (fadtk/utils.py:13-46) ----------------
  * Packed fp64 accumulator of length fad_stats_acc_len(d):

@@ -1,0 +1,80 @@
+"""wav2vec 2.0 / HuBERT / MERT embedders (fad_w2v_forward) against the reference's own dependency:
+transformers' Wav2Vec2FeatureExtractor + Wav2Vec2Model / HubertModel with output_hidden_states, driven as
+fadtk/model_loader.py:262-288, 540-560, 578-596 (oracle/w2v_oracle.py), shared seeded synthetic weights."""
+import numpy as np
+import pytest
+import torch
+
+import fadtk_b200 as fk
+from fadtk_b200 import synth, weights_w2v as ww
+from oracle import w2v_oracle as wo
+
+
+def test_packing_and_registry():
+    sd = ww.synthetic_w2v_state(0, layers=2)
+    assert ww.config_of(sd) == (768, 12, 2, 3072)
+    pk = ww.pack_w2v(sd)
+    assert len(pk) == 14 + 6 + 17 + 2 + 12 * 2
+    assert pk[0].shape == (2 * 512, 64) and pk[2].shape == (2 * 512, 1536) and pk[12].shape == (2 * 512, 1024)
+    w1 = sd["feature_extractor.conv_layers.1.conv.weight"]
+    assert torch.equal(pk[2][9, 2 * 512 + 5].float(), w1[9, 5, 2].to(torch.float16).float())       # column = tap*Cin + c
+    wp = ww.pos_conv_weight(sd)
+    assert torch.allclose(wp.pow(2).sum(dim=(0, 1)).sqrt().flatten(), sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"].flatten(), rtol=1e-5)
+    assert pk[20 + 3].shape == (2 * 128, 128 * 48)
+    assert torch.equal(pk[20 + 3][7, 11 * 48 + 2].float(), wp[3 * 48 + 7, 2, 11].to(torch.float16).float())
+    names = {m.name: m for m in fk.get_all_models()}
+    for n, sr, layer in (("w2v2-base", 16000, 12), ("w2v2-base-3", 16000, 3), ("hubert-base-7", 16000, 7),
+                         ("MERT-v1-95M", 24000, 12), ("MERT-v1-95M-1", 24000, 1)):
+        m = names[n]
+        assert isinstance(m, fk.Wav2VecFamilyModel) and m.sr == sr and m.layer == layer and m.num_features == 768
+    assert isinstance(names["w2v2-large"], fk.UnbuiltModel) and isinstance(names["hubert-large"], fk.UnbuiltModel)
+    from fadtk_b200 import _native
+    assert _native.Engine.w2v_frames(160000) == 499 and _native.Engine.w2v_frames(240000) == 749
+
+
+def test_oracle_is_the_reference_dependency():
+    sd = ww.synthetic_w2v_state(0, layers=2)
+    model, fe = wo.build(sd, "hubert")
+    e = wo.embed(synth.musiclike_clip(1, 1.0, 16000) / 32768.0, model, fe, 2)
+    assert e.shape == (49, 768) and e.dtype == np.float16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,sr,layer", [("w2v2", 16000, 12), ("hubert", 16000, 5), ("mert", 24000, 0)])
+def test_hidden_states_match_transformers(engine, family, sr, layer):
+    clips = [synth.musiclike_clip(4, 4.0, sr), synth.noise_clip(2, 4.0, sr), synth.musiclike_clip(9, 1.3, sr)]
+    name = {"w2v2": "w2v2-base", "hubert": "hubert-base", "mert": "MERT-v1-95M"}[family]
+    ml = fk.Wav2VecFamilyModel(family, name, layer, sr, max_clips=2)
+    ml.load_model()
+    got = ml.embed_pcm_batch(clips)
+    sd = ww.synthetic_w2v_state(0)
+    model, fe = wo.build(sd, "w2v2" if family == "w2v2" else "hubert", sr)
+    for g, c in zip(got, clips):
+        want = wo.embed(c / 32768.0, model, fe, layer, sr).astype(np.float32)
+        g = g.astype(np.float32)
+        assert g.shape == want.shape == (ml._engine.w2v_frames(len(c)), 768)
+        rel = np.sqrt(((g - want) ** 2).mean() / (want ** 2).mean())
+        print(f"{name} layer {layer}, {len(c)} samples: rms rel err {rel:.2e}")
+        assert rel < 5e-3, rel
+    one = ml.get_embedding(clips[2] / 32768.0)
+    assert one.dtype == np.float16 and np.array_equal(one, got[2])
+
+
+@pytest.mark.gpu
+def test_w2v_fad_parity_on_identical_audio(engine):
+    from oracle import fad_oracle as fo
+    n = 8
+    sets = {"base": [synth.noise_clip(i, 4.0, 16000) for i in range(n)],
+            "eval": [synth.musiclike_clip(i, 4.0, 16000) for i in range(n)]}
+    ml = fk.W2V2Model('base', 12, max_clips=8)
+    ml.load_model()
+    sd = ww.synthetic_w2v_state(0)
+    model, fe = wo.build(sd, "w2v2")
+    gpu = {k: np.concatenate(ml.embed_pcm_batch(v)) for k, v in sets.items()}
+    cpu = {k: np.concatenate([wo.embed(c / 32768.0, model, fe, 12) for c in v]) for k, v in sets.items()}
+    assert gpu["eval"].shape == cpu["eval"].shape == (n * 199, 768)
+    fad_gpu = fk.calc_frechet_distance(*fk.calc_embd_statistics(gpu["base"]), *fk.calc_embd_statistics(gpu["eval"]))
+    fad_cpu = fo.frechet_distance(*fo.embd_statistics(cpu["base"]), *fo.embd_statistics(cpu["eval"]))
+    rel = abs(fad_gpu - fad_cpu) / abs(fad_cpu)
+    print(f"w2v2-base FAD gpu {fad_gpu:.6f} cpu reference path {fad_cpu:.6f} rel {rel:.2e}")
+    assert rel < 1e-4, (fad_gpu, fad_cpu, rel)
