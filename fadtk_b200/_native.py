@@ -302,10 +302,10 @@ class Engine:
 
     # ------------------------------------------------------- wav2vec 2.0 / HuBERT / MERT
     def w2v_load(self, cfg: tuple, tensors: list, max_clips: int = 8, max_len: int = 16000 * 30):
-        """cfg = (d_model, heads, layers, ffn); tensors from weights_w2v.pack_w2v."""
+        """cfg = weights_w2v.config_of(state); tensors from weights_w2v.pack_w2v."""
         keep = [t.contiguous() for t in tensors]
         arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
-        c = (C.c_int * 4)(*[int(v) for v in cfg])
+        c = (C.c_int * 6)(*[int(v) for v in cfg])
         _check(lib().fad_w2v_load(self._h, c, arr, len(keep), int(max_clips), int(max_len)))
         self._w2v_d = int(cfg[0])
 

@@ -269,7 +269,8 @@ template <int CHUNKS, int L>
 __global__ void __launch_bounds__(256)
 clap_ln_kernel(const float* x, const float* __restrict__ gamma, const float* __restrict__ beta,
                long long n_rows, int C, int ld_out, int res, int shift, int mode, __half* __restrict__ out,
-               float* out32 = nullptr /* optional fp32 copy of the normalised row (row order o, stride width); may alias x */)
+               float* out32 = nullptr /* optional fp32 copy of the normalised row (row order o, stride width); may alias x */,
+               int gelu = 0 /* exact-erf GELU after the affine (wav2vec2 "layer" feature encoder) */)
 {
     constexpr int R = 32 / L;                                      // rows per warp
     constexpr int width = 4 * L * CHUNKS;
@@ -323,16 +324,20 @@ clap_ln_kernel(const float* x, const float* __restrict__ gamma, const float* __r
         const int i = 4 * (li + L * j);
         const float4 g4 = *reinterpret_cast<const float4*>(gamma + i);
         const float4 b4 = *reinterpret_cast<const float4*>(beta + i);
-        const __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd * g4.x + b4.x, (v[j].y - mean) * rstd * g4.y + b4.y);
-        const __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd * g4.z + b4.z, (v[j].w - mean) * rstd * g4.w + b4.w);
+        float y0 = (v[j].x - mean) * rstd * g4.x + b4.x, y1 = (v[j].y - mean) * rstd * g4.y + b4.y;
+        float y2 = (v[j].z - mean) * rstd * g4.z + b4.z, y3 = (v[j].w - mean) * rstd * g4.w + b4.w;
+        if (gelu) {
+            y0 = 0.5f * y0 * (1.0f + erff(y0 * 0.70710678118654752f)); y1 = 0.5f * y1 * (1.0f + erff(y1 * 0.70710678118654752f));
+            y2 = 0.5f * y2 * (1.0f + erff(y2 * 0.70710678118654752f)); y3 = 0.5f * y3 * (1.0f + erff(y3 * 0.70710678118654752f));
+        }
+        const __half2 h0 = __floats2half2_rn(y0, y1);
+        const __half2 h1 = __floats2half2_rn(y2, y3);
         uint2 pk;
         pk.x = *reinterpret_cast<const uint32_t*>(&h0);
         pk.y = *reinterpret_cast<const uint32_t*>(&h1);
         *reinterpret_cast<uint2*>(dst + i) = pk;
         if (out32 != nullptr)                                      // post-LN transformers: the normalised row IS the new stream
-            *reinterpret_cast<float4*>(out32 + o * width + i) =
-                make_float4((v[j].x - mean) * rstd * g4.x + b4.x, (v[j].y - mean) * rstd * g4.y + b4.y,
-                            (v[j].z - mean) * rstd * g4.z + b4.z, (v[j].w - mean) * rstd * g4.w + b4.w);
+            *reinterpret_cast<float4*>(out32 + o * width + i) = make_float4(y0, y1, y2, y3);
     }
     for (int i = width + li; i < ld_out; i += L) dst[i] = __float2half_rn(0.f);
 }

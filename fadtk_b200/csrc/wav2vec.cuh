@@ -93,4 +93,10 @@ w2v_add_cols_kernel(const float* __restrict__ h, const float* __restrict__ y, lo
     }
 }
 
+__global__ void __launch_bounds__(256)
+f32_to_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ out)
+{
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = __float2half_rn(x[i]);
+}
+
 }  // namespace fad

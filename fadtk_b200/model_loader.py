@@ -331,8 +331,11 @@ class Wav2VecFamilyModel(ModelLoader):
     """
 
     def __init__(self, family: str, name: str, layer: int, sr: int, checkpoint=None, seed: int = 0, limit_minutes: int = 6,
-                 max_clips: int = 8):
-        super().__init__(name, 768, sr)
+                 max_clips: int = 8, size: str = 'base'):
+        from .weights_w2v import ARCH
+        self.size = size
+        self.arch = dict(ARCH[(family, size)])
+        super().__init__(name, self.arch["d"], sr)
         self.family = family
         self.layer = layer
         self.limit = limit_minutes * 60 * sr
@@ -352,7 +355,7 @@ class Wav2VecFamilyModel(ModelLoader):
         from . import _native, weights_w2v
         self._engine = _native.engine()
         env = {"w2v2": "FADTK_W2V2_CKPT", "hubert": "FADTK_HUBERT_CKPT", "mert": "FADTK_MERT_CKPT"}[self.family]
-        state = weights_w2v.load_w2v_state(self.checkpoint, self.seed, env=env)
+        state = weights_w2v.load_w2v_state(self.checkpoint, self.seed, env=env, **self.arch)
         self._packed = (weights_w2v.config_of(state), weights_w2v.pack_w2v(state))
         self._max_len = self.sr * 30                           # workspace: max_clips pieces of up to 30 s
         self._engine.w2v_load(*self._packed, self.max_clips, max_len=self._max_len)
@@ -390,19 +393,22 @@ class Wav2VecFamilyModel(ModelLoader):
         return list(eng.w2v_forward(pcm, self.layer))
 
 
+def _layer_name(prefix: str, size: str, layer: int) -> str:
+    default = 12 if size in ('base', 'v1-95M') else 24
+    return prefix + ("" if layer == default else f"-{layer}")
+
+
 def W2V2Model(size: str, layer: int, **kw):
-    assert size == 'base', "w2v2-large has no sm_100a forward pass yet"
-    return Wav2VecFamilyModel("w2v2", "w2v2-base" + ("" if layer == 12 else f"-{layer}"), layer, 16000, **kw)
+    return Wav2VecFamilyModel("w2v2", _layer_name(f"w2v2-{size}", size, layer), layer, 16000, size=size, **kw)
 
 
 def HuBERTModel(size: str, layer: int, **kw):
-    assert size == 'base', "hubert-large (stable layer norm) has no sm_100a forward pass yet"
-    return Wav2VecFamilyModel("hubert", "hubert-base" + ("" if layer == 12 else f"-{layer}"), layer, 16000, **kw)
+    return Wav2VecFamilyModel("hubert", _layer_name(f"hubert-{size}", size, layer), layer, 16000, size=size, **kw)
 
 
 def MERTModel(size: str = 'v1-95M', layer: int = 12, **kw):
     assert size == 'v1-95M', "only MERT-v1-95M is built"
-    return Wav2VecFamilyModel("mert", "MERT-v1-95M" + ("" if layer == 12 else f"-{layer}"), layer, 24000, **kw)
+    return Wav2VecFamilyModel("mert", _layer_name("MERT-v1-95M", size, layer), layer, 24000, size=size, **kw)
 
 
 class UnbuiltModel(ModelLoader):
@@ -433,8 +439,8 @@ def get_all_models() -> list[ModelLoader]:
         VGGishModel(),
         *[MERTModel('v1-95M', v) for v in range(1, 13)],
         EncodecEmbModel('24k'), EncodecEmbModel('48k'),
-        *[W2V2Model('base', v) for v in range(1, 13)], *_layered("w2v2-large", 1024, 24, 24),
-        *[HuBERTModel('base', v) for v in range(1, 13)], *_layered("hubert-large", 1024, 24, 24),
+        *[W2V2Model('base', v) for v in range(1, 13)], *[W2V2Model('large', v) for v in range(1, 25)],
+        *[HuBERTModel('base', v) for v in range(1, 13)], *[HuBERTModel('large', v) for v in range(1, 25)],
         *_layered("wavlm-base", 768, 12, 12), *_layered("wavlm-base-plus", 768, 12, 12),
         *_layered("wavlm-large", 1024, 24, 24),
         WhisperModel('tiny'), WhisperModel('small'), WhisperModel('base'), WhisperModel('medium'), WhisperModel('large'),

@@ -14,10 +14,17 @@ from .weights import split_hi_lo_tiles
 
 CONV_KERNEL, CONV_STRIDE, CONV_DIM = (10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2), 512
 POS_K, POS_GROUPS = 128, 16
-BASE = dict(d=768, layers=12, ffn=3072)
+# registry family/size -> architecture (transformers configs of the checkpoints the reference names)
+ARCH = {
+    ("w2v2", "base"): dict(d=768, layers=12, ffn=3072, variant="group"),      # facebook/wav2vec2-base-960h
+    ("w2v2", "large"): dict(d=1024, layers=24, ffn=4096, variant="group"),    # facebook/wav2vec2-large-960h
+    ("hubert", "base"): dict(d=768, layers=12, ffn=3072, variant="group"),    # facebook/hubert-base-ls960
+    ("hubert", "large"): dict(d=1024, layers=24, ffn=4096, variant="layer"),  # facebook/hubert-large-ls960: layer-norm convs, stable LN
+    ("mert", "v1-95M"): dict(d=768, layers=12, ffn=3072, variant="group"),    # m-a-p/MERT-v1-95M (24 kHz)
+}
 
 
-def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int = 3072) -> dict:
+def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int = 3072, variant: str = "group") -> dict:
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -33,7 +40,11 @@ def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int 
     for i, k in enumerate(CONV_KERNEL):
         sd[f"feature_extractor.conv_layers.{i}.conv.weight"] = torch.randn((CONV_DIM, cin, k), generator=g) * math.sqrt(2.0 / (cin * k))
         cin = CONV_DIM
-    ln("feature_extractor.conv_layers.0.layer_norm", CONV_DIM)
+        if variant == "layer":                                 # conv bias + LayerNorm after every conv
+            sd[f"feature_extractor.conv_layers.{i}.conv.bias"] = 0.02 * torch.randn((CONV_DIM,), generator=g)
+            ln(f"feature_extractor.conv_layers.{i}.layer_norm", CONV_DIM)
+    if variant == "group":
+        ln("feature_extractor.conv_layers.0.layer_norm", CONV_DIM)
     ln("feature_projection.layer_norm", CONV_DIM)
     lin("feature_projection.projection", d, CONV_DIM)
     cg = d // POS_GROUPS
@@ -63,10 +74,17 @@ def load_w2v_state(path=None, seed: int = 0, env: str = "FADTK_W2V_CKPT", **cfg)
     return synthetic_w2v_state(seed, **cfg)
 
 
+def variant_of(sd: dict) -> str:
+    """"layer": LayerNorm after every feature-encoder conv (those checkpoints also use the stable-LN transformer)."""
+    return "layer" if "feature_extractor.conv_layers.1.layer_norm.weight" in sd else "group"
+
+
 def config_of(sd: dict) -> tuple:
+    """(d_model, heads, layers, ffn, layer-norm convs, stable layer norm)"""
     d = sd["feature_projection.projection.weight"].shape[0]
     layers = len({k.split(".")[2] for k in sd if k.startswith("encoder.layers.")})
-    return d, d // 64, layers, sd["encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0]
+    lay = int(variant_of(sd) == "layer")
+    return d, d // 64, layers, sd["encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0], lay, lay
 
 
 def pos_conv_weight(sd: dict) -> torch.Tensor:
@@ -81,7 +99,7 @@ def _pad_to(v, m):
 
 
 def pack_w2v(sd: dict) -> list:
-    d, heads, layers, ffn = config_of(sd)
+    d, heads, layers, ffn = config_of(sd)[:4]
     fl = lambda t: t.float().contiguous()
     out = []
     for i, k in enumerate(CONV_KERNEL):
@@ -90,9 +108,10 @@ def pack_w2v(sd: dict) -> list:
         m = torch.zeros((cout, _pad_to(k * cin, 64)))
         m[:, :k * cin] = w.permute(0, 2, 1).reshape(cout, k * cin)                     # column = tap*Cin + c
         b = sd.get(f"feature_extractor.conv_layers.{i}.conv.bias", torch.zeros(cout))
-        out += [split_hi_lo_tiles(m), fl(b)]
-    out += [fl(sd["feature_extractor.conv_layers.0.layer_norm.weight"]), fl(sd["feature_extractor.conv_layers.0.layer_norm.bias"]),
-            fl(sd["feature_projection.layer_norm.weight"]), fl(sd["feature_projection.layer_norm.bias"]),
+        ng = sd.get(f"feature_extractor.conv_layers.{i}.layer_norm.weight", torch.ones(cout))
+        nb = sd.get(f"feature_extractor.conv_layers.{i}.layer_norm.bias", torch.zeros(cout))
+        out += [split_hi_lo_tiles(m), fl(b), fl(ng), fl(nb)]
+    out += [fl(sd["feature_projection.layer_norm.weight"]), fl(sd["feature_projection.layer_norm.bias"]),
             split_hi_lo_tiles(fl(sd["feature_projection.projection.weight"])), fl(sd["feature_projection.projection.bias"])]
     wp = pos_conv_weight(sd)
     cg = d // POS_GROUPS
@@ -111,5 +130,5 @@ def pack_w2v(sd: dict) -> list:
                 split_hi_lo_tiles(fl(sd[p + "feed_forward.intermediate_dense.weight"])), fl(sd[p + "feed_forward.intermediate_dense.bias"]),
                 split_hi_lo_tiles(fl(sd[p + "feed_forward.output_dense.weight"])), fl(sd[p + "feed_forward.output_dense.bias"]),
                 fl(sd[p + "final_layer_norm.weight"]), fl(sd[p + "final_layer_norm.bias"])]
-    assert len(out) == 14 + 6 + 17 + 2 + 12 * layers
+    assert len(out) == 28 + 4 + 17 + 2 + 12 * layers
     return out

@@ -12,22 +12,25 @@ from oracle import w2v_oracle as wo
 
 def test_packing_and_registry():
     sd = ww.synthetic_w2v_state(0, layers=2)
-    assert ww.config_of(sd) == (768, 12, 2, 3072)
+    assert ww.config_of(sd) == (768, 12, 2, 3072, 0, 0)
     pk = ww.pack_w2v(sd)
-    assert len(pk) == 14 + 6 + 17 + 2 + 12 * 2
-    assert pk[0].shape == (2 * 512, 64) and pk[2].shape == (2 * 512, 1536) and pk[12].shape == (2 * 512, 1024)
+    assert len(pk) == 28 + 4 + 17 + 2 + 12 * 2
+    assert pk[0].shape == (2 * 512, 64) and pk[4].shape == (2 * 512, 1536) and pk[24].shape == (2 * 512, 1024)
     w1 = sd["feature_extractor.conv_layers.1.conv.weight"]
-    assert torch.equal(pk[2][9, 2 * 512 + 5].float(), w1[9, 5, 2].to(torch.float16).float())       # column = tap*Cin + c
+    assert torch.equal(pk[4][9, 2 * 512 + 5].float(), w1[9, 5, 2].to(torch.float16).float())       # column = tap*Cin + c
     wp = ww.pos_conv_weight(sd)
     assert torch.allclose(wp.pow(2).sum(dim=(0, 1)).sqrt().flatten(), sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"].flatten(), rtol=1e-5)
-    assert pk[20 + 3].shape == (2 * 128, 128 * 48)
-    assert torch.equal(pk[20 + 3][7, 11 * 48 + 2].float(), wp[3 * 48 + 7, 2, 11].to(torch.float16).float())
+    assert pk[32 + 3].shape == (2 * 128, 128 * 48)
+    assert torch.equal(pk[32 + 3][7, 11 * 48 + 2].float(), wp[3 * 48 + 7, 2, 11].to(torch.float16).float())
     names = {m.name: m for m in fk.get_all_models()}
     for n, sr, layer in (("w2v2-base", 16000, 12), ("w2v2-base-3", 16000, 3), ("hubert-base-7", 16000, 7),
                          ("MERT-v1-95M", 24000, 12), ("MERT-v1-95M-1", 24000, 1)):
         m = names[n]
         assert isinstance(m, fk.Wav2VecFamilyModel) and m.sr == sr and m.layer == layer and m.num_features == 768
-    assert isinstance(names["w2v2-large"], fk.UnbuiltModel) and isinstance(names["hubert-large"], fk.UnbuiltModel)
+    assert names["w2v2-large"].num_features == 1024 and names["w2v2-large"].layer == 24 and names["hubert-large-3"].layer == 3
+    lay = ww.synthetic_w2v_state(0, d=1024, layers=1, ffn=4096, variant="layer")
+    assert ww.config_of(lay) == (1024, 16, 1, 4096, 1, 1) and len(ww.pack_w2v(lay)) == 28 + 4 + 17 + 2 + 12
+    assert isinstance(names["wavlm-base"], fk.UnbuiltModel)
     from fadtk_b200 import _native
     assert _native.Engine.w2v_frames(160000) == 499 and _native.Engine.w2v_frames(240000) == 749
 
@@ -44,7 +47,7 @@ def test_oracle_is_the_reference_dependency():
 def test_hidden_states_match_transformers(engine, family, sr, layer):
     clips = [synth.musiclike_clip(4, 4.0, sr), synth.noise_clip(2, 4.0, sr), synth.musiclike_clip(9, 1.3, sr)]
     name = {"w2v2": "w2v2-base", "hubert": "hubert-base", "mert": "MERT-v1-95M"}[family]
-    ml = fk.Wav2VecFamilyModel(family, name, layer, sr, max_clips=2)
+    ml = fk.Wav2VecFamilyModel(family, name, layer, sr, max_clips=2, size='v1-95M' if family == 'mert' else 'base')
     ml.load_model()
     got = ml.embed_pcm_batch(clips)
     sd = ww.synthetic_w2v_state(0)
@@ -58,6 +61,27 @@ def test_hidden_states_match_transformers(engine, family, sr, layer):
         assert rel < 5e-3, rel
     one = ml.get_embedding(clips[2] / 32768.0)
     assert one.dtype == np.float16 and np.array_equal(one, got[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family,size,layer", [("hubert", "large", 24), ("hubert", "large", 2), ("w2v2", "large", 3)])
+def test_large_variants_match_transformers(engine, family, size, layer):
+    """hubert-large: layer-norm feature encoder + stable-LN (pre-LN) transformer, hidden_states[k < 24] = raw stream;
+    w2v2-large: the base architecture at d = 1024.  Synthetic checkpoints with fewer layers keep the CPU oracle quick."""
+    arch = dict(ww.ARCH[(family, size)])
+    arch["layers"] = layer + 1 if layer < 24 else 3             # shortened synthetic stack; layer < 24 taps an inner (raw-stream) state
+    sd = ww.synthetic_w2v_state(0, **arch)
+    tap = layer if layer < 24 else arch["layers"]                # last layer of the shortened stack
+    eng = engine
+    eng.w2v_load(ww.config_of(sd), ww.pack_w2v(sd), 2, max_len=16000 * 5)
+    clips = [synth.musiclike_clip(4, 3.0, 16000), synth.noise_clip(2, 3.0, 16000)]
+    got = eng.w2v_forward(torch.from_numpy(np.stack(clips)).to(eng.torch_device), tap).cpu().numpy().astype(np.float32)
+    model, fe = wo.build(sd, "w2v2" if family == "w2v2" else "hubert")
+    for g, c in zip(got, clips):
+        want = wo.embed(c / 32768.0, model, fe, tap).astype(np.float32)
+        rel = np.sqrt(((g - want) ** 2).mean() / (want ** 2).mean())
+        print(f"{family}-{size} hidden_states[{tap}] of {arch['layers']} layers: rms rel err {rel:.2e}")
+        assert g.shape == want.shape and rel < 5e-3, rel
 
 
 @pytest.mark.gpu
