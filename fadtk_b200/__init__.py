@@ -7,7 +7,7 @@ call loads csrc/libfadtk_b200.so and fails loudly if it or a B200 is missing.
 from .fad import *            # noqa: F401,F403
 from .fad import FADInfResults, FrechetAudioDistance, calc_embd_statistics, calc_frechet_distance, log  # noqa: F401
 from .fad_batch import cache_embedding_files  # noqa: F401
-from .model_loader import ModelLoader, VGGishModel, CLAPLaionModel, WhisperModel, EncodecEmbModel, Wav2VecFamilyModel, W2V2Model, HuBERTModel, MERTModel, UnbuiltModel, get_all_models  # noqa: F401
+from .model_loader import ModelLoader, VGGishModel, CLAPLaionModel, WhisperModel, EncodecEmbModel, Wav2VecFamilyModel, W2V2Model, HuBERTModel, MERTModel, WavLMModel, UnbuiltModel, get_all_models  # noqa: F401
 from .utils import (PathLike, DeviceStatistics, calculate_embd_statistics_online,  # noqa: F401
                     find_sox_formats, get_cache_embedding_path, statistics_of_arrays)
 

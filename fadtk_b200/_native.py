@@ -305,7 +305,7 @@ class Engine:
         """cfg = weights_w2v.config_of(state); tensors from weights_w2v.pack_w2v."""
         keep = [t.contiguous() for t in tensors]
         arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
-        c = (C.c_int * 6)(*[int(v) for v in cfg])
+        c = (C.c_int * 7)(*[int(v) for v in cfg])
         _check(lib().fad_w2v_load(self._h, c, arr, len(keep), int(max_clips), int(max_len)))
         self._w2v_d = int(cfg[0])
 

@@ -93,6 +93,34 @@ w2v_add_cols_kernel(const float* __restrict__ h, const float* __restrict__ y, lo
     }
 }
 
+// WavLM gated relative position bias (modeling_wavlm.WavLMAttention.forward steps 1-3): per (row, head)
+//   p = W_g x_head + b_g (8 values);  a = sigmoid(p0+p1+p2+p3), b = sigmoid(p4+..+p7);  gate = a (b const_h - 1) + 2
+// x: fp32 [rows][d] (the attention input), gate: [rows][heads].  One thread per (row, head).
+__global__ void __launch_bounds__(256)
+wavlm_gate_kernel(const float* __restrict__ x, const float* __restrict__ w /*[8][64]*/, const float* __restrict__ b /*[8]*/,
+                  const float* __restrict__ cst /*[heads]*/, long long n_rows, int heads, int d, float* __restrict__ gate)
+{
+    __shared__ float ws[8 * 64 + 8];
+    for (int i = threadIdx.x; i < 8 * 64 + 8; i += 256) ws[i] = i < 512 ? w[i] : b[i - 512];
+    __syncthreads();
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n_rows * heads; e += (long long)gridDim.x * 256) {
+        const long long row = e / heads;
+        const int hh = (int)(e - row * heads);
+        const float* xr = x + row * d + hh * 64;
+        float p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[j] = ws[512 + j];
+        for (int k = 0; k < 64; ++k) {
+            const float xv = xr[k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[j] = fmaf(ws[j * 64 + k], xv, p[j]);
+        }
+        const float a = 1.0f / (1.0f + expf(-(p[0] + p[1] + p[2] + p[3])));
+        const float bb = 1.0f / (1.0f + expf(-(p[4] + p[5] + p[6] + p[7])));
+        gate[e] = a * (bb * cst[hh] - 1.0f) + 2.0f;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 f32_to_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ out)
 {

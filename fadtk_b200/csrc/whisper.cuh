@@ -148,7 +148,9 @@ whisper_pos_fill_kernel(const float* __restrict__ pos /*[rows_per_clip][d]*/, lo
 // (scores scaled by 1/8 = head_dim^-0.5 as WhisperAttention does).
 constexpr int kFaStride = 72;           // halves per smem row (64 used): conflict-free fragment loads / ldmatrix
 __global__ void __launch_bounds__(128)
-whisper_flash_attention_kernel(const __half* __restrict__ qkv, int S, int d, __half* __restrict__ out)
+whisper_flash_attention_kernel(const __half* __restrict__ qkv, int S, int d, __half* __restrict__ out,
+                               const float* __restrict__ relb = nullptr /* WavLM: [heads][2S-1] bias by key - query + S - 1 */,
+                               const float* __restrict__ gate = nullptr /* WavLM: [clips*S][heads] per-query gate of that bias */)
 {
     __shared__ __align__(16) __half q_s[64 * kFaStride];
     __shared__ __align__(16) __half kv_s[2][2][64 * kFaStride];     // [stage][k | v]
@@ -209,16 +211,31 @@ whisper_flash_attention_kernel(const __half* __restrict__ qkv, int S, int d, __h
                 mma_m16n8k16(s[j], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3],
                              *reinterpret_cast<const uint32_t*>(kr + ks * 16), *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
         }
-        // scale, mask keys past S, running max
+        // scale (+ gated relative position bias), mask keys past S, running max
         const int key0 = tile * 64;
         float mx0 = m0, mx1 = m1;
+        const int qr0 = qb * 64 + warp * 16 + g, qr1 = qr0 + 8;
+        float g0 = 0.f, g1 = 0.f;
+        const float* rb = nullptr;
+        if (relb != nullptr) {
+            rb = relb + (size_t)h * (2 * S - 1) + (S - 1);
+            const int heads = gridDim.y;
+            g0 = gate[(row0 + min(qr0, S - 1)) * heads + h];
+            g1 = gate[(row0 + min(qr1, S - 1)) * heads + h];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int kc = key0 + j * 8 + 2 * t;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const bool valid = kc + (e & 1) < S;
-                s[j][e] = valid ? s[j][e] * sc : -3.0e38f;
+                const int key = kc + (e & 1);
+                const bool valid = key < S;
+                float v = s[j][e] * sc;
+                if (rb != nullptr && valid) {
+                    const int q_ = (e < 2) ? qr0 : qr1;
+                    v = fmaf((e < 2 ? g0 : g1) * rb[key - min(q_, S - 1)], 1.4426950408889634f, v);
+                }
+                s[j][e] = valid ? v : -3.0e38f;
             }
             mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
             mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));

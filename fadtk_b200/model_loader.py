@@ -354,7 +354,7 @@ class Wav2VecFamilyModel(ModelLoader):
     def load_model(self):
         from . import _native, weights_w2v
         self._engine = _native.engine()
-        env = {"w2v2": "FADTK_W2V2_CKPT", "hubert": "FADTK_HUBERT_CKPT", "mert": "FADTK_MERT_CKPT"}[self.family]
+        env = {"w2v2": "FADTK_W2V2_CKPT", "hubert": "FADTK_HUBERT_CKPT", "mert": "FADTK_MERT_CKPT", "wavlm": "FADTK_WAVLM_CKPT"}[self.family]
         state = weights_w2v.load_w2v_state(self.checkpoint, self.seed, env=env, **self.arch)
         self._packed = (weights_w2v.config_of(state), weights_w2v.pack_w2v(state))
         self._max_len = self.sr * 30                           # workspace: max_clips pieces of up to 30 s
@@ -406,6 +406,10 @@ def HuBERTModel(size: str, layer: int, **kw):
     return Wav2VecFamilyModel("hubert", _layer_name(f"hubert-{size}", size, layer), layer, 16000, size=size, **kw)
 
 
+def WavLMModel(size: str, layer: int, **kw):
+    return Wav2VecFamilyModel("wavlm", _layer_name(f"wavlm-{size}", 'base' if size != 'large' else size, layer), layer, 16000, size=size, **kw)
+
+
 def MERTModel(size: str = 'v1-95M', layer: int = 12, **kw):
     assert size == 'v1-95M', "only MERT-v1-95M is built"
     return Wav2VecFamilyModel("mert", _layer_name("MERT-v1-95M", size, layer), layer, 24000, size=size, **kw)
@@ -441,8 +445,8 @@ def get_all_models() -> list[ModelLoader]:
         EncodecEmbModel('24k'), EncodecEmbModel('48k'),
         *[W2V2Model('base', v) for v in range(1, 13)], *[W2V2Model('large', v) for v in range(1, 25)],
         *[HuBERTModel('base', v) for v in range(1, 13)], *[HuBERTModel('large', v) for v in range(1, 25)],
-        *_layered("wavlm-base", 768, 12, 12), *_layered("wavlm-base-plus", 768, 12, 12),
-        *_layered("wavlm-large", 1024, 24, 24),
+        *[WavLMModel('base', v) for v in range(1, 13)], *[WavLMModel('base-plus', v) for v in range(1, 13)],
+        *[WavLMModel('large', v) for v in range(1, 25)],
         WhisperModel('tiny'), WhisperModel('small'), WhisperModel('base'), WhisperModel('medium'), WhisperModel('large'),
     ]
     return ms

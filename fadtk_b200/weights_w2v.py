@@ -21,10 +21,16 @@ ARCH = {
     ("hubert", "base"): dict(d=768, layers=12, ffn=3072, variant="group"),    # facebook/hubert-base-ls960
     ("hubert", "large"): dict(d=1024, layers=24, ffn=4096, variant="layer"),  # facebook/hubert-large-ls960: layer-norm convs, stable LN
     ("mert", "v1-95M"): dict(d=768, layers=12, ffn=3072, variant="group"),    # m-a-p/MERT-v1-95M (24 kHz)
+    # patrickvonplaten/wavlm-libri-clean-100h-{base,base-plus,large}: WavLM adds a gated relative position bias
+    ("wavlm", "base"): dict(d=768, layers=12, ffn=3072, variant="group", wavlm=True),
+    ("wavlm", "base-plus"): dict(d=768, layers=12, ffn=3072, variant="group", wavlm=True),
+    ("wavlm", "large"): dict(d=1024, layers=24, ffn=4096, variant="layer", wavlm=True),
 }
+WAVLM_BUCKETS = 320
 
 
-def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int = 3072, variant: str = "group") -> dict:
+def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int = 3072, variant: str = "group",
+                        wavlm: bool = False) -> dict:
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -56,6 +62,13 @@ def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int 
         p = f"encoder.layers.{i}."
         for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
             lin(p + "attention." + n, d, d)
+        if wavlm:
+            heads = d // 64
+            sd[p + "attention.gru_rel_pos_linear.weight"] = torch.randn((8, 64), generator=g) * 0.125
+            sd[p + "attention.gru_rel_pos_linear.bias"] = 0.1 * torch.randn((8,), generator=g)
+            sd[p + "attention.gru_rel_pos_const"] = 1.0 + 0.2 * torch.randn((1, heads, 1, 1), generator=g)
+            if i == 0:
+                sd[p + "attention.rel_attn_embed.weight"] = 0.5 * torch.randn((WAVLM_BUCKETS, heads), generator=g)
         ln(p + "layer_norm", d)
         lin(p + "feed_forward.intermediate_dense", ffn, d)
         lin(p + "feed_forward.output_dense", d, ffn)
@@ -69,7 +82,7 @@ def load_w2v_state(path=None, seed: int = 0, env: str = "FADTK_W2V_CKPT", **cfg)
         raw = torch.load(path, map_location="cpu")
         raw = raw.get("state_dict", raw)
         drop = ("masked_spec_embed", "lm_head", "quantizer", "project_", "label_embs")
-        return {k.removeprefix("wav2vec2.").removeprefix("hubert."): v.float().contiguous() for k, v in raw.items()
+        return {k.removeprefix("wav2vec2.").removeprefix("hubert.").removeprefix("wavlm."): v.float().contiguous() for k, v in raw.items()
                 if not any(x in k for x in drop)}
     return synthetic_w2v_state(seed, **cfg)
 
@@ -80,11 +93,12 @@ def variant_of(sd: dict) -> str:
 
 
 def config_of(sd: dict) -> tuple:
-    """(d_model, heads, layers, ffn, layer-norm convs, stable layer norm)"""
+    """(d_model, heads, layers, ffn, layer-norm convs, stable layer norm, WavLM)"""
     d = sd["feature_projection.projection.weight"].shape[0]
     layers = len({k.split(".")[2] for k in sd if k.startswith("encoder.layers.")})
     lay = int(variant_of(sd) == "layer")
-    return d, d // 64, layers, sd["encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0], lay, lay
+    wavlm = int("encoder.layers.0.attention.rel_attn_embed.weight" in sd)
+    return d, d // 64, layers, sd["encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0], lay, lay, wavlm
 
 
 def pos_conv_weight(sd: dict) -> torch.Tensor:
@@ -120,6 +134,9 @@ def pack_w2v(sd: dict) -> list:
         wg[:cg] = wp[g * cg:(g + 1) * cg].permute(0, 2, 1).reshape(cg, POS_K * cg)    # column = tap*cg + ci
         out.append(split_hi_lo_tiles(wg))
     out += [fl(sd["encoder.pos_conv_embed.conv.bias"]), fl(sd["encoder.layer_norm.weight"]), fl(sd["encoder.layer_norm.bias"])]
+    wavlm = config_of(sd)[6]
+    if wavlm:
+        out.append(fl(sd["encoder.layers.0.attention.rel_attn_embed.weight"]))               # [320, heads]
     for i in range(layers):
         p = f"encoder.layers.{i}."
         a = p + "attention."
@@ -130,5 +147,7 @@ def pack_w2v(sd: dict) -> list:
                 split_hi_lo_tiles(fl(sd[p + "feed_forward.intermediate_dense.weight"])), fl(sd[p + "feed_forward.intermediate_dense.bias"]),
                 split_hi_lo_tiles(fl(sd[p + "feed_forward.output_dense.weight"])), fl(sd[p + "feed_forward.output_dense.bias"]),
                 fl(sd[p + "final_layer_norm.weight"]), fl(sd[p + "final_layer_norm.bias"])]
-    assert len(out) == 28 + 4 + 17 + 2 + 12 * layers
+        if wavlm:
+            out += [fl(sd[a + "gru_rel_pos_linear.weight"]), fl(sd[a + "gru_rel_pos_linear.bias"]), fl(sd[a + "gru_rel_pos_const"].flatten())]
+    assert len(out) == 28 + 4 + 17 + 2 + (1 + 15 * layers if wavlm else 12 * layers)
     return out

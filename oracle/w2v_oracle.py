@@ -24,7 +24,10 @@ def build(sd: dict, family: str = "w2v2", sr: int = 16000):
               mask_time_prob=0.0, mask_feature_prob=0.0, apply_spec_augment=False)
     if "feature_extractor.conv_layers.1.layer_norm.weight" in sd:      # hubert-large-ls960 style
         kw.update(feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True)
-    model = (tr.Wav2Vec2Model(tr.Wav2Vec2Config(**kw)) if family == "w2v2" else tr.HubertModel(tr.HubertConfig(**kw))).eval()
+    if family == "wavlm":
+        model = tr.WavLMModel(tr.WavLMConfig(**kw)).eval()
+    else:
+        model = (tr.Wav2Vec2Model(tr.Wav2Vec2Config(**kw)) if family == "w2v2" else tr.HubertModel(tr.HubertConfig(**kw))).eval()
     missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected and set(missing) <= {"masked_spec_embed"}, (missing, unexpected)
     return model, tr.Wav2Vec2FeatureExtractor(sampling_rate=sr, do_normalize=True, return_attention_mask=False)

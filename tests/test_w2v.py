@@ -12,7 +12,7 @@ from oracle import w2v_oracle as wo
 
 def test_packing_and_registry():
     sd = ww.synthetic_w2v_state(0, layers=2)
-    assert ww.config_of(sd) == (768, 12, 2, 3072, 0, 0)
+    assert ww.config_of(sd) == (768, 12, 2, 3072, 0, 0, 0)
     pk = ww.pack_w2v(sd)
     assert len(pk) == 28 + 4 + 17 + 2 + 12 * 2
     assert pk[0].shape == (2 * 512, 64) and pk[4].shape == (2 * 512, 1536) and pk[24].shape == (2 * 512, 1024)
@@ -29,8 +29,11 @@ def test_packing_and_registry():
         assert isinstance(m, fk.Wav2VecFamilyModel) and m.sr == sr and m.layer == layer and m.num_features == 768
     assert names["w2v2-large"].num_features == 1024 and names["w2v2-large"].layer == 24 and names["hubert-large-3"].layer == 3
     lay = ww.synthetic_w2v_state(0, d=1024, layers=1, ffn=4096, variant="layer")
-    assert ww.config_of(lay) == (1024, 16, 1, 4096, 1, 1) and len(ww.pack_w2v(lay)) == 28 + 4 + 17 + 2 + 12
-    assert isinstance(names["wavlm-base"], fk.UnbuiltModel)
+    assert ww.config_of(lay) == (1024, 16, 1, 4096, 1, 1, 0) and len(ww.pack_w2v(lay)) == 28 + 4 + 17 + 2 + 12
+    wl = ww.synthetic_w2v_state(0, layers=2, wavlm=True)
+    assert ww.config_of(wl)[6] == 1 and len(ww.pack_w2v(wl)) == 28 + 4 + 17 + 2 + 1 + 15 * 2
+    assert names["wavlm-base-plus-4"].layer == 4 and names["wavlm-large"].num_features == 1024 and names["wavlm-large"].layer == 24
+    assert isinstance(names["clap-2023"], fk.UnbuiltModel)
     from fadtk_b200 import _native
     assert _native.Engine.w2v_frames(160000) == 499 and _native.Engine.w2v_frames(240000) == 749
 
@@ -81,6 +84,24 @@ def test_large_variants_match_transformers(engine, family, size, layer):
         want = wo.embed(c / 32768.0, model, fe, tap).astype(np.float32)
         rel = np.sqrt(((g - want) ** 2).mean() / (want ** 2).mean())
         print(f"{family}-{size} hidden_states[{tap}] of {arch['layers']} layers: rms rel err {rel:.2e}")
+        assert g.shape == want.shape and rel < 5e-3, rel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,layer", [("base", 3), ("large", 2)])
+def test_wavlm_matches_transformers(engine, size, layer):
+    """WavLM: the wav2vec2 skeleton + gated relative position bias (bucketed rel_attn_embed of layer 0, per-query gate)."""
+    arch = dict(ww.ARCH[("wavlm", size)])
+    arch["layers"] = layer + (1 if size == "large" else 0)
+    sd = ww.synthetic_w2v_state(0, **arch)
+    engine.w2v_load(ww.config_of(sd), ww.pack_w2v(sd), 2, max_len=16000 * 5)
+    clips = [synth.musiclike_clip(4, 3.0, 16000), synth.noise_clip(2, 3.0, 16000)]
+    got = engine.w2v_forward(torch.from_numpy(np.stack(clips)).to(engine.torch_device), layer).cpu().numpy().astype(np.float32)
+    model, fe = wo.build(sd, "wavlm")
+    for g, c in zip(got, clips):
+        want = wo.embed(c / 32768.0, model, fe, layer).astype(np.float32)
+        rel = np.sqrt(((g - want) ** 2).mean() / (want ** 2).mean())
+        print(f"wavlm-{size} hidden_states[{layer}] of {arch['layers']} layers: rms rel err {rel:.2e}")
         assert g.shape == want.shape and rel < 5e-3, rel
 
 
