@@ -60,7 +60,7 @@ SIGNATURES = {
     "fad_whisper_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_w2v_load": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int]),
     "fad_w2v_forward": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
-    "fad_encodec_load": (C.c_int, [c_vp, c_vp, C.c_int, c_ll]),
+    "fad_encodec_load": (C.c_int, [c_vp, c_vp, C.c_int, c_ll, C.c_int]),
     "fad_encodec_forward": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp]),
     "fad_resample_geometry": (C.c_int, [C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "fad_resample_length": (c_ll, [C.c_int, C.c_int, c_ll]),
@@ -325,10 +325,10 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ Encodec
-    def encodec_load(self, tensors: list, max_chunk_samples: int = 16 * 240000):
+    def encodec_load(self, tensors: list, max_chunk_samples: int = 16 * 240000, variant: str = "24k"):
         keep = [t.contiguous() for t in tensors]
         arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
-        _check(lib().fad_encodec_load(self._h, arr, len(keep), int(max_chunk_samples)))
+        _check(lib().fad_encodec_load(self._h, arr, len(keep), int(max_chunk_samples), 0 if variant == "24k" else 1))
 
     def encodec_forward(self, pcm: torch.Tensor) -> torch.Tensor:
         """pcm int16 [n_clips, T] (cuda, 24 kHz, equal lengths) -> fp16 [n_clips, ceil(T/320), 128]."""

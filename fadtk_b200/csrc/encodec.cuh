@@ -11,11 +11,51 @@ namespace fad {
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 
+// channels = 2: the mono file duplicated to stereo, as encodec.utils.convert_audio does for the 48 kHz model
 __global__ void __launch_bounds__(256)
-pcm_to_f32_kernel(const int16_t* __restrict__ pcm, long long n, float* __restrict__ out)
+pcm_to_f32_kernel(const int16_t* __restrict__ pcm, long long n, float* __restrict__ out, int channels = 1)
 {
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
-        out[i] = (float)pcm[i] * (1.0f / 32768.0f);                // torchaudio.load normalisation (model_loader.py:168)
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float v = (float)pcm[i] * (1.0f / 32768.0f);          // torchaudio.load normalisation (model_loader.py:168)
+        if (channels == 1) out[i] = v;
+        else { out[2 * i] = v; out[2 * i + 1] = v; }
+    }
+}
+
+// GroupNorm(1, C) ("time_group_norm" of the 48 kHz model): statistics over all T x C values of one sample.
+// stats[b] = {mean, rstd}; one block per sample.
+__global__ void __launch_bounds__(1024)
+groupnorm1_stats_kernel(const float* __restrict__ x, long long per_sample, float* __restrict__ stats)
+{
+    __shared__ double r1[1024], r2[1024];
+    const float* xb = x + (size_t)blockIdx.x * per_sample;
+    double s = 0.0, q = 0.0;
+    for (long long i = threadIdx.x; i < per_sample; i += 1024) { const double v = xb[i]; s += v; q += v * v; }
+    r1[threadIdx.x] = s; r2[threadIdx.x] = q;
+    __syncthreads();
+    for (int k = 512; k > 0; k >>= 1) {
+        if (threadIdx.x < k) { r1[threadIdx.x] += r1[threadIdx.x + k]; r2[threadIdx.x] += r2[threadIdx.x + k]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double m = r1[0] / per_sample, var = r2[0] / per_sample - m * m;
+        stats[2 * blockIdx.x] = (float)m; stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
+}
+// x[b][t][c] = (x - mean_b) rstd_b gamma[c] + beta[c] (+ add[b][t][c]); optional fp16 copy
+__global__ void __launch_bounds__(256)
+groupnorm1_apply_kernel(float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ add, long long per_sample, int C, long long n,
+                        __half* __restrict__ out16)
+{
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+        const long long b = e / per_sample;
+        const int c = (int)(e % C);
+        float v = (x[e] - stats[2 * b]) * stats[2 * b + 1] * gamma[c] + beta[c];
+        if (add != nullptr) v += add[e];
+        x[e] = v;
+        if (out16 != nullptr) out16[e] = __float2half_rn(v);
+    }
 }
 
 // a[(b*T_out + t)][tap*C + c] = act(x[b][t*stride + tap - pad_left][c]).  Encodec's causal SConv1d pads

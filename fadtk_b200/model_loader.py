@@ -263,8 +263,9 @@ class WhisperModel(ModelLoader):
 class EncodecEmbModel(ModelLoader):
     """Encodec (https://github.com/facebookresearch/encodec) continuous encoder output, B200-native
     (model_loader.py:111-176).  ``variant='24k'`` (registry name ``encodec-emb``): the causal SEANet encoder
-    of ``EncodecModel.encodec_model_24khz()`` on the whole file -> [T/320, 128].  The 48 kHz variant
-    (non-causal, time-group norm, 1-s segments) is not built.
+    of ``EncodecModel.encodec_model_24khz()`` on the whole file -> [T/320, 128].  ``variant='48k'``
+    (``encodec-emb-48k``): the non-causal GroupNorm encoder of ``encodec_model_48khz()`` on 1-s segments with
+    stride = segment (:139-152), the mono file duplicated to stereo as ``convert_audio`` does.
     """
 
     def __init__(self, variant: str = '24k', checkpoint=None, seed: int = 0, max_chunk_samples: int = 16 * 240000):
@@ -283,12 +284,10 @@ class EncodecEmbModel(ModelLoader):
         return st
 
     def load_model(self):
-        if self.variant != '24k':
-            raise NotImplementedError("encodec-emb-48k has no sm_100a forward pass yet")
         from . import _native, weights_encodec
         self._engine = _native.engine()
-        self._engine.encodec_load(weights_encodec.pack_encodec(weights_encodec.load_encodec_state(self.checkpoint, self.seed)),
-                                  self.max_chunk_samples)
+        state = weights_encodec.load_encodec_state(self.checkpoint, self.seed, self.variant)
+        self._engine.encodec_load(weights_encodec.pack_encodec(state), self.max_chunk_samples, self.variant)
         self.model = self._engine
         self.device = self._engine.torch_device
 
@@ -317,7 +316,18 @@ class EncodecEmbModel(ModelLoader):
             raise RuntimeError("load_model() has not been called")
         eng = self._engine
         pcm = torch.from_numpy(np.stack(clips)).pin_memory().to(eng.torch_device, non_blocking=True)
-        return list(eng.encodec_forward(pcm))
+        if self.variant == '24k':
+            return list(eng.encodec_forward(pcm))
+        # 48 kHz: every clip is cut into 1-s segments that are encoded independently (model_loader.py:139-152)
+        n, T = pcm.shape
+        seg = 48000
+        full = T // seg
+        parts = []
+        if full:
+            parts.append(eng.encodec_forward(pcm[:, :full * seg].reshape(n * full, seg).contiguous()).reshape(n, full * 150, 128))
+        if T - full * seg:
+            parts.append(eng.encodec_forward(pcm[:, full * seg:].contiguous()))
+        return list(torch.cat(parts, dim=1))
 
 
 class Wav2VecFamilyModel(ModelLoader):

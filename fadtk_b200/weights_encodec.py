@@ -33,11 +33,19 @@ def _conv_keys(prefix):
     return prefix + ".conv.parametrizations.weight.original0", prefix + ".conv.parametrizations.weight.original1", prefix + ".conv.bias"
 
 
-def synthetic_encodec_state(seed: int = 0) -> dict:
+def synthetic_encodec_state(seed: int = 0, variant: str = "24k") -> dict:
+    """24k: causal, weight-normalised convs, mono.  48k: non-causal, plain convs followed by GroupNorm(1, C)
+    ("time_group_norm"), stereo input (encodec_model_48khz, model_loader.py:124-126)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
     def conv(prefix, cout, cin, k):
+        if variant == "48k":
+            sd[prefix + ".conv.weight"] = torch.randn((cout, cin, k), generator=g) * math.sqrt(2.0 / (cin * k))
+            sd[prefix + ".conv.bias"] = 0.02 * torch.randn((cout,), generator=g)
+            sd[prefix + ".norm.weight"] = 1.0 + 0.1 * torch.randn((cout,), generator=g)
+            sd[prefix + ".norm.bias"] = 0.05 * torch.randn((cout,), generator=g)
+            return
         kg, kv, kb = _conv_keys(prefix)
         v = torch.randn((cout, cin, k), generator=g)
         sd[kv] = v
@@ -45,6 +53,8 @@ def synthetic_encodec_state(seed: int = 0) -> dict:
         sd[kb] = 0.02 * torch.randn((cout,), generator=g)
 
     for idx, kind, cin, cout, k, s in conv_table():
+        if kind == "in" and variant == "48k":
+            cin = 2
         if kind == "res":
             conv(f"layers.{idx}.block.1", cin // 2, cin, 3)
             conv(f"layers.{idx}.block.3", cin, cin // 2, 1)
@@ -58,17 +68,24 @@ def synthetic_encodec_state(seed: int = 0) -> dict:
     return sd
 
 
-def load_encodec_state(path=None, seed: int = 0) -> dict:
-    path = path or os.environ.get("FADTK_ENCODEC_CKPT")
+def load_encodec_state(path=None, seed: int = 0, variant: str = "24k") -> dict:
+    path = path or os.environ.get("FADTK_ENCODEC_CKPT" if variant == "24k" else "FADTK_ENCODEC48_CKPT")
     if path and Path(path).exists():
         raw = torch.load(path, map_location="cpu")
         raw = raw.get("state_dict", raw)
         return {k.removeprefix("encoder."): v.float().contiguous() for k, v in raw.items() if "layers." in k and not k.startswith(("decoder.", "quantizer."))}
-    return synthetic_encodec_state(seed)
+    return synthetic_encodec_state(seed, variant)
+
+
+def variant_of(sd: dict) -> str:
+    return "48k" if "layers.0.conv.weight" in sd else "24k"
 
 
 def effective_weight(sd: dict, prefix: str) -> torch.Tensor:
-    """weight_norm: w = g * v / ||v|| with the norm over (in, k) per output channel -> [Cout, Cin, k]"""
+    """weight_norm: w = g * v / ||v|| with the norm over (in, k) per output channel -> [Cout, Cin, k]
+    (the 48 kHz model stores plain weights)"""
+    if prefix + ".conv.weight" in sd:
+        return sd[prefix + ".conv.weight"]
     kg, kv, _ = _conv_keys(prefix)
     v = sd[kv]
     return sd[kg] * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)
@@ -94,14 +111,18 @@ def _bias(b, n):
 
 def pack_encodec(sd: dict) -> list:
     """-> contiguous CPU tensors in the order fad_encodec_load expects (csrc/encodec_host.inc):
-    per conv (execution order; a residual block contributes conv3, conv1, shortcut): weight tiles, bias;
+    per conv (execution order; a residual block contributes conv3, conv1, shortcut): weight tiles, bias, GroupNorm
+    weight, GroupNorm bias (ones / zeros for the 24 kHz model, which has no norm layers);
     then per LSTM layer: W_ih tiles [2048, 512], W_hh tiles over [h_hi | h_lo] = [2048, 1024], bias_ih + bias_hh."""
     out = []
     for idx, kind, cin, cout, k, s in conv_table():
         names = [f"layers.{idx}.block.1", f"layers.{idx}.block.3", f"layers.{idx}.shortcut"] if kind == "res" else [f"layers.{idx}"]
         for p in names:
             w = effective_weight(sd, p)
-            out += [_gemm_weight(w), _bias(sd[p + ".conv.bias"], w.shape[0])]
+            cout = w.shape[0]
+            out += [_gemm_weight(w), _bias(sd[p + ".conv.bias"], cout),
+                    sd.get(p + ".norm.weight", torch.ones(cout)).float().contiguous(),
+                    sd.get(p + ".norm.bias", torch.zeros(cout)).float().contiguous()]
     for l in range(LSTM_LAYERS):
         wih, whh = sd[f"layers.13.lstm.weight_ih_l{l}"], sd[f"layers.13.lstm.weight_hh_l{l}"]
         out += [split_hi_lo_tiles(wih.contiguous()), split_hi_lo_tiles(torch.cat([whh, whh], 1).contiguous()),

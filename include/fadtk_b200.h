@@ -134,10 +134,12 @@ int fad_whisper_logmel(fad_handle* h, const int16_t* pcm, const long long* clip_
 
 /* ---- Encodec: replaces EncodecEmbModel.load_model / _get_frame for the 24 kHz variant
  * (fadtk/model_loader.py:123-130, 155-166): EncodecModel.encodec_model_24khz().encoder(audio) -> [T/320, 128].
- * tensors_host: 42 host pointers in the order documented at the top of csrc/encodec_host.inc, packed by
+ * tensors_host: 78 host pointers in the order documented at the top of csrc/encodec_host.inc, packed by
  * fadtk_b200/weights_encodec.py (weight-norm folded, im2col column order, fp16 hi/lo tiles).
+ * variant 0: encodec_model_24khz (causal, mono, whole file); 1: encodec_model_48khz (non-causal, GroupNorm(1, C)
+ * after every conv, the mono file duplicated to stereo; the caller passes the 1-s segments of :139-152 as clips).
  * max_chunk_samples bounds clips x samples per convolution chunk (0.55 KB of workspace per sample). */
-int fad_encodec_load(fad_handle* h, const void* const* tensors_host, int n_tensors, long long max_chunk_samples);
+int fad_encodec_load(fad_handle* h, const void* const* tensors_host, int n_tensors, long long max_chunk_samples, int variant);
 /* pcm: int16 mono 24 kHz [n_clips][T] (device), all clips of one call have the same length T.
  * emb_out: fp16 [n_clips][ceil(T/320)][128] (device). */
 int fad_encodec_forward(fad_handle* h, const int16_t* pcm, long long n_clips, int T, void* emb_out_f16, void* stream);

@@ -18,14 +18,19 @@ import torch.nn.functional as F
 from fadtk_b200.weights_encodec import conv_table, effective_weight, LSTM_LAYERS
 
 
-def _causal_conv(x, w, b, stride):
-    """x [B, C, T]; causal SConv1d: pad (k - stride) on the left, extra on the right so the last window is full; reflect."""
+def _sconv(x, w, b, stride, causal=True):
+    """x [B, C, T]; SConv1d: causal pads (k - stride) on the left; non-causal splits it (left gets the odd sample);
+    the right side is extended so the last window is full; reflect."""
     k = w.shape[-1]
     pad_total = k - stride
     n_frames = (x.shape[-1] - k + pad_total) / stride + 1
     ideal = (math.ceil(n_frames) - 1) * stride + (k - pad_total)
     extra = ideal - x.shape[-1]
-    x = _reflect_pad(x, pad_total, extra)
+    if causal:
+        x = _reflect_pad(x, pad_total, extra)
+    else:
+        right = pad_total // 2
+        x = _reflect_pad(x, pad_total - right, right + extra)
     return F.conv1d(x, w, b, stride=stride)
 
 
@@ -43,7 +48,14 @@ def _reflect_pad(x, left, right):
 @torch.no_grad()
 def encoder(x: torch.Tensor, sd: dict) -> torch.Tensor:
     """[B, 1, T] float32 -> [B, 128, ceil(T / 320)]"""
-    conv = lambda t, p, s=1: _causal_conv(t, effective_weight(sd, p), sd[p + ".conv.bias"], s)
+    causal = "layers.0.conv.weight" not in sd                  # 48 kHz: non-causal + GroupNorm(1, C) after every conv
+
+    def conv(t, p, s=1):
+        y = _sconv(t, effective_weight(sd, p), sd[p + ".conv.bias"], s, causal)
+        if p + ".norm.weight" in sd:
+            y = F.group_norm(y, 1, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-5)
+        return y
+
     for idx, kind, cin, cout, k, s in conv_table():
         if kind == "in":
             x = conv(x, f"layers.{idx}")
@@ -65,6 +77,12 @@ def encoder(x: torch.Tensor, sd: dict) -> torch.Tensor:
 
 @torch.no_grad()
 def embed(wave: np.ndarray, sd: dict) -> np.ndarray:
-    """What ModelLoader.get_embedding returns for encodec-emb: fp16 [T/320, 128]."""
+    """What ModelLoader.get_embedding returns: fp16 [T/320, 128].  24 kHz: the whole file at once; 48 kHz
+    (model_loader.py:139-152): mono duplicated to stereo (convert_audio), 1-s segments with stride = segment."""
     x = torch.from_numpy(np.asarray(wave, dtype=np.float32)).reshape(1, 1, -1)
-    return encoder(x, sd)[0].transpose(0, 1).numpy().astype(np.float16)
+    if "layers.0.conv.weight" not in sd:
+        return encoder(x, sd)[0].transpose(0, 1).numpy().astype(np.float16)
+    x = x.expand(1, 2, -1)
+    seg = 48000
+    outs = [encoder(x[:, :, o:o + seg], sd)[0].transpose(0, 1) for o in range(0, x.shape[-1], seg)]
+    return torch.cat(outs).numpy().astype(np.float16)

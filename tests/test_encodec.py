@@ -12,7 +12,7 @@ def test_registry_entry():
     names = {m.name: m for m in fk.get_all_models()}
     ml = names["encodec-emb"]
     assert isinstance(ml, fk.EncodecEmbModel) and ml.num_features == 128 and ml.sr == 24000
-    assert names["encodec-emb-48k"].sr == 48000
+    assert names["encodec-emb-48k"].sr == 48000 and isinstance(names["encodec-emb-48k"], fk.EncodecEmbModel)
 
 
 @pytest.mark.gpu
@@ -50,3 +50,20 @@ def test_encodec_fad_parity_on_identical_audio(engine):
     rel = abs(fad_gpu - fad_cpu) / abs(fad_cpu)
     print(f"encodec FAD gpu {fad_gpu:.6f} cpu reference path {fad_cpu:.6f} rel {rel:.2e}")
     assert rel < 1e-4, (fad_gpu, fad_cpu, rel)
+
+
+@pytest.mark.gpu
+def test_48k_variant_matches_oracle(engine):
+    """encodec-emb-48k: non-causal GroupNorm encoder on 1-s segments of the duplicated-mono signal."""
+    clips = [synth.musiclike_clip(3, 2.4, 48000), synth.noise_clip(1, 2.4, 48000)]
+    ml = fk.EncodecEmbModel('48k', max_chunk_samples=8 * 48000)
+    ml.load_model()
+    got = ml.embed_pcm_batch(clips)
+    sd = we.synthetic_encodec_state(0, "48k")
+    for g, c in zip(got, clips):
+        want = eo.embed(c / 32768.0, sd).astype(np.float32)
+        g = g.astype(np.float32)
+        assert g.shape == want.shape == (150 + 150 + 60, 128)
+        rel = np.sqrt(((g - want) ** 2).mean() / (want ** 2).mean())
+        print(f"encodec-48k: rms rel err {rel:.2e}")
+        assert rel < 3e-3, rel

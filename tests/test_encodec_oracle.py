@@ -8,17 +8,21 @@ from fadtk_b200 import weights_encodec as we
 from oracle import encodec_oracle as eo
 
 
-@pytest.mark.parametrize("length", [24000, 24000 * 3 + 137, 500])
-def test_encoder_matches_independent_hf_port(length):
+@pytest.mark.parametrize("variant,length", [("24k", 24000), ("24k", 24000 * 3 + 137), ("24k", 500), ("48k", 48000), ("48k", 31337)])
+def test_encoder_matches_independent_hf_port(variant, length):
     tr = pytest.importorskip("transformers")
-    sd = we.synthetic_encodec_state(3)
-    cfg = tr.EncodecConfig()
-    assert list(cfg.upsampling_ratios)[::-1] == list(we.RATIOS) and cfg.use_causal_conv and cfg.norm_type == "weight_norm"
+    sd = we.synthetic_encodec_state(3, variant)
+    if variant == "24k":
+        cfg = tr.EncodecConfig()
+        assert list(cfg.upsampling_ratios)[::-1] == list(we.RATIOS) and cfg.use_causal_conv and cfg.norm_type == "weight_norm"
+    else:
+        cfg = tr.EncodecConfig(sampling_rate=48000, audio_channels=2, normalize=True, chunk_length_s=1.0, overlap=0.01,
+                               norm_type="time_group_norm", use_causal_conv=False)
     enc = tr.EncodecModel(cfg).eval().encoder
     hf = enc.state_dict()
     assert set(hf) == set(sd) and all(hf[k].shape == sd[k].shape for k in hf)
     enc.load_state_dict(sd)
-    x = 0.3 * torch.randn((2, 1, length), generator=torch.Generator().manual_seed(length))
+    x = 0.3 * torch.randn((2, 1 if variant == "24k" else 2, length), generator=torch.Generator().manual_seed(length))
     with torch.no_grad():
         want = enc(x)
     got = eo.encoder(x, sd)
@@ -32,9 +36,9 @@ def test_embed_shape_and_packing():
     assert e.shape == (150, 128) and e.dtype == np.float16                     # 75 frames per second
     pk = we.pack_encodec(sd)
     n_convs = 1 + 4 * 4 + 1
-    assert len(pk) == 2 * n_convs + 3 * 2
+    assert len(pk) == 4 * n_convs + 3 * 2
     assert pk[0].shape == (2 * 128, 64) and pk[0].dtype == torch.float16       # conv0: 32 x (7 taps x 1 ch) -> [128 pad, 64 pad]
     w = we.effective_weight(sd, "layers.3")                                     # first down conv [64, 32, 4]
     assert torch.allclose(w.flatten(1).norm(dim=1), sd["layers.3.conv.parametrizations.weight.original0"].flatten())
-    g = pk[2 * 4]                                                               # its GEMM weight: column = tap * 32 + c
+    g = pk[4 * 4]                                                               # its GEMM weight: column = tap * 32 + c
     assert g.shape == (2 * 128, 128) and torch.equal(g[5, 2 * 32 + 7].float(), w[5, 7, 2].to(torch.float16).float())
