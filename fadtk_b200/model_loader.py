@@ -301,7 +301,7 @@ class EncodecEmbModel(ModelLoader):
 
     def embed_pcm_batch(self, clips):
         """Clips of equal length share one launch sequence; others are embedded one length group at a time."""
-        clips = [np.asarray(c, dtype=np.int16) for c in clips]
+        clips = [np.asarray(c, dtype=np.int16)[: 3 * 60 * self.sr] for c in clips]       # the reference's 3-minute cut (:171-173)
         out = [None] * len(clips)
         groups = {}
         for i, c in enumerate(clips):

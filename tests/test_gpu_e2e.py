@@ -200,3 +200,25 @@ def test_fad_parity_1e4_on_identical_audio(vgg_engine, vgg_state):
     fad_cpu = fo.frechet_distance(*fo.embd_statistics(cpu["base"]), *fo.embd_statistics(cpu["eval"]))
     rel = abs(fad_gpu - fad_cpu) / abs(fad_cpu)
     assert rel < 1e-4, f"FAD gpu {fad_gpu} vs cpu reference path {fad_cpu}: rel {rel}"
+
+
+@pytest.mark.parametrize("name,seconds", [("encodec-emb", 2.0), ("whisper-tiny", 2.0), ("hubert-base-2", 2.0), ("clap-laion-music", 1.5)])
+def test_directory_flow_for_every_embedder_family(engine, tmp_path, name, seconds):
+    """cache_embedding_files (batched, fad_batch.py:25-48) must write what the plugin contract
+    (load_wav -> get_embedding, model_loader.py:40-70) gives file by file, in the reference's cache layout."""
+    ml = {m.name: m for m in fk.get_all_models()}[name]
+    d = tmp_path / "set"
+    d.mkdir()
+    clips = []
+    for i in range(3):
+        pcm = synth.musiclike_clip(i, seconds + 0.25 * i, ml.sr)
+        synth.write_wav(d / f"c{i}.wav", pcm, ml.sr)
+        clips.append(pcm)
+    fk.cache_embedding_files(d, ml, workers=2)
+    for i, pcm in enumerate(clips):
+        e = np.load(d / "embeddings" / name / f"c{i}.npy")
+        assert e.dtype == np.float16 and e.ndim == 2 and e.shape[1] == ml.num_features
+        one = ml.get_embedding(ml.load_wav(d / "convert" / str(ml.sr) / f"c{i}.wav"))
+        assert np.array_equal(e, one), (name, i)
+    mu, cov = fk.FrechetAudioDistance(ml, load_model=False).load_stats(d)
+    assert mu.shape == (ml.num_features,) and cov.shape == (ml.num_features, ml.num_features) and np.isfinite(cov).all()
