@@ -90,7 +90,7 @@ MODELS = {
                         workload="encodec-emb (24 kHz SEANet encoder) FAD, {clips} x 10 s synthetic 24 kHz clips per GPU (750 rows per clip) "
                                  "vs {base}-clip baseline (BASELINE.json configs[3] embedding stage)",
                         rows_flop=ENCODEC_GEMM_FLOP),
-    "whisper-small": dict(sr=16000, clips=256, baseline_clips=64, chunk_clips=32, d=768,
+    "whisper-small": dict(sr=16000, clips=256, baseline_clips=64, chunk_clips=64, d=768,
                           workload="whisper-small FAD, {clips} x 10 s synthetic 16 kHz clips per GPU (each padded to 30 s, 2 rows per clip) "
                                    "vs {base}-clip baseline (BASELINE.json configs[4] embedding stage)",
                           rows_flop=WHISPER_SMALL_GEMM_FLOP),
