@@ -133,5 +133,25 @@ def main():
     print("indiv:", list(zip(names, scores))[:3], "... kept", len(rows), "of", len(songs))
 
 
+def registry():
+    """names / num_features / sample rates of the reference's get_all_models() (model_loader.py:676-701) ->
+    tests/golden/registry.json.  Only the constructors run (no model code); laion_clap's version probe
+    (model_loader.py:317) is answered with the locked version."""
+    import importlib.metadata as md
+    import json
+    load_reference()
+    real = md.version
+    md.version = lambda name: "1.1.7" if name == "laion_clap" else real(name)
+    try:
+        from fadtk.model_loader import get_all_models
+        rows = [[m.name, int(m.num_features), int(m.sr)] for m in get_all_models()]
+    finally:
+        md.version = real
+    OUT.mkdir(parents=True, exist_ok=True)
+    (OUT / "registry.json").write_text(json.dumps(rows, indent=0))
+    print(f"registry.json: {len(rows)} models")
+
+
 if __name__ == "__main__":
     main()
+    registry()

@@ -161,3 +161,14 @@ def test_two_rank_statistics_allreduce_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "rank0:ok" in out.stdout and "rank1:ok" in out.stdout, out.stdout
+
+
+def test_registry_matches_the_reference(golden_dir):
+    """get_all_models(): same names, order, dimensionality and sample rate as the reference's registry
+    (fadtk/model_loader.py:676-701; golden list generated from the real package by oracle/make_golden.py)."""
+    import json
+    want = json.loads((golden_dir / "registry.json").read_text())
+    got = [[m.name, int(m.num_features), int(m.sr)] for m in fk.get_all_models()]
+    assert got == want
+    unbuilt = [m.name for m in fk.get_all_models() if isinstance(m, fk.UnbuiltModel)]
+    assert unbuilt == ["clap-2023"]                       # every other embedder has an sm_100a forward pass
