@@ -109,10 +109,31 @@ def _bias(b, n):
     return out
 
 
+def time_pack(cout: int) -> int:
+    """outputs computed per GEMM row: thin layers (Cout < 128) pack P consecutive time steps into one row so the
+    128-wide tensor-core tile is full (P * Cout = 128)"""
+    return max(1, 128 // cout) if cout < 128 else 1
+
+
+def _packed_weight(w: torch.Tensor, stride: int, P: int) -> torch.Tensor:
+    """[Cout, Cin, k] -> banded [P*Cout, (k + (P-1) stride) * Cin]: row p*Cout + co, column j*Cin + ci holds
+    w[co, ci, j - p*stride] (P outputs of the strided conv from one window of k + (P-1) stride inputs)"""
+    cout, cin, k = w.shape
+    kp = k + (P - 1) * stride
+    m = torch.zeros((P * cout, kp, cin))
+    wt = w.permute(0, 2, 1)                                            # [Cout, k, Cin]
+    for p_ in range(P):
+        m[p_ * cout:(p_ + 1) * cout, p_ * stride:p_ * stride + k, :] = wt
+    full = torch.zeros((_pad_to(P * cout, 128), _pad_to(kp * cin, 64)))
+    full[:P * cout, :kp * cin] = m.reshape(P * cout, kp * cin)
+    return split_hi_lo_tiles(full)
+
+
 def pack_encodec(sd: dict) -> list:
     """-> contiguous CPU tensors in the order fad_encodec_load expects (csrc/encodec_host.inc):
     per conv (execution order; a residual block contributes conv3, conv1, shortcut): weight tiles, bias, GroupNorm
-    weight, GroupNorm bias (ones / zeros for the 24 kHz model, which has no norm layers);
+    weight, GroupNorm bias (ones / zeros for the 24 kHz model, which has no norm layers), time-packed weight tiles
+    and bias (see time_pack; identical to the plain ones when P = 1);
     then per LSTM layer: W_ih tiles [2048, 512], W_hh tiles over [h_hi | h_lo] = [2048, 1024], bias_ih + bias_hh."""
     out = []
     for idx, kind, cin, cout, k, s in conv_table():
@@ -120,9 +141,11 @@ def pack_encodec(sd: dict) -> list:
         for p in names:
             w = effective_weight(sd, p)
             cout = w.shape[0]
+            P = time_pack(cout)
             out += [_gemm_weight(w), _bias(sd[p + ".conv.bias"], cout),
                     sd.get(p + ".norm.weight", torch.ones(cout)).float().contiguous(),
-                    sd.get(p + ".norm.bias", torch.zeros(cout)).float().contiguous()]
+                    sd.get(p + ".norm.bias", torch.zeros(cout)).float().contiguous(),
+                    _packed_weight(w, s, P), _bias(sd[p + ".conv.bias"].repeat(P), P * cout)]
     for l in range(LSTM_LAYERS):
         wih, whh = sd[f"layers.13.lstm.weight_ih_l{l}"], sd[f"layers.13.lstm.weight_hh_l{l}"]
         out += [split_hi_lo_tiles(wih.contiguous()), split_hi_lo_tiles(torch.cat([whh, whh], 1).contiguous()),

@@ -36,9 +36,13 @@ def test_embed_shape_and_packing():
     assert e.shape == (150, 128) and e.dtype == np.float16                     # 75 frames per second
     pk = we.pack_encodec(sd)
     n_convs = 1 + 4 * 4 + 1
-    assert len(pk) == 4 * n_convs + 3 * 2
+    assert len(pk) == 6 * n_convs + 3 * 2
     assert pk[0].shape == (2 * 128, 64) and pk[0].dtype == torch.float16       # conv0: 32 x (7 taps x 1 ch) -> [128 pad, 64 pad]
     w = we.effective_weight(sd, "layers.3")                                     # first down conv [64, 32, 4]
     assert torch.allclose(w.flatten(1).norm(dim=1), sd["layers.3.conv.parametrizations.weight.original0"].flatten())
-    g = pk[4 * 4]                                                               # its GEMM weight: column = tap * 32 + c
+    g = pk[6 * 4]                                                               # its GEMM weight: column = tap * 32 + c
     assert g.shape == (2 * 128, 128) and torch.equal(g[5, 2 * 32 + 7].float(), w[5, 7, 2].to(torch.float16).float())
+    gp = pk[6 * 4 + 4]                               # time-packed: 2 outputs per row from 4 + 2 = 6 input steps (stride 2)
+    assert we.time_pack(64) == 2 and gp.shape == (2 * 128, 6 * 32)
+    assert torch.equal(gp[64 + 5, (2 + 1) * 32 + 7].float(), w[5, 7, 1].to(torch.float16).float())     # output 1 is shifted by the stride
+    assert not gp[:64, 4 * 32:].any() and not gp[64:128, :2 * 32].any()
