@@ -73,6 +73,20 @@ def _encodec_gemm_flop(T=240000):
 
 
 ENCODEC_GEMM_FLOP = _encodec_gemm_flop()
+
+
+def _w2v_gemm_flop(L=160000, d=768, layers=12, ffn=3072):
+    """conv feature encoder + projection + positional conv + transformer GEMMs per clip of L samples"""
+    t, fl, cin = L, 0, 1
+    for k, s_ in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
+        t = (t - k) // s_ + 1
+        fl += 2 * t * 512 * k * cin
+        cin = 512
+    fl += 2 * t * d * 512 + 2 * t * d * (d // 16) * 128
+    return fl + layers * 2 * t * (4 * d * d + 2 * d * ffn)
+
+
+W2V2_BASE_GEMM_FLOP = _w2v_gemm_flop()
 CLAP_MUSIC_GEMM_FLOP = _htsat_gemm_flop(128, (2, 2, 12, 2))
 
 MODELS = {
@@ -86,10 +100,13 @@ MODELS = {
     "clap-laion-music": dict(sr=48000, clips=250, baseline_clips=50, chunk_clips=25, d=512,
                              workload="clap-laion-music (HTSAT-base) FAD, {clips} x 10 s synthetic 48 kHz clips per GPU vs {base}-clip baseline",
                              rows_flop=CLAP_MUSIC_GEMM_FLOP),
-    "encodec-emb": dict(sr=24000, clips=512, baseline_clips=64, chunk_clips=128, d=128,
+    "encodec-emb": dict(sr=24000, clips=512, baseline_clips=64, chunk_clips=512, d=128,
                         workload="encodec-emb (24 kHz SEANet encoder) FAD, {clips} x 10 s synthetic 24 kHz clips per GPU (750 rows per clip) "
                                  "vs {base}-clip baseline (BASELINE.json configs[3] embedding stage)",
                         rows_flop=ENCODEC_GEMM_FLOP),
+    "w2v2-base": dict(sr=16000, clips=256, baseline_clips=32, chunk_clips=32, d=768,
+                      workload="w2v2-base (hidden_states[12]) FAD, {clips} x 10 s synthetic 16 kHz clips per GPU (499 rows per clip) vs {base}-clip baseline",
+                      rows_flop=W2V2_BASE_GEMM_FLOP),
     "whisper-small": dict(sr=16000, clips=256, baseline_clips=64, chunk_clips=64, d=768,
                           workload="whisper-small FAD, {clips} x 10 s synthetic 16 kHz clips per GPU (each padded to 30 s, 2 rows per clip) "
                                    "vs {base}-clip baseline (BASELINE.json configs[4] embedding stage)",
@@ -151,6 +168,10 @@ def oracle_embed_fn(model: str, state):
     if model == "encodec-emb":
         from oracle import encodec_oracle as eo
         return lambda pcm: eo.embed(pcm / 32768.0, state)
+    if model == "w2v2-base":
+        from oracle import w2v_oracle as wv
+        hf, fe = wv.build(state, "w2v2")
+        return lambda pcm: wv.embed(pcm / 32768.0, hf, fe, 12)
     if model.startswith("whisper-"):
         from fadtk_b200 import weights_whisper
         from oracle import whisper_oracle as wo
@@ -228,6 +249,9 @@ def main():
     elif args.model == "encodec-emb":
         from fadtk_b200 import weights_encodec
         state = weights_encodec.synthetic_encodec_state(0)
+    elif args.model == "w2v2-base":
+        from fadtk_b200 import weights_w2v
+        state = weights_w2v.synthetic_w2v_state(0)
     elif args.model.startswith("whisper-"):
         from fadtk_b200 import weights_whisper
         state = weights_whisper.synthetic_whisper_state(0, args.model.split("-", 1)[1])
@@ -270,6 +294,8 @@ def main():
     eng = _native.Engine(local_rank, max_examples=args.chunk_clips * ROWS_PER_CLIP)
     if args.model == "vggish":
         eng.vggish_load(weights.pack_vggish(state))
+    elif args.model == "w2v2-base":
+        eng.w2v_load(weights_w2v.config_of(state), weights_w2v.pack_w2v(state), args.chunk_clips, max_len=int(CLIP_SECONDS * sr))
     elif args.model == "encodec-emb":
         eng.encodec_load(weights_encodec.pack_encodec(state), max_chunk_samples=16 * int(CLIP_SECONDS * sr))
     elif args.model.startswith("whisper-"):
@@ -322,7 +348,7 @@ def main():
 
     # ---- roofline of the dominant kernel: the tcgen05 conv/FC (GEMM) kernel
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    rows = args.clips * (1 if args.model.startswith("whisper-") or args.model == "encodec-emb" else ROWS_PER_CLIP) * args.steps   # examples (VGGish) / 10-s windows (CLAP) / clips (Whisper)
+    rows = args.clips * (1 if args.model.startswith("whisper-") or args.model in ("encodec-emb", "w2v2-base") else ROWS_PER_CLIP) * args.steps   # examples (VGGish) / 10-s windows (CLAP) / clips (Whisper)
     gemm_keys = list(UMMA_LAYER_FLOP) if args.model == "vggish" else ["clap_gemm"]
     umma_ms = sum(prof[k][0] for k in gemm_keys if k in prof)
     umma_launch = sum(prof[k][1] for k in gemm_keys if k in prof)

@@ -47,6 +47,11 @@ class EvalSetFAD:
             for ratio in (2, 4, 5, 8):                       # ceil at every down-sampling conv
                 r = -(-r // ratio)
             self.rows_per_clip = r
+        elif model.split("-")[0] in ("w2v2", "hubert", "wavlm", "MERT"):
+            self.d = 1024 if "large" in model else 768
+            self.rows_per_clip = _native.Engine.w2v_frames(self.clip_samples)
+            tail = model.rsplit("-", 1)[-1]
+            self.w2v_layer = int(tail) if tail.isdigit() else (24 if "large" in model else 12)
         elif model.startswith("whisper-"):
             from .model_loader import WhisperModel
             self.d = WhisperModel.DIMS[model.split("-", 1)[1]]
@@ -66,7 +71,7 @@ class EvalSetFAD:
             if self.model == "vggish":
                 ex, _ = self.eng.vggish_plan(off)
                 self._plans[n_clips] = (torch.from_numpy(ex).to(self.dev),)
-            elif self.model == "encodec-emb":
+            elif self.model == "encodec-emb" or hasattr(self, "w2v_layer"):
                 self._plans[n_clips] = ()
             elif self.model.startswith("whisper-"):
                 self._plans[n_clips] = (torch.from_numpy(off[:-1].copy()).to(self.dev),
@@ -81,7 +86,9 @@ class EvalSetFAD:
         flat = pcm_dev.reshape(-1)
         if self.model == "vggish":
             return self.eng.vggish_forward(flat, plan[0], out)
-        if self.model == "encodec-emb":
+        if hasattr(self, "w2v_layer"):
+            emb = self.eng.w2v_forward(pcm_dev.contiguous(), self.w2v_layer).reshape(-1, self.d)
+        elif self.model == "encodec-emb":
             emb = self.eng.encodec_forward(pcm_dev.contiguous()).reshape(-1, self.d)
         elif self.model.startswith("whisper-"):
             emb = self.eng.whisper_forward(flat, plan[0], plan[1]).reshape(-1, self.d)
