@@ -197,10 +197,13 @@ int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw
 // a_cols: channels actually stored per pixel/row of the activation (<= g.Cin); the TMA box reads
 // zeros beyond it, so a K that is not a multiple of 64 needs no padding columns in HBM.
 int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const void* w,
-                      CUtensorMap* mx, CUtensorMap* mw, int a_cols = 0) {
+                      CUtensorMap* mx, CUtensorMap* mw, int a_cols = 0, long long a_row_stride = 0) {
     const uint64_t ac = a_cols > 0 ? (uint64_t)a_cols : (uint64_t)g.Cin;
     const uint64_t xd[4] = {ac, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)nb_dim};
-    const uint64_t xs[3] = {ac * 2, (uint64_t)g.W * ac * 2, (uint64_t)g.H * g.W * ac * 2};
+    uint64_t xs[3] = {ac * 2, (uint64_t)g.W * ac * 2, (uint64_t)g.H * g.W * ac * 2};
+    // 1x1 geometry only: rows a_row_stride elements apart (< a_cols = overlapping rows, e.g. the sliding
+    // windows of a strided 1-D convolution read straight from the [T][C] activation, no im2col copy)
+    if (a_row_stride > 0) xs[0] = xs[1] = xs[2] = (uint64_t)a_row_stride * 2;
     const uint32_t xb[4] = {64, (uint32_t)g.box_w, (uint32_t)g.box_h, (uint32_t)g.box_n};
     if (encode_f16_map(mx, x, 4, xd, xs, xb)) return 1;
     const uint64_t K = (uint64_t)g.taps * g.Cin;
@@ -725,13 +728,8 @@ int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, 
 // ----------------------------------------------------------------------------- Frechet
 namespace {
 int launch_dgemm2(fad_handle* h, const fad::DgemmBatch& batch, int nprob, int d, cudaStream_t st) {
-    if (d <= 768) {                                            // 32x32 tiles: >= 2 waves of CTAs from d = 512 down
-        dim3 grid((d + 31) / 32, (d + 31) / 32, nprob);
-        fad::dgemm_kernel<32><<<grid, 256, 0, st>>>(batch, d);
-    } else {
-        dim3 grid((d + 63) / 64, (d + 63) / 64, nprob);
-        fad::dgemm_kernel<64><<<grid, 256, 0, st>>>(batch, d);
-    }
+    dim3 grid((d + fad::kDgTileN - 1) / fad::kDgTileN, (d + fad::kDgTileM - 1) / fad::kDgTileM, nprob);
+    fad::dgemm_kernel<<<grid, 256, 0, st>>>(batch, d);
     CK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -888,12 +886,9 @@ int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, c
     float* flags = reinterpret_cast<float*>(scalM + 2 * G);
     int* ok = reinterpret_cast<int*>(flags + 3 * G);
     const int dt = (d + 31) / 32;
-    const bool small = d <= 768;
-    const int gt = small ? dt : (d + 63) / 64;
     auto gemm = [&](const fad::DgemmStrided& p, int families) -> int {
-        dim3 grid(gt, gt, (unsigned)(p.items * families));
-        if (small) fad::dgemm_strided_kernel<32><<<grid, 256, 0, st>>>(p, d);
-        else       fad::dgemm_strided_kernel<64><<<grid, 256, 0, st>>>(p, d);
+        dim3 grid((d + fad::kDgTileN - 1) / fad::kDgTileN, (d + fad::kDgTileM - 1) / fad::kDgTileM, (unsigned)(p.items * families));
+        fad::dgemm_strided_kernel<<<grid, 256, 0, st>>>(p, d);
         CK(cudaGetLastError());
         h->launches++;
         return 0;

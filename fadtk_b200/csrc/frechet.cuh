@@ -20,8 +20,7 @@ namespace fad {
 
 // C = alpha * A * B + beta_diag * I   (row-major d x d, fp64), optional trace(C) accumulation.
 // Up to two independent problems per launch (blockIdx.z): the Y <- Y W and Z <- W Z updates of
-// one Newton-Schulz iteration run side by side.  TM x TM tile / 256 threads, K step 16;
-// TM = 32 for small d (more CTAs), 64 otherwise.
+// one Newton-Schulz iteration run side by side.  64 x 32 tile / 256 threads (dgemm_tile below).
 //
 // Convergence control without host round trips: a launch whose `dev_in` (max |W - I| of the previous
 // iteration) is below `tol` returns immediately, so a fixed-length launch sequence costs only
@@ -33,49 +32,100 @@ struct DgemmBatch {
     const float* dev_in; float* dev_out; float* dev_clear; float tol;
 };
 
-// one TM x TM tile of C = alpha A B + beta_diag I; returns max |C - I| over this thread's outputs and
-// its share of tr C
-template <int TM>
+// One 64 x 32 tile of C = alpha A B + beta_diag I per 256-thread CTA; returns max |C - I| over this thread's
+// outputs and its share of tr C (both zero for threads that hold no final outputs).
+// Layout: 4 k-groups x 2 warps.  A warp owns 32 x 32 outputs (4 x 8 threads of 8 x 4 each: 32 DFMAs per
+// 6 LDS.128, so the fp64 pipe and not shared memory is the limit); the four k-groups split every 16-wide
+// K chunk between them (in-CTA split-K keeps 8 warps per CTA busy although a d = 768 problem has only 288
+// tiles) and are summed through shared memory in a fixed order.  Global loads of chunk c+1 are issued
+// before the FMAs of chunk c (register staging, two smem buffers, one barrier per chunk).
+constexpr int kDgTileM = 64, kDgTileN = 32, kDgKC = 16;
+
 __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, const double* __restrict__ B,
                                            double* __restrict__ C, int d, double alpha, double beta_diag,
                                            float& dev, double& tr)
 {
-    constexpr int R = TM / 16;                                 // outputs per thread per dimension
-    __shared__ double As[16][TM + 1], Bs[16][TM + 1];
-    const int bi = blockIdx.y * TM, bj = blockIdx.x * TM;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double c[R][R] = {};
-    for (int k0 = 0; k0 < d; k0 += 16) {
-        for (int i = threadIdx.x; i < TM * 16; i += 256) {
-            const int r = i >> 4, k = i & 15;                  // A tile: TM rows x 16 k
-            const int gi = bi + r, gk = k0 + k;
-            As[k][r] = (gi < d && gk < d) ? A[(size_t)gi * d + gk] : 0.0;
+    __shared__ __align__(16) double As[2][kDgKC][kDgTileM + 2];
+    __shared__ __align__(16) double Bs[2][kDgKC][kDgTileN + 2];
+    const int bi = blockIdx.y * kDgTileM, bj = blockIdx.x * kDgTileN;
+    const int t = threadIdx.x, kg = t >> 6, lane = t & 31;
+    const int r0 = ((t >> 5) & 1) * 32 + (lane >> 3) * 8, c0 = (lane & 7) * 4;
+    // loader roles: A chunk = 64 rows x 16 k (4 consecutive k per thread), B chunk = 16 k x 32 cols (2 cols per thread)
+    const int la_row = t >> 2, la_k = (t & 3) * 4, lb_k = t >> 4, lb_c = (t & 15) * 2;
+    const bool a_row_ok = bi + la_row < d;
+    const double* a_src = A + (size_t)(bi + la_row) * d + la_k;
+    double ra[4], rb[2];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ra[e] = (a_row_ok && k0 + la_k + e < d) ? a_src[k0 + e] : 0.0;
+        const bool kok = k0 + lb_k < d;
+        const double* b_src = B + (size_t)(k0 + lb_k) * d + bj + lb_c;
+        rb[0] = (kok && bj + lb_c < d) ? b_src[0] : 0.0;
+        rb[1] = (kok && bj + lb_c + 1 < d) ? b_src[1] : 0.0;
+    };
+    auto stage = [&](int buf) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) As[buf][la_k + e][la_row] = ra[e];
+        *reinterpret_cast<double2*>(&Bs[buf][lb_k][lb_c]) = make_double2(rb[0], rb[1]);
+    };
+    double c[8][4] = {};
+    const int chunks = (d + kDgKC - 1) / kDgKC;
+    fetch(0);
+    stage(0);
+    __syncthreads();
+    for (int ch = 0; ch < chunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < chunks) fetch((ch + 1) * kDgKC);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = kg * 4 + kk;
+            double a[8], b[4];
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&As[buf][k][r0 + u]);
+                a[u] = v.x; a[u + 1] = v.y;
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v += 2) {
+                const double2 w = *reinterpret_cast<const double2*>(&Bs[buf][k][c0 + v]);
+                b[v] = w.x; b[v + 1] = w.y;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) c[u][v] = fma(a[u], b[v], c[u][v]);
         }
-        for (int i = threadIdx.x; i < 16 * TM; i += 256) {
-            const int k = i / TM, cc = i % TM;                 // B tile: 16 k x TM cols
-            const int gk = k0 + k, gj = bj + cc;
-            Bs[k][cc] = (gk < d && gj < d) ? B[(size_t)gk * d + gj] : 0.0;
+        if (ch + 1 < chunks) stage(buf ^ 1);
+        __syncthreads();
+    }
+    // sum the k-groups: groups 1..3 hand their partial tiles to group 0 one after the other
+    double* red = &As[0][0][0];                                 // 64 x 32 doubles <= sizeof(As)
+    static_assert(sizeof(double) * kDgTileM * kDgTileN <= sizeof(As), "reduction scratch");
+    const int slot = (t & 63) * 32;                             // 32 doubles per thread, thread-major
+    for (int g = 1; g < 4; ++g) {
+        if (kg == g) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) red[slot + ((u * 4 + v + (t & 31)) & 31)] = c[u][v];
         }
         __syncthreads();
+        if (kg == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            double a[R], b[R];
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int u = 0; u < R; ++u) { a[u] = As[k][ty * R + u]; b[u] = Bs[k][tx * R + u]; }
-#pragma unroll
-            for (int u = 0; u < R; ++u)
-#pragma unroll
-                for (int v = 0; v < R; ++v) c[u][v] = fma(a[u], b[v], c[u][v]);
+                for (int v = 0; v < 4; ++v) c[u][v] += red[slot + ((u * 4 + v + (t & 31)) & 31)];
         }
         __syncthreads();
     }
     tr = 0.0;
     dev = 0.0f;
+    if (kg != 0) return;
 #pragma unroll
-    for (int u = 0; u < R; ++u)
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int v = 0; v < R; ++v) {
-            const int gi = bi + ty * R + u, gj = bj + tx * R + v;
+        for (int v = 0; v < 4; ++v) {
+            const int gi = bi + r0 + u, gj = bj + c0 + v;
             if (gi < d && gj < d) {
                 double val = alpha * c[u][v];
                 if (gi == gj) { val += beta_diag; tr += val; }
@@ -85,8 +135,8 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, const d
         }
 }
 
-template <int TM>
-__global__ void __launch_bounds__(256)
+// grid (ceil(d / 32), ceil(d / 64), problems)
+__global__ void __launch_bounds__(256, 2)
 dgemm_kernel(const DgemmBatch batch, int d)
 {
     if (batch.dev_in != nullptr && *batch.dev_in < batch.tol) return;      // already converged
@@ -95,13 +145,13 @@ dgemm_kernel(const DgemmBatch batch, int d)
     const DgemmProblem pr = batch.p[blockIdx.z];
     float dev;
     double tr;
-    dgemm_tile<TM>(pr.A, pr.B, pr.C, d, pr.alpha, pr.beta_diag, dev, tr);
+    dgemm_tile(pr.A, pr.B, pr.C, d, pr.alpha, pr.beta_diag, dev, tr);
     if (batch.dev_out != nullptr) {
         for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
         if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(batch.dev_out), __float_as_uint(dev));
     }
-    if (pr.trace_out != nullptr && blockIdx.x == blockIdx.y) {
-        // diagonal blocks only; reduce inside the block, one atomic per block
+    if (pr.trace_out != nullptr && (blockIdx.x >> 1) == blockIdx.y) {
+        // tiles that meet the diagonal only; reduce inside the block, one atomic per block
         __shared__ double red[256];
         red[threadIdx.x] = tr;
         __syncthreads();

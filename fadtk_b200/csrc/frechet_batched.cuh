@@ -102,8 +102,7 @@ struct DgemmStrided {
     float tol;
 };
 
-template <int TM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dgemm_strided_kernel(const DgemmStrided p, int d)
 {
     const int fam = blockIdx.z >= p.items ? 1 : 0;
@@ -114,7 +113,7 @@ dgemm_strided_kernel(const DgemmStrided p, int d)
     const DgemmFamily f = p.f[fam];
     float dev;
     double tr;
-    dgemm_tile<TM>(f.A + (size_t)z * f.sA, f.B + (size_t)z * f.sB, f.C + (size_t)z * f.sC, d, f.alpha, f.beta_diag, dev, tr);
+    dgemm_tile(f.A + (size_t)z * f.sA, f.B + (size_t)z * f.sB, f.C + (size_t)z * f.sC, d, f.alpha, f.beta_diag, dev, tr);
     if (fl && p.out_slot >= 0) {
         for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
         if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(fl + p.out_slot), __float_as_uint(dev));

@@ -56,6 +56,106 @@ w2v_groupnorm_gelu_kernel(float* __restrict__ x, int T, int C, const float* __re
     }
 }
 
+// ---- conv 0 of the group-norm feature encoder, fused: Conv1d(1, 512, k = 10, stride 5) -> GroupNorm(512, 512)
+// -> GELU, written once as fp16.  GroupNorm's per-(clip, channel) statistics over time are linear / quadratic
+// forms of the clip's window moments: with y[t][c] = sum_j w[c][j] x[5t + j] + b[c],
+//   mean_t y = w[c] . m + b[c],   var_t y = w[c]^T (R - m m^T) w[c],
+//   m[j] = mean_t x[5t + j],  R[j][j'] = mean_t x[5t + j] x[5t + j'],
+// so the fp32 [T][512] conv output never exists in HBM (it was written once and read three times before).
+// Moments and the 10 x 10 forms are evaluated in fp64.
+
+// acc[b][0..9] += sum_t x[5t + j];  acc[b][10 + j(j+1)/2 + j'] += sum_t x[5t + j] x[5t + j']  (j' <= j).  grid (slices, B).
+__global__ void __launch_bounds__(256)
+w2v_conv0_moments_kernel(const float* __restrict__ xn, int L, int T1, double* __restrict__ acc /*[B][65]*/)
+{
+    __shared__ double red[8][65];
+    const float* x = xn + (size_t)blockIdx.y * L;
+    double a[65];
+#pragma unroll
+    for (int i = 0; i < 65; ++i) a[i] = 0.0;
+    for (int t = blockIdx.x * 256 + threadIdx.x; t < T1; t += gridDim.x * 256) {
+        double v[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) v[j] = (double)x[5 * t + j];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            a[j] += v[j];
+#pragma unroll
+            for (int k = 0; k <= j; ++k) a[10 + j * (j + 1) / 2 + k] = fma(v[j], v[k], a[10 + j * (j + 1) / 2 + k]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 65; ++i) {
+        double r = a[i];
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 65) {
+        double r = 0.0;
+        for (int w = 0; w < 8; ++w) r += red[w][threadIdx.x];
+        atomicAdd(acc + (size_t)blockIdx.y * 65 + threadIdx.x, r);
+    }
+}
+
+// coef[b][c] = (scale, shift) with GroupNorm(y)*gamma + beta = conv_nobias(x) * scale + shift.  One thread per (b, c).
+__global__ void __launch_bounds__(256)
+w2v_conv0_coef_kernel(const double* __restrict__ acc, const float* __restrict__ w /*[512][10]*/, const float* __restrict__ bias,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int T1, int n /* B*512 */, float2* __restrict__ coef)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int b = i >> 9, c = i & 511;
+    const double* a = acc + (size_t)b * 65;
+    const double inv = 1.0 / (double)T1;
+    double wv[10], m[10];
+    for (int j = 0; j < 10; ++j) { wv[j] = (double)w[c * 10 + j]; m[j] = a[j] * inv; }
+    double mean = 0.0, var = 0.0;
+    for (int j = 0; j < 10; ++j) {
+        mean += wv[j] * m[j];
+        for (int k = 0; k <= j; ++k) {
+            const double cov = a[10 + j * (j + 1) / 2 + k] * inv - m[j] * m[k];
+            var += (k == j ? 1.0 : 2.0) * wv[j] * wv[k] * cov;
+        }
+    }
+    const double scale = (double)gamma[c] / sqrt(var + 1e-5);
+    // y = conv + bias, mean_y = mean + bias: (y - mean_y) * scale + beta = conv * scale + (beta - mean * scale)
+    (void)bias;
+    coef[i] = make_float2((float)scale, (float)((double)beta[c] - mean * scale));
+}
+
+// out[b][t][c] = fp16(GELU(conv(x)[t][c] * scale + shift)) for t < T1, zeros for T1 <= t < P1 (row pitch P1 per clip,
+// chosen so that the next layers can read their sliding windows as strided GEMM rows).
+// grid (ceil(P1 / 128), B), 256 threads = 2 channels each.
+__global__ void __launch_bounds__(256)
+w2v_conv0_apply_kernel(const float* __restrict__ xn, int L, int T1, int P1, const float* __restrict__ w /*[512][10]*/,
+                       const float2* __restrict__ coef /*[B][512]*/, __half* __restrict__ out)
+{
+    constexpr int TT = 128;
+    __shared__ float xs[5 * TT + 8];
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    const float* x = xn + (size_t)b * L;
+    for (int i = threadIdx.x; i < 5 * TT + 5; i += 256) { const int g = 5 * t0 + i; xs[i] = g < L ? x[g] : 0.f; }
+    const int c = 2 * threadIdx.x;
+    float w0[10], w1[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { w0[j] = w[c * 10 + j]; w1[j] = w[c * 10 + 10 + j]; }
+    const float2 k0 = coef[(size_t)b * 512 + c], k1 = coef[(size_t)b * 512 + c + 1];
+    __syncthreads();
+    __half2* o = reinterpret_cast<__half2*>(out + ((size_t)b * P1 + t0) * 512 + c);
+    const int t_end = min(TT, P1 - t0);
+    for (int t = 0; t < t_end; ++t) {
+        float y0 = 0.f, y1 = 0.f;
+        if (t0 + t < T1) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { const float v = xs[5 * t + j]; y0 = fmaf(w0[j], v, y0); y1 = fmaf(w1[j], v, y1); }
+            y0 = gelu_erf(fmaf(y0, k0.x, k0.y));
+            y1 = gelu_erf(fmaf(y1, k1.x, k1.y));
+        }
+        o[(size_t)t * 256] = __floats2half2_rn(y0, y1);
+    }
+}
+
 // im2col of the grouped positional convolution (k = 128, padding 64, groups of 48 channels):
 // a[(b*T + t)][tap*cg + ci] = h[b][t + tap - 64][g*cg + ci] (zero outside the sequence).  8 channels per thread.
 __global__ void __launch_bounds__(256)
