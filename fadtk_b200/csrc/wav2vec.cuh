@@ -1,7 +1,7 @@
 // wav2vec 2.0 / HuBERT / MERT style encoders (W2V2Model, HuBERTModel, MERTModel of fadtk/model_loader.py:
 // processor normalisation -> 7-layer conv feature encoder -> feature projection -> grouped positional conv ->
 // post-LN transformer layers -> hidden_states[layer]).  Convs and Linears run on the tcgen05 GEMM
-// (im2col by encodec_im2col_kernel), attention on whisper_flash_attention_kernel, LayerNorm on clap_ln_kernel;
+// (operands read in place through overlapping-row tensor maps), attention on whisper_flash_attention_kernel, LayerNorm on clap_ln_kernel;
 // this file adds the pieces those do not cover.
 #pragma once
 #include <cuda_fp16.h>
@@ -27,33 +27,6 @@ w2v_normalize_kernel(const int16_t* __restrict__ pcm, int L, float* __restrict__
     const float m = (float)mean, inv = (float)(1.0 / sqrt(var + 1e-7));
     float* dst = out + (size_t)blockIdx.x * L;
     for (int i = threadIdx.x; i < L; i += 1024) dst[i] = ((float)src[i] * (1.0f / 32768.0f) - m) * inv;
-}
-
-// GroupNorm(num_groups = C, C) (= per-channel normalisation over time, eps 1e-5, affine) + exact GELU, in place.
-// x: fp32 [B][T][C].  grid (C / 64, B), 256 threads = 64 channels x 4 time lanes.
-__global__ void __launch_bounds__(256)
-w2v_groupnorm_gelu_kernel(float* __restrict__ x, int T, int C, const float* __restrict__ gamma, const float* __restrict__ beta)
-{
-    __shared__ double s1[4][64], s2[4][64];
-    __shared__ float mean_s[64], rstd_s[64];
-    const int c = blockIdx.x * 64 + (threadIdx.x & 63), lane_t = threadIdx.x >> 6;
-    float* base = x + (size_t)blockIdx.y * T * C + c;
-    double a = 0.0, b = 0.0;
-    for (int t = lane_t; t < T; t += 4) { const double v = base[(size_t)t * C]; a += v; b += v * v; }
-    s1[lane_t][threadIdx.x & 63] = a; s2[lane_t][threadIdx.x & 63] = b;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        const double sum = s1[0][threadIdx.x] + s1[1][threadIdx.x] + s1[2][threadIdx.x] + s1[3][threadIdx.x];
-        const double sq = s2[0][threadIdx.x] + s2[1][threadIdx.x] + s2[2][threadIdx.x] + s2[3][threadIdx.x];
-        const double m = sum / T, var = sq / T - m * m;
-        mean_s[threadIdx.x] = (float)m; rstd_s[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
-    }
-    __syncthreads();
-    const float m = mean_s[threadIdx.x & 63], r = rstd_s[threadIdx.x & 63], g = gamma[c], be = beta[c];
-    for (int t = lane_t; t < T; t += 4) {
-        const float v = (base[(size_t)t * C] - m) * r * g + be;
-        base[(size_t)t * C] = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-    }
 }
 
 // ---- conv 0 of the group-norm feature encoder, fused: Conv1d(1, 512, k = 10, stride 5) -> GroupNorm(512, 512)
@@ -156,40 +129,48 @@ w2v_conv0_apply_kernel(const float* __restrict__ xn, int L, int T1, int P1, cons
     }
 }
 
-// im2col of the grouped positional convolution (k = 128, padding 64, groups of 48 channels):
-// a[(b*T + t)][tap*cg + ci] = h[b][t + tap - 64][g*cg + ci] (zero outside the sequence).  8 channels per thread.
+// Operand layout of the grouped positional convolution (k = 128, padding 64, 16 groups of cg channels; the
+// even kernel's extra last output is dropped, Wav2Vec2SamePadLayer): per group a zero-padded fp16 sequence
+//   a[g][b*Pp + p][ci] = h[b][p - 64][g*cg + ci]   (0 outside the clip),  Pp = T + 128,
+// so that output (b, t) of group g is the contiguous run of 128*cg values starting at row b*Pp + t: a GEMM
+// operand with row stride cg (overlapping rows) - no im2col copy.  Rows t >= T of every clip are dead.
+// slab = rows per group (B*Pp + 128: the last dead rows read past the last clip).  8 channels per thread.
 __global__ void __launch_bounds__(256)
-w2v_posconv_im2col_kernel(const float* __restrict__ h, int T, int d, int cg, int g, int k, long long n_rows, __half* __restrict__ a)
+w2v_posconv_layout_kernel(const float* __restrict__ h, int T, int d, int cg, int Pp, long long B, long long slab,
+                          __half* __restrict__ a)
 {
-    const int vecs = k * cg / 8, per_tap = cg / 8;
-    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n_rows * vecs; e += (long long)gridDim.x * 256) {
-        const long long row = e / vecs;
-        const int v = (int)(e - row * vecs);
-        const int tap = v / per_tap, ci = (v - tap * per_tap) * 8;
-        const long long b = row / T;
-        const int t = (int)(row - b * T) + tap - k / 2;
+    const int per_row = cg / 8;
+    const long long per_group = slab * per_row;
+    for (long long e = blockIdx.x * 256LL + threadIdx.x; e < 16 * per_group; e += (long long)gridDim.x * 256) {
+        const int g = (int)(e / per_group);
+        const long long q = e - g * per_group;
+        const long long row = q / per_row;
+        const int ci = (int)(q - row * per_row) * 8;
+        const long long b = row / Pp;
+        const int t = (int)(row - b * Pp) - 64;
         uint4 o = make_uint4(0, 0, 0, 0);
-        if (t >= 0 && t < T) {
+        if (b < B && t >= 0 && t < T) {
             const float* src = h + ((b * T + t) * (long long)d + g * cg + ci);
-            const float4 p = *reinterpret_cast<const float4*>(src), q = *reinterpret_cast<const float4*>(src + 4);
+            const float4 p = *reinterpret_cast<const float4*>(src), r = *reinterpret_cast<const float4*>(src + 4);
             const __half2 h0 = __floats2half2_rn(p.x, p.y), h1 = __floats2half2_rn(p.z, p.w);
-            const __half2 h2 = __floats2half2_rn(q.x, q.y), h3 = __floats2half2_rn(q.z, q.w);
+            const __half2 h2 = __floats2half2_rn(r.x, r.y), h3 = __floats2half2_rn(r.z, r.w);
             o = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
                            *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
         }
-        *reinterpret_cast<uint4*>(a + row * (long long)(k * cg) + v * 8) = o;
+        *reinterpret_cast<uint4*>(a + (g * slab + row) * cg + ci) = o;
     }
 }
 
-// out[row][col0 + c] = h[row][col0 + c] + y[row][c],  c < cg     (hidden + GELU(pos_conv(hidden)), one group)
+// out[b*T + t][col0 + c] = h[b*T + t][col0 + c] + y[b*Pp + t][c],  c < cg   (hidden + GELU(pos_conv(hidden)), one group)
 __global__ void __launch_bounds__(256)
-w2v_add_cols_kernel(const float* __restrict__ h, const float* __restrict__ y, long long n_rows, int d, int col0, int cg,
-                    float* __restrict__ out)
+w2v_add_cols_kernel(const float* __restrict__ h, const float* __restrict__ y, long long n_rows, int T, int Pp, int d, int col0,
+                    int cg, float* __restrict__ out)
 {
     for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n_rows * cg; e += (long long)gridDim.x * 256) {
         const long long row = e / cg;
         const int c = (int)(e - row * cg);
-        out[row * d + col0 + c] = h[row * d + col0 + c] + y[e];
+        const long long b = row / T;
+        out[row * d + col0 + c] = h[row * d + col0 + c] + y[(b * Pp + (row - b * T)) * cg + c];
     }
 }
 
