@@ -21,8 +21,11 @@ from . import _native, dist
 class EvalSetFAD:
     """FAD of equal-length PCM16 clips against fixed baseline statistics.
 
-    ``model``: "vggish" (16 kHz, 128-d, one row per 0.96 s) or "clap-laion-audio" (48 kHz, 512-d,
-    one row per started second); the engine must already hold that model's weights.
+    ``model`` (the engine must already hold that model's weights):
+    "vggish" (16 kHz, 128-d, one row per 0.96 s); "clap-laion-audio" / "clap-laion-music" (48 kHz, 512-d,
+    one row per started second); "encodec-emb" (24 kHz, 128-d, one row per 320 samples); "whisper-<size>"
+    (16 kHz, two rows per clip); "w2v2-", "hubert-", "wavlm-", "MERT-" names (16 / 24 kHz, 768- or 1024-d,
+    one row per 20 ms; a trailing "-<k>" selects hidden_states[k], default the last layer).
     """
 
     def __init__(self, engine: _native.Engine, mu_base: torch.Tensor, cov_base: torch.Tensor,
@@ -35,6 +38,7 @@ class EvalSetFAD:
         self.cov_base = cov_base.to(self.dev, torch.float64).contiguous()
         self.clip_samples = int(clip_samples)
         self.clips_per_chunk = int(clips_per_chunk)
+        self.w2v_layer = None
         if model == "vggish":
             self.d = 128
             self.rows_per_clip = int(_native.lib().fad_vggish_num_examples(self.clip_samples))
@@ -71,7 +75,7 @@ class EvalSetFAD:
             if self.model == "vggish":
                 ex, _ = self.eng.vggish_plan(off)
                 self._plans[n_clips] = (torch.from_numpy(ex).to(self.dev),)
-            elif self.model == "encodec-emb" or hasattr(self, "w2v_layer"):
+            elif self.model == "encodec-emb" or self.w2v_layer is not None:
                 self._plans[n_clips] = ()
             elif self.model.startswith("whisper-"):
                 self._plans[n_clips] = (torch.from_numpy(off[:-1].copy()).to(self.dev),
@@ -86,7 +90,7 @@ class EvalSetFAD:
         flat = pcm_dev.reshape(-1)
         if self.model == "vggish":
             return self.eng.vggish_forward(flat, plan[0], out)
-        if hasattr(self, "w2v_layer"):
+        if self.w2v_layer is not None:
             emb = self.eng.w2v_forward(pcm_dev.contiguous(), self.w2v_layer).reshape(-1, self.d)
         elif self.model == "encodec-emb":
             emb = self.eng.encodec_forward(pcm_dev.contiguous()).reshape(-1, self.d)
