@@ -7,6 +7,8 @@ error behaviour; the arithmetic runs on the B200 through the C ABI.
 """
 from __future__ import annotations
 
+import hashlib
+import json
 import logging
 import os
 import traceback
@@ -222,8 +224,13 @@ class FrechetAudioDistance:
         cache_dir = path / "stats" / self.ml.name
         emb_dir = path / "embeddings" / self.ml.name
         if cache_dir.exists():
-            log.info(f"Embedding statistics is already cached for {path}, loading...")
-            return np.load(cache_dir / "mu.npy"), np.load(cache_dir / "cov.npy")
+            # The reference trusts this cache forever (fad.py:279-283): adding or re-embedding files silently
+            # keeps the old statistics.  Caches written here carry a fingerprint of the embedding files they
+            # were computed from; a cache without one (written by the reference) is loaded as the reference does.
+            if self._stats_cache_is_current(cache_dir, emb_dir):
+                log.info(f"Embedding statistics is already cached for {path}, loading...")
+                return np.load(cache_dir / "mu.npy"), np.load(cache_dir / "cov.npy")
+            log.info(f"Embedding files of {path} changed since the statistics were cached, recomputing...")
 
         if not path.is_dir():
             log.error(f"The dataset you want to use ({path}) is not a directory nor a file.")
@@ -236,7 +243,27 @@ class FrechetAudioDistance:
         cache_dir.mkdir(parents=True, exist_ok=True)
         np.save(cache_dir / "mu.npy", mu)
         np.save(cache_dir / "cov.npy", cov)
+        (cache_dir / "source.json").write_text(json.dumps(self._embedding_fingerprint(emb_dir)))
         return mu, cov
+
+    @staticmethod
+    def _embedding_fingerprint(emb_dir: Path) -> dict:
+        """What the cached statistics depend on: the embedding files' names, sizes and newest mtime."""
+        files = sorted(emb_dir.glob("*.npy"))
+        stats = [f.stat() for f in files]
+        names = hashlib.sha1("\n".join(f.name for f in files).encode()).hexdigest()
+        return {"files": len(files), "bytes": int(sum(st.st_size for st in stats)), "names_sha1": names,
+                "newest_mtime_ns": int(max((st.st_mtime_ns for st in stats), default=0))}
+
+    @classmethod
+    def _stats_cache_is_current(cls, cache_dir: Path, emb_dir: Path) -> bool:
+        src = cache_dir / "source.json"
+        if not src.exists() or not emb_dir.is_dir():       # reference-written cache, or statistics shipped without embeddings
+            return True
+        try:
+            return json.loads(src.read_text()) == cls._embedding_fingerprint(emb_dir)
+        except (OSError, ValueError):
+            return False
 
     # ------------------------------------------------------------------ scores
     def score(self, baseline: PathLike, eval: PathLike):

@@ -172,3 +172,42 @@ def test_registry_matches_the_reference(golden_dir):
     assert got == want
     unbuilt = [m.name for m in fk.get_all_models() if isinstance(m, fk.UnbuiltModel)]
     assert unbuilt == ["clap-2023"]                       # every other embedder has an sm_100a forward pass
+
+
+def test_stats_cache_is_invalidated_when_embeddings_change(tmp_path, monkeypatch):
+    """SURVEY.md section 8 (f)3: the reference reuses stats/<model>/{mu,cov}.npy forever (fad.py:279-283);
+    caches written here are recomputed when the embedding files they came from change, while a cache
+    without a fingerprint (written by the reference) is still loaded as is."""
+    import numpy as np
+    from fadtk_b200 import fad as fad_mod
+
+    def cpu_stats(files):
+        e = np.concatenate([np.load(f) for f in files]).astype(np.float64)
+        return e.mean(0), np.cov(e, rowvar=False)
+
+    monkeypatch.setattr(fad_mod, "calculate_embd_statistics_online", cpu_stats)
+
+    class _ML:
+        name = "vggish"
+
+    f = fad_mod.FrechetAudioDistance.__new__(fad_mod.FrechetAudioDistance)
+    f.ml = _ML()
+    emb = tmp_path / "embeddings" / "vggish"
+    emb.mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    np.save(emb / "a.npy", rng.standard_normal((8, 4)).astype(np.float16))
+    np.save(emb / "b.npy", rng.standard_normal((8, 4)).astype(np.float16))
+    mu1, cov1 = f.load_stats(tmp_path)
+    assert (tmp_path / "stats" / "vggish" / "source.json").exists()
+    mu1b, _ = f.load_stats(tmp_path)                        # unchanged directory: served from the cache
+    np.testing.assert_array_equal(mu1, mu1b)
+
+    np.save(emb / "c.npy", (5 + rng.standard_normal((8, 4))).astype(np.float16))
+    mu2, cov2 = f.load_stats(tmp_path)                      # a new file: recomputed
+    assert not np.allclose(mu1, mu2)
+    np.testing.assert_allclose(mu2, cpu_stats(sorted(emb.glob("*.npy")))[0])
+
+    (tmp_path / "stats" / "vggish" / "source.json").unlink()   # a reference-written cache has no fingerprint
+    np.save(emb / "d.npy", (9 + rng.standard_normal((8, 4))).astype(np.float16))
+    mu3, _ = f.load_stats(tmp_path)
+    np.testing.assert_array_equal(mu2, mu3)                 # trusted like the reference does
