@@ -1,0 +1,147 @@
+"""libfadtk_io.so (include/fadtk_b200_io.h): batched WAV / .npy I/O against Python's wave module and numpy -
+the formats of the reference's convert cache (fad.py:160), load_wav (model_loader.py:63-70) and embedding
+cache (fad.py:200-209).  Host only: runs without a GPU."""
+import io
+import re
+import struct
+import wave
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from fadtk_b200 import _io_native as ion
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _write_wave(path, pcm, sr, channels=1):
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(channels)
+        w.setsampwidth(2)
+        w.setframerate(sr)
+        w.writeframes(np.ascontiguousarray(pcm, dtype="<i2").tobytes())
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "fadtk_b200_io.h").read_text()
+    declared = set(re.findall(r"\b(fad_io_\w+)\s*\(", header))
+    assert declared == set(ion.SIGNATURES)
+    lib = ion.lib()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.fad_io_version() == 1
+
+
+def test_wav_probe_and_read_match_the_wave_module(tmp_path):
+    rng = np.random.default_rng(0)
+    specs = [(16000, 1, 16000), (48000, 2, 12345), (24000, 1, 1), (44100, 3, 777), (16000, 1, 0)]
+    paths, want = [], []
+    for i, (sr, ch, n) in enumerate(specs):
+        pcm = rng.integers(-32768, 32768, size=n * ch, dtype=np.int16)
+        p = tmp_path / f"clip {i} ü.wav"                      # spaces / non-ASCII in the path
+        _write_wave(p, pcm, sr, ch)
+        paths.append(p)
+        want.append(pcm)
+    sr, ch, fr, st = ion.wav_probe(paths, threads=3)
+    assert st.tolist() == [0] * len(specs)
+    assert list(zip(sr.tolist(), ch.tolist(), fr.tolist())) == specs
+    out = np.full(int((fr * ch).sum()) + 5, 99, dtype=np.int16)
+    off, st = ion.wav_read(paths, fr, ch, out, threads=2)
+    assert st.tolist() == [0] * len(specs)
+    for i, pcm in enumerate(want):
+        np.testing.assert_array_equal(out[off[i]:off[i + 1]], pcm)
+    assert (out[off[-1]:] == 99).all()                        # nothing written past the last clip
+
+
+def test_wav_chunks_extensible_header_and_errors(tmp_path):
+    pcm = np.arange(-50, 50, dtype=np.int16)
+    # LIST chunk before fmt, WAVE_FORMAT_EXTENSIBLE fmt, odd-sized chunk (padded), data size 0xFFFFFFFF (streamed writer)
+    fmt = struct.pack("<HHIIHHHHIH14s", 0xFFFE, 1, 22050, 44100, 2, 16, 22, 16, 4, 1, b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71")
+    body = b"WAVE" + b"LIST" + struct.pack("<I", 3) + b"abc\x00" + b"fmt " + struct.pack("<I", len(fmt)) + fmt \
+        + b"data" + struct.pack("<I", 0xFFFFFFFF) + pcm.tobytes()
+    ext = tmp_path / "ext.wav"
+    ext.write_bytes(b"RIFF" + struct.pack("<I", 4 + len(body)) + body)
+    f32 = tmp_path / "float.wav"                              # IEEE float WAV: valid but not PCM16
+    fmt3 = struct.pack("<HHIIHH", 3, 1, 16000, 64000, 4, 32)
+    body3 = b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt3 + b"data" + struct.pack("<I", 8) + b"\x00" * 8
+    f32.write_bytes(b"RIFF" + struct.pack("<I", len(body3)) + body3)
+    junk = tmp_path / "junk.wav"
+    junk.write_bytes(b"not a riff file at all")
+    missing = tmp_path / "missing.wav"
+    sr, ch, fr, st = ion.wav_probe([ext, f32, junk, missing])
+    assert st.tolist() == [ion.OK, ion.EUNSUPPORTED, ion.EFORMAT, ion.EOPEN]
+    assert (sr[0], ch[0], fr[0]) == (22050, 1, 100)
+    out = np.zeros(100, dtype=np.int16)
+    _, st = ion.wav_read([ext], fr[:1], ch[:1], out)
+    assert st.tolist() == [0]
+    np.testing.assert_array_equal(out, pcm)
+    # a file that shrank between probe and read is reported, not read past
+    _write_wave(ext, pcm[:10], 22050)
+    _, st = ion.wav_read([ext], fr[:1], ch[:1], out)
+    assert st.tolist() == [ion.ESHORT]
+
+
+def test_wav_write_is_readable_by_the_wave_module(tmp_path):
+    rng = np.random.default_rng(1)
+    src = rng.integers(-32768, 32768, size=5000, dtype=np.int16)
+    offsets, frames = np.array([0, 1000, 1000, 4000]), np.array([1000, 0, 3000, 1000])
+    paths = [tmp_path / f"o{i}.wav" for i in range(4)]
+    st = ion.wav_write(paths, src, offsets, frames, 24000, threads=4)
+    assert st.tolist() == [0, 0, 0, 0]
+    for p, o, n in zip(paths, offsets, frames):
+        with wave.open(str(p), "rb") as w:
+            assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 24000, n)
+            np.testing.assert_array_equal(np.frombuffer(w.readframes(n), dtype="<i2"), src[o:o + n])
+    st = ion.wav_write([tmp_path / "no_such_dir" / "x.wav"], src, [0], [10], 24000)
+    assert st.tolist() == [ion.EOPEN]
+
+
+def test_npy_files_are_byte_identical_to_numpy_save(tmp_path):
+    rng = np.random.default_rng(2)
+    emb = rng.standard_normal((1500, 128)).astype(np.float16)
+    rows = np.array([10, 0, 750, 1, 739])
+    off = np.concatenate([[0], np.cumsum(rows)])
+    paths = [tmp_path / f"e{i}.npy" for i in range(len(rows))]
+    st = ion.npy_write_f16(paths, emb, off[:-1], rows, threads=2)
+    assert st.tolist() == [0] * len(rows)
+    for p, o, n in zip(paths, off, rows):
+        buf = io.BytesIO()
+        np.save(buf, emb[o:o + n])
+        assert p.read_bytes() == buf.getvalue()
+    # header widths around the 64-byte alignment boundary
+    wide = rng.standard_normal((3, 1280)).astype(np.float16)
+    for r, d in ((3, 1280), (1, 1), (99999, 2)):
+        a = np.resize(wide, (r, d)).astype(np.float16)
+        p = tmp_path / f"w{r}_{d}.npy"
+        assert ion.npy_write_f16([p], a, [0], [r]).tolist() == [0]
+        buf = io.BytesIO()
+        np.save(buf, a)
+        assert p.read_bytes() == buf.getvalue()
+
+
+def test_npy_probe_and_ragged_read(tmp_path):
+    rng = np.random.default_rng(3)
+    arrays = [rng.standard_normal((n, 64)).astype(np.float16) for n in (5, 1, 300, 0, 17)]
+    paths = []
+    for i, a in enumerate(arrays):
+        p = tmp_path / f"a{i}.npy"
+        np.save(p, a)
+        paths.append(p)
+    odd = {"f32": rng.standard_normal((4, 64)).astype(np.float32), "vec": rng.standard_normal(64).astype(np.float16),
+           "fortran": np.asfortranarray(rng.standard_normal((4, 64)).astype(np.float16)), "int": np.arange(6).reshape(2, 3)}
+    for k, a in odd.items():
+        np.save(tmp_path / f"{k}.npy", a)
+    rows, cols, nd, dt, st = ion.npy_probe(paths + [tmp_path / f"{k}.npy" for k in odd] + [tmp_path / "nope.npy"])
+    assert st.tolist() == [0] * 5 + [ion.OK, ion.OK, ion.EUNSUPPORTED, ion.EUNSUPPORTED, ion.EOPEN]
+    assert rows[:7].tolist() == [5, 1, 300, 0, 17, 4, 64] and dt[:7].tolist() == [2] * 5 + [4, 2] and nd[:7].tolist() == [2] * 6 + [1]
+    out, off = ion.load_embedding_files(paths, threads=3)
+    np.testing.assert_array_equal(out, np.concatenate(arrays))
+    assert off.tolist() == [0, 5, 6, 306, 306, 323]
+    # a float32 cache among fp16 ones: same result as np.load + np.concatenate
+    mixed, off = ion.load_embedding_files(paths + [tmp_path / "f32.npy"])
+    ref = np.concatenate(arrays + [odd["f32"]])
+    assert mixed.dtype == ref.dtype
+    np.testing.assert_array_equal(mixed, ref)
+    with pytest.raises(ValueError):
+        ion.load_embedding_files([paths[0], tmp_path / "vec.npy"])
