@@ -1,26 +1,35 @@
 """Batch embedding driver (mirror of fadtk/fad_batch.py:15-48).
 
 The reference shards the file list over ``workers`` spawn processes, each loading its own copy
-of the model on cuda:0 and looping file by file at batch size one.  Here one process owns one
-GPU: ``workers`` host threads decode / convert audio and write ``.npy`` files, while clips are
-packed into large batches for the sm_100a forward.  Under torchrun (one rank per GPU) the file
-list is sharded across ranks the way the reference shards it across processes.
+of the model on cuda:0 and looping file by file at batch size one - three filesystem round trips
+per clip through Python.  Here one process owns one GPU and the host
+side is batched too: the PCM16 payloads of a whole chunk of files are read by native threads
+straight into ONE pinned buffer (libfadtk_io.so, include/fadtk_b200_io.h), packed into large
+batches for the sm_100a forward, and the convert cache and the fp16 ``.npy`` embedding cache
+are written back by the same native threads - byte-compatible with what the reference writes.
+Files the native reader cannot take as they are (other sample rates, multi-channel, non-PCM16,
+other containers) go through FrechetAudioDistance.convert_audio (GPU resampler) on ``workers``
+host threads.  Under torchrun (one rank per GPU) the file list is sharded across ranks the way
+the reference shards it across processes.
 """
 from __future__ import annotations
 
+import os
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Union
 
 import numpy as np
+import torch
 
-from . import dist
+from . import _io_native, dist
 from .fad import FrechetAudioDistance, log
 from .model_loader import ModelLoader
-from .utils import get_cache_embedding_path
 
 # clips per GPU launch sequence: bounded by audio seconds so ragged sets keep batches even
 _BATCH_AUDIO_SECONDS = 4096.0
+# files decoded ahead per round of host I/O (bounds the pinned staging buffer: 2048 x 10 s x 48 kHz = 2 GB)
+_CHUNK_FILES = 2048
 
 
 def _batches(files, lengths_s, limit_s):
@@ -35,6 +44,99 @@ def _batches(files, lengths_s, limit_s):
         yield cur
 
 
+def _derived_paths(files, model: str, sr: int):
+    """(embedding cache path, convert cache path) of every file as plain strings - the same names as
+    utils.get_cache_embedding_path / FrechetAudioDistance._converted_path, without a dozen pathlib objects per file."""
+    emb, conv = [], []
+    for f in files:
+        parent, name = os.path.split(os.fspath(f))
+        stem = os.path.splitext(name)[0]
+        emb.append(os.path.join(parent, "embeddings", model, stem + ".npy"))
+        conv.append(os.path.join(parent, "convert", str(sr), stem + ".wav"))
+    return emb, conv
+
+
+def _names_in(directory) -> set:
+    try:
+        return set(os.listdir(directory))
+    except OSError:
+        return set()
+
+
+_staging = None
+
+
+def _host_buffer(n_samples: int) -> np.ndarray:
+    """int16 staging buffer, reused from chunk to chunk (every clip of a chunk has been consumed by the forward
+    before the next chunk is read); pinned when a GPU is present so the H2D copy is a straight DMA."""
+    global _staging
+    if _staging is None or _staging.numel() < n_samples:
+        _staging = torch.empty(max(1, n_samples), dtype=torch.int16, pin_memory=torch.cuda.is_available())
+    return _staging.numpy()[:max(1, n_samples)]
+
+
+def _read_clips(part, fad: FrechetAudioDistance, ml: ModelLoader, workers: int, pool: ThreadPoolExecutor):
+    """int16 mono clips at ml.sr for every file of ``part`` (in order), filling the convert cache on the way."""
+    _, conv = _derived_paths(part, ml.name, ml.sr)
+    have = {d: _names_in(d) for d in {os.path.dirname(c) for c in conv}}
+    cached = np.array([os.path.basename(c) in have[os.path.dirname(c)] for c in conv], dtype=bool)
+    # candidates for the native reader: the convert cache when it exists, else a .wav source
+    src = [c if ok else os.fspath(f) for f, c, ok in zip(part, conv, cached)]
+    is_wav = np.array([s.lower().endswith(".wav") for s in src], dtype=bool)
+    sr, ch, fr, st = _io_native.wav_probe(src, workers)
+    fast = is_wav & (st == _io_native.OK) & (ch == 1) & (sr == ml.sr)
+    clips = [None] * len(part)
+    idx = np.nonzero(fast)[0]
+    if len(idx):
+        buf = _host_buffer(int(fr[idx].sum()))
+        off, st2 = _io_native.wav_read([src[i] for i in idx], fr[idx], ch[idx], buf, threads=workers)
+        ok = st2 == _io_native.OK
+        for j, i in enumerate(idx):
+            if ok[j]:
+                clips[i] = buf[off[j]:off[j + 1]]
+        # The reference always leaves <dir>/convert/<sr>/<stem>.wav behind (fad.py:143-160).  A source that already
+        # is mono PCM16 at the model rate IS that file: hard-link it (no second copy of the payload on disk, no
+        # write traffic); where links are not possible (other filesystem, no permission) write it out.
+        new = [j for j, i in enumerate(idx) if ok[j] and not cached[i]]
+        if new:
+            for d in {os.path.dirname(conv[idx[j]]) for j in new}:
+                os.makedirs(d, exist_ok=True)
+            copy = []
+            for j in new:
+                try:
+                    os.link(src[idx[j]], conv[idx[j]])
+                except OSError:
+                    copy.append(j)
+            if copy:
+                stw = _io_native.wav_write([conv[idx[j]] for j in copy], buf, off[copy], fr[idx[copy]], ml.sr, workers)
+                for j in np.nonzero(stw != _io_native.OK)[0]:
+                    raise OSError(f"cannot write {conv[idx[copy[j]]]} (status {int(stw[j])})")
+    rest = [i for i in range(len(part)) if clips[i] is None]
+    if rest:                                                   # resample / mix down / decode: per file
+        for i, pcm in zip(rest, pool.map(fad.convert_audio, [part[i] for i in rest])):
+            clips[i] = pcm
+    return clips
+
+
+def _save_embeddings(ml: ModelLoader, group, embs, workers: int):
+    """``<dir>/embeddings/<model>/<stem>.npy`` for every file of ``group`` (fp16 [n_frames, d], as np.save writes it)."""
+    paths, _ = _derived_paths(group, ml.name, ml.sr)
+    for d in {os.path.dirname(p) for p in paths}:
+        os.makedirs(d, exist_ok=True)
+    native = [i for i, e in enumerate(embs) if e.dtype == np.float16 and e.ndim == 2 and e.shape[1] == embs[0].shape[1]]
+    if len(native) == len(embs):
+        rows = np.array([e.shape[0] for e in embs], dtype=np.int64)
+        off = np.zeros(len(embs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum(rows)
+        flat = np.concatenate(embs) if len(embs) > 1 else np.ascontiguousarray(embs[0])
+        st = _io_native.npy_write_f16(paths, flat, off[:-1], rows, workers)
+        for i in np.nonzero(st != _io_native.OK)[0]:
+            raise OSError(f"cannot write {paths[i]} (status {int(st[i])})")
+    else:                                                      # a plugin returning something else: numpy decides the format
+        for p, e in zip(paths, embs):
+            np.save(p, e)
+
+
 def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, workers: int = 8, **kwargs):
     """Get embeddings for all audio files in a directory (or list) and cache them as
     ``<dir>/embeddings/<model>/<stem>.npy`` (fp16 [n_frames, d]), skipping files already done.
@@ -44,7 +146,10 @@ def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, 
     if isinstance(files, (str, Path)):
         files = list(Path(files).glob('*.*'))
 
-    files = [Path(f) for f in files if not get_cache_embedding_path(ml.name, f).exists()]
+    files = [Path(f) for f in files]
+    emb_paths, _ = _derived_paths(files, ml.name, ml.sr)
+    done = {d: _names_in(d) for d in {os.path.dirname(p) for p in emb_paths}}
+    files = [f for f, p in zip(files, emb_paths) if os.path.basename(p) not in done[os.path.dirname(p)]]
     if len(files) == 0:
         log.info("All files already have embeddings, skipping.")
         return
@@ -56,26 +161,18 @@ def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, 
     fad = FrechetAudioDistance(ml, **kwargs)
     workers = max(1, int(workers))
 
-    def save(item):
-        f, embd = item
-        cache = get_cache_embedding_path(ml.name, f)
-        cache.parent.mkdir(parents=True, exist_ok=True)
-        np.save(cache, embd)
-
     with ThreadPoolExecutor(workers) as pool:
-        # decode ahead in chunks so host I/O overlaps the GPU
-        chunk = 2048
-        pending = None
-        for s in range(0, len(files), chunk):
-            part = files[s:s + chunk]
-            clips = list(pool.map(fad.convert_audio, part))
+        writer = None                                          # embedding writes of batch k overlap the forward of batch k+1
+        for s in range(0, len(files), _CHUNK_FILES):
+            part = files[s:s + _CHUNK_FILES]
+            clips = _read_clips(part, fad, ml, workers, pool)
             secs = [len(c) / ml.sr for c in clips]
             by_file = dict(zip(part, clips))
             for group in _batches(part, secs, _BATCH_AUDIO_SECONDS):
                 embs = ml.embed_pcm_batch([by_file[f] for f in group])
-                if pending is not None:
-                    list(pending)
-                pending = pool.map(save, list(zip(group, embs)))
-        if pending is not None:
-            list(pending)
+                if writer is not None:
+                    writer.result()
+                writer = pool.submit(_save_embeddings, ml, group, embs, workers)
+        if writer is not None:
+            writer.result()
     dist.barrier()

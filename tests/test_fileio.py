@@ -145,3 +145,78 @@ def test_npy_probe_and_ragged_read(tmp_path):
     np.testing.assert_array_equal(mixed, ref)
     with pytest.raises(ValueError):
         ion.load_embedding_files([paths[0], tmp_path / "vec.npy"])
+
+
+def test_batch_driver_paths_match_the_reference_layout(tmp_path):
+    """fad_batch derives cache paths with string operations; they must be the names utils.get_cache_embedding_path
+    (fadtk/utils.py:60-68) and FrechetAudioDistance._converted_path (fad.py:143) produce."""
+    from fadtk_b200 import fad_batch
+    from fadtk_b200.fad import FrechetAudioDistance
+    from fadtk_b200.utils import get_cache_embedding_path
+
+    class _ML:
+        name, sr = "clap-laion-audio", 48000
+
+    f = FrechetAudioDistance.__new__(FrechetAudioDistance)
+    f.ml = _ML()
+    files = [tmp_path / "a.wav", tmp_path / "x y" / "b.c.flac", tmp_path / "noext", Path("rel") / "d.WAV", Path("e.mp3")]
+    emb, conv = fad_batch._derived_paths(files, _ML.name, _ML.sr)
+    assert [Path(p) for p in emb] == [get_cache_embedding_path(_ML.name, x) for x in files]
+    assert [Path(p) for p in conv] == [f._converted_path(x) for x in files]
+
+
+def test_cache_embedding_files_with_a_stub_model(tmp_path):
+    """The whole host flow without a GPU: native batch read -> stub embedder -> convert cache + .npy cache."""
+    from fadtk_b200 import fad_batch, synth
+    from fadtk_b200.model_loader import ModelLoader
+
+    class Stub(ModelLoader):
+        def __init__(self):
+            super().__init__("stub", 4, 16000)
+
+        def load_model(self):
+            pass
+
+        def _get_embedding(self, audio):
+            raise NotImplementedError
+
+        def embed_pcm_batch(self, clips):                     # [n, 4]: n = seconds, features = simple statistics
+            return [np.stack([[c[:16000 * (k + 1)].astype(np.float64).mean(), c.min(), c.max(), len(c)] for k in range(max(1, len(c) // 16000))]).astype(np.float16)
+                    for c in clips]
+
+    rng = np.random.default_rng(5)
+    clips = {f"c{i}.wav": rng.integers(-3000, 3000, size=16000 * (1 + i % 3), dtype=np.int16) for i in range(7)}
+    for name, pcm in clips.items():
+        synth.write_wav(tmp_path / name, pcm, 16000)
+    stereo = rng.integers(-3000, 3000, size=(16000, 2), dtype=np.int16)   # not mono: must NOT take the native fast path
+    _write_wave(tmp_path / "stereo.wav", stereo, 16000, 2)
+    ml = Stub()
+    calls = []
+
+    class _FAD(fad_batch.FrechetAudioDistance):
+        def convert_audio(self, f):
+            calls.append(Path(f).name)
+            return np.zeros(16000, dtype=np.int16)
+
+    orig = fad_batch.FrechetAudioDistance
+    fad_batch.FrechetAudioDistance = _FAD
+    try:
+        fad_batch.cache_embedding_files(tmp_path, ml, workers=3, load_model=False)
+        assert calls == ["stereo.wav"]
+        for name, pcm in clips.items():
+            e = np.load(tmp_path / "embeddings" / "stub" / (Path(name).stem + ".npy"))
+            np.testing.assert_array_equal(e, ml.embed_pcm_batch([pcm])[0])
+            with wave.open(str(tmp_path / "convert" / "16000" / name), "rb") as w:
+                np.testing.assert_array_equal(np.frombuffer(w.readframes(w.getnframes()), dtype="<i2"), pcm)
+        calls.clear()
+        fad_batch.cache_embedding_files(tmp_path, ml, workers=3, load_model=False)       # everything cached: no work
+        assert calls == []
+        # new file next to a populated convert cache; one embedding removed -> read back from the convert cache
+        synth.write_wav(tmp_path / "late.wav", clips["c1.wav"], 16000)
+        (tmp_path / "embeddings" / "stub" / "c2.npy").unlink()
+        (tmp_path / "c2.wav").unlink()
+        fad_batch.cache_embedding_files([tmp_path / "late.wav", tmp_path / "c2.wav"], ml, workers=2, load_model=False)
+        np.testing.assert_array_equal(np.load(tmp_path / "embeddings" / "stub" / "c2.npy"), ml.embed_pcm_batch([clips["c2.wav"]])[0])
+        assert (tmp_path / "embeddings" / "stub" / "late.npy").exists()
+    finally:
+        fad_batch.FrechetAudioDistance = orig
