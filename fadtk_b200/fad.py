@@ -188,6 +188,12 @@ class FrechetAudioDistance:
     def _load_embeddings(self, files: list[Path], max_count: int = -1, concat: bool = True):
         if len(files) == 0:
             raise ValueError("No files provided")
+        if max_count == -1 and concat:
+            from . import _io_native
+            caches = [get_cache_embedding_path(self.ml.name, f) for f in files]
+            for c in caches:
+                assert c.exists(), f"Embedding file {c} does not exist, please run cache_embedding_file first."
+            return _io_native.load_embedding_files(caches, self.audio_load_worker)[0]
         if max_count == -1:
             with ThreadPoolExecutor(max(1, self.audio_load_worker)) as ex:
                 embd_lst = list(ex.map(self.read_embedding_file, files))
@@ -282,7 +288,8 @@ class FrechetAudioDistance:
         log.info(f"Calculating FAD-inf for {self.ml.name}...")
         mu_base, cov_base = self.load_stats(baseline)
         if all([Path(f).suffix == '.npy' for f in eval_files]):
-            embeds = np.concatenate([np.load(f) for f in eval_files], axis=0)
+            from . import _io_native
+            embeds, _ = _io_native.load_embedding_files(eval_files, self.audio_load_worker)
         else:
             embeds = self._load_embeddings(eval_files, concat=True)
 
@@ -357,29 +364,40 @@ class FrechetAudioDistance:
         scores: list = [None] * len(_files)
         # fp16 caches (what the reference writes, model_loader.py:47-48): one ragged batch, every song's
         # statistics and Frechet chain in lock-step on the device (fad_frechet_batched)
-        batch_idx, batch_rows = [], []
-        for i, f in enumerate(_files):
+        # read natively in one pass (libfadtk_io.so) into one pinned buffer; anything else goes file by file
+        from . import _io_native
+        d = len(mu)
+        caches = [get_cache_embedding_path(self.ml.name, f) for f in _files]
+        n_rows, cols, ndim, dt, st = _io_native.npy_probe(caches, self.audio_load_worker)
+        fast = (st == _io_native.OK) & (dt == 2) & (ndim == 2) & (cols == d)
+        batch_idx = [int(i) for i in np.nonzero(fast)[0]]
+        for i in np.nonzero(~fast)[0]:
+            f = _files[i]
             try:
                 embd = self.read_embedding_file(f)
             except Exception as e:
                 traceback.print_exc()
                 _report(f, e)
                 continue
-            if embd.dtype == np.float16 and embd.ndim == 2 and embd.shape[1] == len(mu):
-                batch_idx.append(i)
-                batch_rows.append(np.ascontiguousarray(embd))
-            else:
-                scores[i] = _find_z_helper(f, embd)
+            scores[i] = _find_z_helper(f, embd)
         if batch_idx:
-            offs = np.zeros(len(batch_rows) + 1, dtype=np.int64)
-            offs[1:] = np.cumsum([len(r) for r in batch_rows])
-            flat = torch.from_numpy(np.concatenate(batch_rows)).to(eng.torch_device)
+            rows = n_rows[batch_idx]
+            offs = np.zeros(len(batch_idx) + 1, dtype=np.int64)
+            offs[1:] = np.cumsum(rows)
+            host = torch.empty((max(1, int(offs[-1])), d), dtype=torch.float16, pin_memory=torch.cuda.is_available())
+            _, st = _io_native.npy_read_f16([caches[i] for i in batch_idx], rows, d, host.numpy(), offs, self.audio_load_worker)
+            for k in np.nonzero(st != _io_native.OK)[0]:       # vanished / rewritten since the probe: an empty item, reported below
+                _report(_files[batch_idx[k]], OSError(f"cannot read {caches[batch_idx[k]]} (status {int(st[k])})"))
+                host[offs[k]:offs[k + 1]] = float("nan")
+            flat = host[:int(offs[-1])].to(eng.torch_device, non_blocking=True)
             out = base.frechet_batched(flat, torch.from_numpy(offs).to(eng.torch_device)).cpu().numpy()
             for k, i in enumerate(batch_idx):
-                n_rows, fad_k = int(out[k, 7]), float(out[k, 0])
-                if n_rows < 2:
+                n_k, fad_k = int(out[k, 7]), float(out[k, 0])
+                if st[k] != _io_native.OK:
+                    continue
+                if n_k < 2:
                     _report(_files[i], AssertionError(
-                        f"FAD requires at least two embedding window frames, you have {batch_rows[k].shape}."
+                        f"FAD requires at least two embedding window frames, you have {(int(rows[k]), d)}."
                         " (This probably means that your audio is too short)"))
                 elif not np.isfinite(fad_k):
                     _report(_files[i], ValueError("non-finite covariance statistics (NaN/Inf input)"))

@@ -148,24 +148,53 @@ def calculate_embd_statistics_online(files: list[PathLike]) -> tuple[np.ndarray,
     its one row instead of turning the whole covariance into NaN (utils.py:16).
     """
     assert len(files) > 0, "No files provided"
+    from . import _io_native
+    files = list(files)
     st = None
     m_in, m64, counts = [], [], []
     quirk = True
-    for f in files:
-        a = np.load(f)
+    for s in range(0, len(files), _FILES_PER_READ):
+        # one native batched read per chunk of files (libfadtk_io.so), one Gram accumulation per chunk
+        flat, off = _io_native.load_embedding_files(files[s:s + _FILES_PER_READ])
         if st is None:
-            st = DeviceStatistics(a.shape[-1])
-        st.add(a)
-        quirk = quirk and a.dtype == np.float16
-        with np.errstate(all="ignore"):
-            m_in.append(np.mean(a, axis=0))                 # numpy semantics: fp16 in -> fp16 out
-        m64.append(a.mean(axis=0, dtype=np.float64))
-        counts.append(a.shape[0])
+            st = DeviceStatistics(flat.shape[-1])
+        st.add(flat)
+        quirk = quirk and flat.dtype == np.float16
+        a, b, c = per_file_means(flat, off)
+        m_in.append(a), m64.append(b), counts.append(c)
     mu, cov = st.finalize()
     mu, cov = mu.cpu().numpy(), cov.cpu().numpy()
     if not quirk:
         return mu, cov
-    return mirror_file_mean_rounding(mu, cov, float(sum(counts)), np.stack(m_in), np.stack(m64), counts)
+    counts = np.concatenate(counts)
+    return mirror_file_mean_rounding(mu, cov, float(counts.sum()), np.concatenate(m_in), np.concatenate(m64), counts)
+
+
+_FILES_PER_READ = 2048
+
+
+def per_file_means(flat: np.ndarray, off: np.ndarray):
+    """Per-file means of a ragged concatenation (file i = flat[off[i]:off[i+1]]), empty files dropped:
+    -> (np.mean(file, axis=0) in the array's own dtype - fp16 in, fp16 out, as _process_file computes it
+    (fadtk/utils.py:14) -, the same mean in fp64, row counts).  Files of equal length are reduced together;
+    the result is bit-identical to calling np.mean file by file."""
+    rows = np.diff(off)
+    keep = np.nonzero(rows > 0)[0]
+    m_in = np.empty((len(keep), flat.shape[1]), dtype=flat.dtype)
+    m64 = np.empty((len(keep), flat.shape[1]), dtype=np.float64)
+    pos = {int(i): k for k, i in enumerate(keep)}
+    for r in np.unique(rows[keep]):
+        idx = keep[rows[keep] == r]
+        starts = off[idx]
+        if len(idx) > 1 and np.all(np.diff(starts) == r):         # contiguous run of equal-length files: a plain view
+            block = flat[starts[0]:starts[0] + len(idx) * r].reshape(len(idx), r, -1)
+        else:
+            block = flat[(starts[:, None] + np.arange(r)[None, :]).reshape(-1)].reshape(len(idx), r, -1)
+        k = [pos[int(i)] for i in idx]
+        with np.errstate(all="ignore"):
+            m_in[k] = np.mean(block, axis=1)
+        m64[k] = block.mean(axis=1, dtype=np.float64)
+    return m_in, m64, rows[keep].astype(np.int64)
 
 
 def pack_statistics_numpy(rows: np.ndarray, shift: np.ndarray) -> np.ndarray:

@@ -220,3 +220,25 @@ def test_cache_embedding_files_with_a_stub_model(tmp_path):
         assert (tmp_path / "embeddings" / "stub" / "late.npy").exists()
     finally:
         fad_batch.FrechetAudioDistance = orig
+
+
+def test_per_file_means_equal_numpy_file_by_file():
+    """utils.per_file_means reduces equal-length files together; _process_file (fadtk/utils.py:14) calls np.mean
+    per file on an fp16 array.  The fp16 results must be bit-identical (they feed the mirrored rounding quirk)."""
+    from fadtk_b200.utils import per_file_means
+    rng = np.random.default_rng(7)
+    rows = [750, 750, 3, 750, 0, 1, 3, 10, 10, 10, 1234]
+    arrays = [(rng.standard_normal((r, 96)) * rng.uniform(0.1, 30)).astype(np.float16) for r in rows]
+    flat = np.concatenate(arrays)
+    off = np.concatenate([[0], np.cumsum(rows)])
+    m_in, m64, counts = per_file_means(flat, off)
+    kept = [a for a in arrays if len(a)]
+    assert counts.tolist() == [len(a) for a in kept] and m_in.dtype == np.float16
+    for k, a in enumerate(kept):
+        assert np.array_equal(m_in[k], np.mean(a, axis=0))
+        np.testing.assert_allclose(m64[k], a.mean(axis=0, dtype=np.float64), rtol=1e-14, atol=1e-300)
+    wide = flat.astype(np.float32)
+    m_in32, _, _ = per_file_means(wide, off)
+    assert m_in32.dtype == np.float32
+    for k, a in enumerate(kept):
+        assert np.array_equal(m_in32[k], np.mean(a.astype(np.float32), axis=0))
