@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--clips", type=int, default=4000)
     ap.add_argument("--workers", type=int, default=8)
     ap.add_argument("--dir", default="/tmp/fadtk_host_io")
+    ap.add_argument("--repeats", type=int, default=3)
     args = ap.parse_args()
     root = Path(args.dir) / "set"
     root.mkdir(parents=True, exist_ok=True)
@@ -83,16 +84,23 @@ def main():
         fn()
         return time.perf_counter() - t0
 
-    res = {"clips": args.clips, "workers": args.workers, "cores": os.cpu_count(), "clip_seconds": 10.0, "sample_rate": 16000}
+    res = {"clips": args.clips, "workers": args.workers, "cores": os.cpu_count(), "clip_seconds": 10.0, "sample_rate": 16000,
+           "repeats": args.repeats, "statistic": "median of the repeats (shared disks are noisy); best in *_best"}
+
+    def leg(name, convert, fn):
+        ts = []
+        for _ in range(args.repeats):
+            clean(convert=convert)
+            ts.append(timed(fn))
+        t = float(np.median(ts))
+        res[name] = {"files_per_s": args.clips / t, "audio_s_per_s": audio_s / t, "files_per_s_best": args.clips / min(ts)}
+
+    native = lambda: fad_batch.cache_embedding_files(root, Stub(), workers=args.workers, load_model=False)  # noqa: E731
+    leg("python_per_file", True, lambda: python_flow(files, args.workers))
+    leg("native_first_pass", True, native)
     clean()
-    t = timed(lambda: python_flow(files, args.workers))
-    res["python_per_file"] = {"files_per_s": args.clips / t, "audio_s_per_s": audio_s / t}
-    clean()
-    t = timed(lambda: fad_batch.cache_embedding_files(root, Stub(), workers=args.workers, load_model=False))
-    res["native_first_pass"] = {"files_per_s": args.clips / t, "audio_s_per_s": audio_s / t}
-    clean(convert=False)
-    t = timed(lambda: fad_batch.cache_embedding_files(root, Stub(), workers=args.workers, load_model=False))
-    res["native_convert_cached"] = {"files_per_s": args.clips / t, "audio_s_per_s": audio_s / t}
+    native()                                                   # leaves the convert cache behind for the next leg
+    leg("native_convert_cached", False, native)
 
     # embedding caches of per-song size ([750, 128], encodec-emb) read back for --indiv / statistics
     songs = Path(args.dir) / "songs"

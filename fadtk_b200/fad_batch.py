@@ -118,23 +118,22 @@ def _read_clips(part, fad: FrechetAudioDistance, ml: ModelLoader, workers: int, 
     return clips
 
 
-def _save_embeddings(ml: ModelLoader, group, embs, workers: int):
-    """``<dir>/embeddings/<model>/<stem>.npy`` for every file of ``group`` (fp16 [n_frames, d], as np.save writes it)."""
+def _save_embeddings(ml: ModelLoader, group, flat: np.ndarray, rows, workers: int):
+    """``<dir>/embeddings/<model>/<stem>.npy`` for every file of ``group`` (fp16 [n_frames, d], as np.save writes it):
+    file i = the next rows[i] rows of ``flat``."""
     paths, _ = _derived_paths(group, ml.name, ml.sr)
     for d in {os.path.dirname(p) for p in paths}:
         os.makedirs(d, exist_ok=True)
-    native = [i for i, e in enumerate(embs) if e.dtype == np.float16 and e.ndim == 2 and e.shape[1] == embs[0].shape[1]]
-    if len(native) == len(embs):
-        rows = np.array([e.shape[0] for e in embs], dtype=np.int64)
-        off = np.zeros(len(embs) + 1, dtype=np.int64)
-        off[1:] = np.cumsum(rows)
-        flat = np.concatenate(embs) if len(embs) > 1 else np.ascontiguousarray(embs[0])
-        st = _io_native.npy_write_f16(paths, flat, off[:-1], rows, workers)
+    rows = np.asarray(rows, dtype=np.int64)
+    off = np.zeros(len(rows) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(rows)
+    if flat.dtype == np.float16 and flat.ndim == 2:
+        st = _io_native.npy_write_f16(paths, np.ascontiguousarray(flat), off[:-1], rows, workers)
         for i in np.nonzero(st != _io_native.OK)[0]:
             raise OSError(f"cannot write {paths[i]} (status {int(st[i])})")
-    else:                                                      # a plugin returning something else: numpy decides the format
-        for p, e in zip(paths, embs):
-            np.save(p, e)
+    else:                                                      # a plugin returning another dtype / rank: numpy decides the format
+        for i, p in enumerate(paths):
+            np.save(p, flat[off[i]:off[i + 1]])
 
 
 def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, workers: int = 8, **kwargs):
@@ -169,10 +168,10 @@ def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, 
             secs = [len(c) / ml.sr for c in clips]
             by_file = dict(zip(part, clips))
             for group in _batches(part, secs, _BATCH_AUDIO_SECONDS):
-                embs = ml.embed_pcm_batch([by_file[f] for f in group])
+                flat, rows = ml.embed_pcm_batch_flat([by_file[f] for f in group])
                 if writer is not None:
                     writer.result()
-                writer = pool.submit(_save_embeddings, ml, group, embs, workers)
+                writer = pool.submit(_save_embeddings, ml, group, flat, rows, workers)
         if writer is not None:
             writer.result()
     dist.barrier()

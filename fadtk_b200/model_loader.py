@@ -80,6 +80,28 @@ class ModelLoader(ABC):
             out.append(self.get_embedding(wav))
         return out
 
+    def embed_pcm_batch_flat(self, clips):
+        """list of int16 mono arrays -> (fp16 [sum n_i, d] host array, rows per clip).  What the batch driver
+        writes to the ``.npy`` caches; the native embedders produce it with ONE device -> host copy."""
+        embs = self.embed_pcm_batch(clips)
+        rows = [int(e.shape[0]) for e in embs]
+        return (np.concatenate(embs) if len(embs) > 1 else np.ascontiguousarray(embs[0])), rows
+
+
+class _DeviceBatch:
+    """Shared by the native embedders: ``_embed_device(clips)`` returns one cuda fp16 tensor per clip."""
+
+    def embed_pcm_batch(self, clips):
+        return [t.cpu().numpy() for t in self._embed_device(clips)]
+
+    def embed_pcm_batch_flat(self, clips):
+        parts = self._embed_device(clips)
+        rows = [int(p.shape[0]) for p in parts]
+        flat = torch.cat(parts) if len(parts) > 1 else parts[0].contiguous()
+        host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+        host.copy_(flat)                                     # one D2H for the whole batch (synchronous: pinned destination)
+        return host.numpy(), rows
+
 
 def _as_pcm16(audio: np.ndarray) -> np.ndarray:
     """The reference feeds ``int16 / 32768.0`` (load_wav); recover the integers exactly."""
@@ -94,7 +116,7 @@ def _as_pcm16(audio: np.ndarray) -> np.ndarray:
     return pcm.astype(np.int16)
 
 
-class VGGishModel(ModelLoader):
+class VGGishModel(_DeviceBatch, ModelLoader):
     """S. Hershey et al., "CNN Architectures for Large-Scale Audio Classification", ICASSP 2017.
 
     Same registry name, dimensionality, sample rate and minimum length as the reference
@@ -129,7 +151,7 @@ class VGGishModel(ModelLoader):
     def _get_embedding(self, audio: np.ndarray):
         return self._embed_flat([_as_pcm16(audio)])[0]
 
-    def embed_pcm_batch(self, clips):
+    def _embed_device(self, clips):
         padded = []
         need = self.min_len * self.sr
         for c in clips:
@@ -137,7 +159,7 @@ class VGGishModel(ModelLoader):
             if c.shape[0] < need:
                 c = np.pad(c, (0, need - c.shape[0]))
             padded.append(c)
-        return [t.cpu().numpy() for t in self._embed_flat(padded)]
+        return self._embed_flat(padded)
 
     def _embed_flat(self, clips):
         """list of int16 arrays -> list of fp16 cuda tensors [n_i, 128]."""
@@ -154,7 +176,7 @@ class VGGishModel(ModelLoader):
         return list(torch.split(emb, [int(r) for r in rows]))
 
 
-class CLAPLaionModel(ModelLoader):
+class CLAPLaionModel(_DeviceBatch, ModelLoader):
     """CLAP from https://github.com/LAION-AI/CLAP, audio branch, B200-native.
 
     Same registry names, dimensionality and sample rate as the reference (model_loader.py:296-297):
@@ -191,8 +213,8 @@ class CLAPLaionModel(ModelLoader):
     def _get_embedding(self, audio: np.ndarray):
         return self._embed_flat([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
 
-    def embed_pcm_batch(self, clips):
-        return [t.cpu().numpy() for t in self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])]
+    def _embed_device(self, clips):
+        return self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])
 
     def _embed_flat(self, clips):
         if self._engine is None:
@@ -207,7 +229,7 @@ class CLAPLaionModel(ModelLoader):
         return list(torch.split(emb, [int(r) for r in plan["rows_per_clip"]]))
 
 
-class WhisperModel(ModelLoader):
+class WhisperModel(_DeviceBatch, ModelLoader):
     """Whisper from https://huggingface.co/openai/whisper-<size>, B200-native (model_loader.py:636-672).
 
     Same registry names (``whisper-tiny|base|small|medium|large``), dimensionality and sample rate.  The
@@ -243,8 +265,8 @@ class WhisperModel(ModelLoader):
     def _get_embedding(self, audio: np.ndarray):
         return self._embed_flat([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
 
-    def embed_pcm_batch(self, clips):
-        return [t.cpu().numpy() for t in self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])]
+    def _embed_device(self, clips):
+        return self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])
 
     def _embed_flat(self, clips):
         if self._engine is None:
@@ -260,7 +282,7 @@ class WhisperModel(ModelLoader):
         return list(emb)                                   # [2, d_model] per clip
 
 
-class EncodecEmbModel(ModelLoader):
+class EncodecEmbModel(_DeviceBatch, ModelLoader):
     """Encodec (https://github.com/facebookresearch/encodec) continuous encoder output, B200-native
     (model_loader.py:111-176).  ``variant='24k'`` (registry name ``encodec-emb``): the causal SEANet encoder
     of ``EncodecModel.encodec_model_24khz()`` on the whole file -> [T/320, 128].  ``variant='48k'``
@@ -299,7 +321,7 @@ class EncodecEmbModel(ModelLoader):
     def _get_embedding(self, audio: np.ndarray):
         return self.embed_equal_length([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
 
-    def embed_pcm_batch(self, clips):
+    def _embed_device(self, clips):
         """Clips of equal length share one launch sequence; others are embedded one length group at a time."""
         clips = [np.asarray(c, dtype=np.int16)[: 3 * 60 * self.sr] for c in clips]       # the reference's 3-minute cut (:171-173)
         out = [None] * len(clips)
@@ -308,7 +330,7 @@ class EncodecEmbModel(ModelLoader):
             groups.setdefault(len(c), []).append(i)
         for _, idx in groups.items():
             for i, e in zip(idx, self.embed_equal_length([clips[i] for i in idx])):
-                out[i] = e.cpu().numpy()
+                out[i] = e
         return out
 
     def embed_equal_length(self, clips):
@@ -330,7 +352,7 @@ class EncodecEmbModel(ModelLoader):
         return list(torch.cat(parts, dim=1))
 
 
-class Wav2VecFamilyModel(ModelLoader):
+class Wav2VecFamilyModel(_DeviceBatch, ModelLoader):
     """wav2vec 2.0 / HuBERT / MERT hidden-state embedders, B200-native (model_loader.py:254-288, 525-596).
 
     One class for the three reference loaders whose checkpoints share the "group-norm conv feature encoder +
@@ -379,7 +401,7 @@ class Wav2VecFamilyModel(ModelLoader):
             pcm = pcm[:self.limit]
         return self.embed_equal_length([pcm])[0]
 
-    def embed_pcm_batch(self, clips):
+    def _embed_device(self, clips):
         clips = [np.asarray(c, dtype=np.int16)[:self.limit] for c in clips]
         out = [None] * len(clips)
         groups = {}
@@ -387,7 +409,7 @@ class Wav2VecFamilyModel(ModelLoader):
             groups.setdefault(len(c), []).append(i)
         for _, idx in groups.items():
             for i, e in zip(idx, self.embed_equal_length([clips[i] for i in idx])):
-                out[i] = e.cpu().numpy()
+                out[i] = e
         return out
 
     def embed_equal_length(self, clips):
