@@ -157,6 +157,7 @@ def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, 
     log.info(f"[Frechet Audio Distance] Loading {len(files)} audio files...")
 
     kwargs.setdefault("audio_load_worker", workers)
+    kwargs.setdefault("load_model", ml.model is None)         # a model loaded by an earlier call (baseline dir, then eval dir) is reused
     fad = FrechetAudioDistance(ml, **kwargs)
     workers = max(1, int(workers))
 
