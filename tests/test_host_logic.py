@@ -211,3 +211,22 @@ def test_stats_cache_is_invalidated_when_embeddings_change(tmp_path, monkeypatch
     np.save(emb / "d.npy", (9 + rng.standard_normal((8, 4))).astype(np.float16))
     mu3, _ = f.load_stats(tmp_path)
     np.testing.assert_array_equal(mu2, mu3)                 # trusted like the reference does
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) needs no GPU: one JSON line with the
+    driver's keys, cpu_baseline describing the run and e2e repeating the value."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "audio-s/s"
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert "workload" in line["config"]
