@@ -142,8 +142,12 @@ class FrechetAudioDistance:
             return synth.read_wav(new)[0]
         new.parent.mkdir(parents=True, exist_ok=True)
         if f.suffix.lower() == ".wav":
-            pcm, sr = synth.read_wav(f)          # int16 [T] or [T, channels]
-            x = None
+            try:
+                pcm, sr = synth.read_wav(f)      # int16 [T] or [T, channels]
+                x = None
+            except Exception:                    # 8/24/32-bit PCM, IEEE float, extensible headers: float path
+                x, sr = synth.read_wav_float(f)  # float32 [channels, T], torchaudio.load's normalisation
+                x, pcm = torch.from_numpy(x), None
         else:
             import torchaudio                    # container decode only (needs a backend; absent in this image)
             x, sr = torchaudio.load(str(f))      # float32 [channels, T]

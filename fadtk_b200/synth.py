@@ -91,3 +91,60 @@ def read_wav(path):
     if ch > 1:
         data = data.reshape(-1, ch)
     return data, sr
+
+
+def read_wav_float(path):
+    """Any uncompressed RIFF/WAVE sample format -> (float32 [channels, T] in [-1, 1), sample_rate), normalised the
+    way ``torchaudio.load`` hands it to the reference's load_audio (fadtk/fad.py:147): 8-bit unsigned, 16 / 24 / 32-bit
+    signed PCM (integer / 2^(bits-1)), 32 / 64-bit IEEE float (as is), plain or WAVE_FORMAT_EXTENSIBLE headers.
+    Python's ``wave`` module reads only integer PCM with a plain header; this covers what music datasets ship."""
+    data = Path(path).read_bytes()
+    if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise ValueError(f"{path}: not a RIFF/WAVE file")
+    at, fmt, payload = 12, None, None
+    while at + 8 <= len(data):
+        tag, size = data[at:at + 4], int.from_bytes(data[at + 4:at + 8], "little")
+        body = at + 8
+        if tag == b"fmt ":
+            if size < 16:
+                raise ValueError(f"{path}: short fmt chunk")
+            code = int.from_bytes(data[body:body + 2], "little")
+            ch = int.from_bytes(data[body + 2:body + 4], "little")
+            sr = int.from_bytes(data[body + 4:body + 8], "little")
+            block = int.from_bytes(data[body + 12:body + 14], "little")
+            bits = int.from_bytes(data[body + 14:body + 16], "little")
+            if code == 0xFFFE and size >= 26:                  # extensible: the sub-format GUID starts with the real code
+                code = int.from_bytes(data[body + 24:body + 26], "little")
+            fmt = (code, ch, sr, block, bits)
+        elif tag == b"data":
+            if size in (0, 0xFFFFFFFF) or body + size > len(data):
+                size = len(data) - body                        # streamed writers leave the size open
+            payload = data[body:body + size]
+            break
+        at = body + size + (size & 1)
+    if fmt is None or payload is None:
+        raise ValueError(f"{path}: fmt or data chunk missing")
+    code, ch, sr, block, bits = fmt
+    if ch < 1 or sr < 1 or block != ch * bits // 8:
+        raise ValueError(f"{path}: inconsistent fmt chunk")
+    n = len(payload) // block
+    raw = np.frombuffer(payload, dtype=np.uint8, count=n * block)
+    if code == 1 and bits == 8:
+        x = (raw.astype(np.float32) - 128.0) / 128.0
+    elif code == 1 and bits == 16:
+        x = raw.view("<i2").astype(np.float32) / 32768.0
+    elif code == 1 and bits == 24:
+        b = raw.reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        v = np.where(v >= 1 << 23, v - (1 << 24), v)
+        x = v.astype(np.float32) / float(1 << 23)
+    elif code == 1 and bits == 32:
+        x = (raw.view("<i4").astype(np.float64) / float(1 << 31)).astype(np.float32)
+    elif code == 3 and bits == 32:
+        x = raw.view("<f4").astype(np.float32)
+    elif code == 3 and bits == 64:
+        x = raw.view("<f8").astype(np.float32)
+    else:
+        raise ValueError(f"{path}: unsupported WAV sample format (code {code}, {bits} bits)")
+    return np.ascontiguousarray(x.reshape(n, ch).T), sr
+

@@ -242,3 +242,39 @@ def test_per_file_means_equal_numpy_file_by_file():
     assert m_in32.dtype == np.float32
     for k, a in enumerate(kept):
         assert np.array_equal(m_in32[k], np.mean(a.astype(np.float32), axis=0))
+
+
+def test_read_wav_float_decodes_every_pcm_and_float_format(tmp_path):
+    """synth.read_wav_float against scipy.io.wavfile (which writes / reads these formats) with torchaudio.load's
+    normalisation: the convert step (fad.py:147) sees float32 [channels, T] whatever the file stores."""
+    from scipy.io import wavfile
+    from fadtk_b200 import synth
+    rng = np.random.default_rng(11)
+    T, sr = 1000, 44100
+    cases = {
+        "u8": (rng.integers(0, 256, size=(T, 2), dtype=np.uint8), lambda a: (a.astype(np.float32) - 128) / 128),
+        "i16": (rng.integers(-32768, 32768, size=(T, 1), dtype=np.int16), lambda a: a.astype(np.float32) / 32768),
+        "i32": (rng.integers(-2**31, 2**31, size=(T, 2), dtype=np.int32), lambda a: (a.astype(np.float64) / 2**31).astype(np.float32)),
+        "f32": (rng.uniform(-1, 1, size=(T, 3)).astype(np.float32), lambda a: a),
+        "f64": (rng.uniform(-1, 1, size=(T, 1)), lambda a: a.astype(np.float32)),
+    }
+    for name, (a, norm) in cases.items():
+        p = tmp_path / f"{name}.wav"
+        wavfile.write(p, sr, a)
+        x, got_sr = synth.read_wav_float(p)
+        assert got_sr == sr and x.dtype == np.float32 and x.shape == (a.shape[1], T)
+        np.testing.assert_array_equal(x, norm(a).T)
+    # 24-bit PCM, written by hand (scipy cannot write it), WAVE_FORMAT_EXTENSIBLE header
+    v = rng.integers(-2**23, 2**23, size=(T, 2), dtype=np.int64)
+    b = (v & 0xFFFFFF).astype(np.uint32)
+    payload = np.stack([(b >> s) & 255 for s in (0, 8, 16)], axis=-1).astype(np.uint8).tobytes()
+    fmt = struct.pack("<HHIIHHHHIH14s", 0xFFFE, 2, sr, sr * 6, 6, 24, 22, 24, 3, 1, b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71")
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(payload)) + payload
+    p24 = tmp_path / "i24.wav"
+    p24.write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+    x, _ = synth.read_wav_float(p24)
+    np.testing.assert_array_equal(x, (v.astype(np.float32) / 2**23).T)
+    sr_sp, a_sp = wavfile.read(p24)                            # scipy reads 24-bit into the high bytes of int32
+    np.testing.assert_array_equal(x, (a_sp.astype(np.float64) / 2**31).astype(np.float32).T)
+    with pytest.raises(ValueError):
+        synth.read_wav_float(__file__)                         # not a RIFF file
