@@ -11,6 +11,7 @@ import hashlib
 import json
 import logging
 import os
+import threading
 import traceback
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
@@ -33,6 +34,9 @@ if not log.handlers:
     log.setLevel(os.environ.get("FADTK_LOGLEVEL", "INFO"))
 
 sox_path = os.environ.get('SOX_PATH', 'sox')
+
+
+_RESAMPLE_LOCK = threading.Lock()
 
 
 class FADInfResults(NamedTuple):
@@ -160,7 +164,8 @@ class FrechetAudioDistance:
             from . import _native
             eng = _native.engine()
             src = torch.from_numpy(np.array(pcm, copy=True)) if pcm is not None else x.to(torch.float32).contiguous()
-            out = eng.resample(src.to(eng.torch_device), int(sr), int(self.ml.sr)).cpu().numpy()
+            with _RESAMPLE_LOCK:                 # a fad_handle is single-threaded; convert_audio runs on worker threads
+                out = eng.resample(src.to(eng.torch_device), int(sr), int(self.ml.sr)).cpu().numpy()
         synth.write_wav(new, out, self.ml.sr)
         return out
 

@@ -63,20 +63,20 @@ def _names_in(directory) -> set:
         return set()
 
 
-_staging = None
+_staging = [None, None]
 
 
-def _host_buffer(n_samples: int) -> np.ndarray:
-    """int16 staging buffer, reused from chunk to chunk (every clip of a chunk has been consumed by the forward
-    before the next chunk is read); pinned when a GPU is present so the H2D copy is a straight DMA."""
-    global _staging
-    if _staging is None or _staging.numel() < n_samples:
-        _staging = torch.empty(max(1, n_samples), dtype=torch.int16, pin_memory=torch.cuda.is_available())
-    return _staging.numpy()[:max(1, n_samples)]
+def _host_buffer(n_samples: int, slot: int) -> np.ndarray:
+    """int16 staging buffer of one of the two chunk slots (chunk k+1 is read while chunk k is embedded; a slot is
+    reused only after its chunk has been consumed); pinned when a GPU is present so the H2D copy is a straight DMA."""
+    if _staging[slot] is None or _staging[slot].numel() < n_samples:
+        _staging[slot] = torch.empty(max(1, n_samples), dtype=torch.int16, pin_memory=torch.cuda.is_available())
+    return _staging[slot].numpy()[:max(1, n_samples)]
 
 
-def _read_clips(part, fad: FrechetAudioDistance, ml: ModelLoader, workers: int, pool: ThreadPoolExecutor):
-    """int16 mono clips at ml.sr for every file of ``part`` (in order), filling the convert cache on the way."""
+def _read_native(part, ml: ModelLoader, workers: int, slot: int):
+    """int16 mono clips at ml.sr for the files of ``part`` the native reader can take as they are (None for the
+    others), filling the convert cache on the way.  Touches no GPU state: safe to run ahead on another thread."""
     _, conv = _derived_paths(part, ml.name, ml.sr)
     have = {d: _names_in(d) for d in {os.path.dirname(c) for c in conv}}
     cached = np.array([os.path.basename(c) in have[os.path.dirname(c)] for c in conv], dtype=bool)
@@ -88,7 +88,7 @@ def _read_clips(part, fad: FrechetAudioDistance, ml: ModelLoader, workers: int, 
     clips = [None] * len(part)
     idx = np.nonzero(fast)[0]
     if len(idx):
-        buf = _host_buffer(int(fr[idx].sum()))
+        buf = _host_buffer(int(fr[idx].sum()), slot)
         off, st2 = _io_native.wav_read([src[i] for i in idx], fr[idx], ch[idx], buf, threads=workers)
         ok = st2 == _io_native.OK
         for j, i in enumerate(idx):
@@ -111,8 +111,14 @@ def _read_clips(part, fad: FrechetAudioDistance, ml: ModelLoader, workers: int, 
                 stw = _io_native.wav_write([conv[idx[j]] for j in copy], buf, off[copy], fr[idx[copy]], ml.sr, workers)
                 for j in np.nonzero(stw != _io_native.OK)[0]:
                     raise OSError(f"cannot write {conv[idx[copy[j]]]} (status {int(stw[j])})")
+    return clips
+
+
+def _convert_rest(part, clips, fad: FrechetAudioDistance, pool: ThreadPoolExecutor):
+    """Everything the native reader left: decode / mix down / resample per file (convert_audio: decoding and file
+    I/O on the pool's threads, the GPU resampler serialised inside)."""
     rest = [i for i in range(len(part)) if clips[i] is None]
-    if rest:                                                   # resample / mix down / decode: per file
+    if rest:
         for i, pcm in zip(rest, pool.map(fad.convert_audio, [part[i] for i in rest])):
             clips[i] = pcm
     return clips
@@ -161,11 +167,15 @@ def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, 
     fad = FrechetAudioDistance(ml, **kwargs)
     workers = max(1, int(workers))
 
-    with ThreadPoolExecutor(workers) as pool:
+    chunks = [files[s:s + _CHUNK_FILES] for s in range(0, len(files), _CHUNK_FILES)]
+    with ThreadPoolExecutor(workers) as pool, ThreadPoolExecutor(1) as reader:
         writer = None                                          # embedding writes of batch k overlap the forward of batch k+1
-        for s in range(0, len(files), _CHUNK_FILES):
-            part = files[s:s + _CHUNK_FILES]
-            clips = _read_clips(part, fad, ml, workers, pool)
+        ahead = reader.submit(_read_native, chunks[0], ml, workers, 0)
+        for k, part in enumerate(chunks):
+            clips = ahead.result()
+            if k + 1 < len(chunks):                            # chunk k+1 is read while chunk k is embedded
+                ahead = reader.submit(_read_native, chunks[k + 1], ml, workers, (k + 1) & 1)
+            clips = _convert_rest(part, clips, fad, pool)
             secs = [len(c) / ml.sr for c in clips]
             by_file = dict(zip(part, clips))
             for group in _batches(part, secs, _BATCH_AUDIO_SECONDS):

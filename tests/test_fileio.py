@@ -201,7 +201,10 @@ def test_cache_embedding_files_with_a_stub_model(tmp_path):
     orig = fad_batch.FrechetAudioDistance
     fad_batch.FrechetAudioDistance = _FAD
     try:
+        monkey_chunk = fad_batch._CHUNK_FILES
+        fad_batch._CHUNK_FILES = 3                             # several chunks: exercises the read-ahead and both staging slots
         fad_batch.cache_embedding_files(tmp_path, ml, workers=3, load_model=False)
+        fad_batch._CHUNK_FILES = monkey_chunk
         assert calls == ["stereo.wav"]
         for name, pcm in clips.items():
             e = np.load(tmp_path / "embeddings" / "stub" / (Path(name).stem + ".npy"))
