@@ -281,3 +281,49 @@ def test_read_wav_float_decodes_every_pcm_and_float_format(tmp_path):
     np.testing.assert_array_equal(x, (a_sp.astype(np.float64) / 2**31).astype(np.float32).T)
     with pytest.raises(ValueError):
         synth.read_wav_float(__file__)                         # not a RIFF file
+
+
+_SHARD_WORKER = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from pathlib import Path
+from fadtk_b200 import dist, fad_batch
+from fadtk_b200.model_loader import ModelLoader
+dist.init_from_env("gloo")
+
+class Stub(ModelLoader):
+    def __init__(self):
+        super().__init__("stub", 2, 16000)
+    def load_model(self):
+        pass
+    def _get_embedding(self, audio):
+        raise NotImplementedError
+    def embed_pcm_batch(self, clips):                          # row 0: this rank, clip length
+        return [np.array([[dist.rank(), len(c) // 16000]] * 2, dtype=np.float16) for c in clips]
+
+fad_batch.cache_embedding_files(Path(sys.argv[2]), Stub(), workers=2, load_model=False)
+sys.stdout.write(f"[rank{dist.rank()}:ok]\n"); sys.stdout.flush()
+"""
+
+
+def test_two_ranks_shard_the_directory_gloo(tmp_path):
+    """Under torchrun every rank embeds its contiguous share of the sorted file list (fad_batch.py:43's array_split)
+    and all of them meet at the barrier: every file embedded exactly once, by the rank array_split assigns."""
+    import os
+    import subprocess
+    import sys
+    from fadtk_b200 import synth
+    data = tmp_path / "set"
+    data.mkdir()
+    for i in range(7):
+        synth.write_wav(data / f"c{i}.wav", np.zeros(16000 * (1 + i % 2), dtype=np.int16), 16000)
+    script = tmp_path / "worker.py"
+    script.write_text(_SHARD_WORKER)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), str(ROOT), str(data)],
+                         capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "rank0:ok" in out.stdout and "rank1:ok" in out.stdout
+    owners = [int(np.load(data / "embeddings" / "stub" / f"c{i}.npy")[0, 0]) for i in range(7)]
+    assert owners == [0, 0, 0, 0, 1, 1, 1]                     # np.array_split(7 files, 2)
+    assert [int(np.load(data / "embeddings" / "stub" / f"c{i}.npy")[0, 1]) for i in range(7)] == [1 + i % 2 for i in range(7)]
