@@ -230,3 +230,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert "workload" in line["config"]
+
+
+def test_acceptance_harness_comparison_rule(tmp_path):
+    """python -m fadtk_b200.test mirrors fadtk/test/__main__.py: per model, max |ours - published| must stay below
+    5 % of the mean of our scores; song ids are 'samples/<stem>' whatever the path style."""
+    sys.path.insert(0, str(ROOT))
+    import importlib
+    t = importlib.import_module("fadtk_b200.test.__main__")
+    table = tmp_path / "scores.csv"
+    table.write_text("song_id,dataset,FAD_vggish_fma_pop,FAD_clap_laion_audio_fma_pop\n"
+                     "samples/all,all,5.0,0.4\nsamples/mg-1,mg,20.0,1.6\nsamples/mg-2,mg,10.0,\n")
+    ref = t.reference_scores(table)
+    assert ref["vggish"] == {"samples/all": 5.0, "samples/mg-1": 20.0, "samples/mg-2": 10.0}
+    assert ref["clap_laion_audio"] == {"samples/all": 0.4, "samples/mg-1": 1.6}
+    assert t.song_id(r"C:\data\samples\mg-1.opus") == "samples/mg-1" and t.song_id("/x/samples/all") == "samples/all"
+    ok = t.compare({"samples/all": 5.1, "samples/mg-1": 20.4, "samples/mg-2": 9.9}, ref["vggish"])
+    assert ok["pass"] and abs(ok["max_abs_diff"] - 0.4) < 1e-12 and abs(ok["mad%"] - 0.4 / (35.4 / 3) * 100) < 1e-9
+    bad = t.compare({"samples/all": 5.0, "samples/mg-1": 21.0}, ref["vggish"])
+    assert not bad["pass"]                                      # 1.0 / 13.0 = 7.7 %
