@@ -142,7 +142,7 @@ dgemm_kernel(const DgemmBatch batch, int d)
     if (batch.dev_in != nullptr && *batch.dev_in < batch.tol) return;      // already converged
     if (batch.dev_clear != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
         *batch.dev_clear = 0.0f;
-    const DgemmProblem pr = batch.p[blockIdx.z];
+    const DgemmProblem pr = blockIdx.z ? batch.p[1] : batch.p[0];   // no dynamically indexed copy of the parameter block
     float dev;
     double tr;
     dgemm_tile(pr.A, pr.B, pr.C, d, pr.alpha, pr.beta_diag, dev, tr);
