@@ -103,6 +103,30 @@ class _DeviceBatch:
         return host.numpy(), rows
 
 
+def flat_pcm(clips) -> np.ndarray:
+    """The int16 clips back to back as ONE array.  The batch driver hands over consecutive views of its pinned
+    staging buffer (fad_batch._read_native); then the result is a view of that buffer - no host copy, and the
+    H2D transfer that follows is a straight DMA from pinned memory.  Anything else is concatenated."""
+    if len(clips) == 1:
+        return np.ascontiguousarray(clips[0])
+    first = clips[0]
+    owner = first
+    while isinstance(owner.base, np.ndarray):
+        owner = owner.base
+    if owner.dtype == np.int16 and owner.ndim == 1 and owner.flags.c_contiguous:
+        ptr = first.ctypes.data
+        start = (ptr - owner.ctypes.data) // 2
+        total = 0
+        for c in clips:
+            if c.dtype != np.int16 or c.ndim != 1 or not c.flags.c_contiguous or c.ctypes.data != ptr + 2 * total:
+                break
+            total += c.shape[0]
+        else:
+            if 0 <= start and start + total <= owner.shape[0]:
+                return owner[start:start + total]
+    return np.concatenate(clips)
+
+
 def _as_pcm16(audio: np.ndarray) -> np.ndarray:
     """The reference feeds ``int16 / 32768.0`` (load_wav); recover the integers exactly."""
     audio = np.asarray(audio)
@@ -169,7 +193,7 @@ class VGGishModel(_DeviceBatch, ModelLoader):
         offsets = np.zeros(len(clips) + 1, dtype=np.int64)
         offsets[1:] = np.cumsum([len(c) for c in clips])
         ex_start, rows = eng.vggish_plan(offsets)
-        flat = torch.from_numpy(np.concatenate(clips)) if len(clips) > 1 else torch.from_numpy(np.ascontiguousarray(clips[0]))
+        flat = torch.from_numpy(flat_pcm(clips))
         pcm = flat.pin_memory().to(eng.torch_device, non_blocking=True)
         ex = torch.from_numpy(ex_start).to(eng.torch_device)
         emb = eng.vggish_forward(pcm, ex)
@@ -223,7 +247,7 @@ class CLAPLaionModel(_DeviceBatch, ModelLoader):
         offsets = np.zeros(len(clips) + 1, dtype=np.int64)
         offsets[1:] = np.cumsum([len(c) for c in clips])
         plan = eng.clap_plan_frames(offsets)
-        flat = torch.from_numpy(np.concatenate(clips)) if len(clips) > 1 else torch.from_numpy(np.ascontiguousarray(clips[0]))
+        flat = torch.from_numpy(flat_pcm(clips))
         pcm = flat.pin_memory().to(eng.torch_device, non_blocking=True)
         emb = eng.clap_forward(pcm, eng.clap_plan_to_device(plan))
         return list(torch.split(emb, [int(r) for r in plan["rows_per_clip"]]))
@@ -275,7 +299,7 @@ class WhisperModel(_DeviceBatch, ModelLoader):
         lens = np.array([len(c) for c in clips], dtype=np.int32)
         starts = np.zeros(len(clips), dtype=np.int64)
         starts[1:] = np.cumsum(lens[:-1])
-        flat = torch.from_numpy(np.concatenate(clips)) if len(clips) > 1 else torch.from_numpy(np.ascontiguousarray(clips[0]))
+        flat = torch.from_numpy(flat_pcm(clips))
         dev = eng.torch_device
         emb = eng.whisper_forward(flat.pin_memory().to(dev, non_blocking=True), torch.from_numpy(starts).to(dev),
                                   torch.from_numpy(lens).to(dev))
@@ -337,7 +361,7 @@ class EncodecEmbModel(_DeviceBatch, ModelLoader):
         if self._engine is None:
             raise RuntimeError("load_model() has not been called")
         eng = self._engine
-        pcm = torch.from_numpy(np.stack(clips)).pin_memory().to(eng.torch_device, non_blocking=True)
+        pcm = torch.from_numpy(flat_pcm(clips).reshape(len(clips), -1)).pin_memory().to(eng.torch_device, non_blocking=True)
         if self.variant == '24k':
             return list(eng.encodec_forward(pcm))
         # 48 kHz: every clip is cut into 1-s segments that are encoded independently (model_loader.py:139-152)
@@ -421,7 +445,7 @@ class Wav2VecFamilyModel(_DeviceBatch, ModelLoader):
             self._max_len = L
             eng.w2v_load(*self._packed, 1, max_len=L)
             self.max_clips = 1
-        pcm = torch.from_numpy(np.stack(clips)).pin_memory().to(eng.torch_device, non_blocking=True)
+        pcm = torch.from_numpy(flat_pcm(clips).reshape(len(clips), -1)).pin_memory().to(eng.torch_device, non_blocking=True)
         return list(eng.w2v_forward(pcm, self.layer))
 
 

@@ -327,3 +327,23 @@ def test_two_ranks_shard_the_directory_gloo(tmp_path):
     owners = [int(np.load(data / "embeddings" / "stub" / f"c{i}.npy")[0, 0]) for i in range(7)]
     assert owners == [0, 0, 0, 0, 1, 1, 1]                     # np.array_split(7 files, 2)
     assert [int(np.load(data / "embeddings" / "stub" / f"c{i}.npy")[0, 1]) for i in range(7)] == [1 + i % 2 for i in range(7)]
+
+
+def test_flat_pcm_is_zero_copy_for_consecutive_views():
+    from fadtk_b200.model_loader import flat_pcm
+    buf = np.arange(1000, dtype=np.int16)
+    stage = buf[:900]                                          # like fad_batch._host_buffer: a slice of the staging array
+    clips = [stage[100:300], stage[300:301], stage[301:800]]
+    flat = flat_pcm(clips)
+    assert np.shares_memory(flat, buf) and flat.shape == (700,) and flat[0] == 100 and flat[-1] == 799
+    gap = flat_pcm([stage[0:10], stage[20:30]])                # not adjacent: a copy with the same contents
+    assert not np.shares_memory(gap, buf) and gap.tolist() == list(range(10)) + list(range(20, 30))
+    swapped = flat_pcm([stage[10:20], stage[0:10]])
+    assert swapped.tolist() == list(range(10, 20)) + list(range(0, 10))
+    padded = flat_pcm([np.pad(stage[0:5], (0, 3)), stage[5:10]])
+    assert padded.tolist() == [0, 1, 2, 3, 4, 0, 0, 0, 5, 6, 7, 8, 9]
+    one = flat_pcm([stage[7:9]])
+    assert one.tolist() == [7, 8]
+    other = flat_pcm([np.arange(4, dtype=np.int16), np.arange(4, 8, dtype=np.int16)])   # separate allocations
+    assert other.tolist() == list(range(8))
+    assert flat_pcm([stage[0:4], stage[4:8]]).reshape(2, -1).tolist() == [[0, 1, 2, 3], [4, 5, 6, 7]]
