@@ -347,3 +347,27 @@ def test_flat_pcm_is_zero_copy_for_consecutive_views():
     other = flat_pcm([np.arange(4, dtype=np.int16), np.arange(4, 8, dtype=np.int16)])   # separate allocations
     assert other.tolist() == list(range(8))
     assert flat_pcm([stage[0:4], stage[4:8]]).reshape(2, -1).tolist() == [[0, 1, 2, 3], [4, 5, 6, 7]]
+
+
+def test_c_abi_is_usable_from_plain_c(tmp_path):
+    """gcc -std=c99 compiles a C program against include/*.h, links libfadtk_io.so and round-trips WAV / .npy files:
+    the boundary really is `extern "C"` with plain pointers and sizes."""
+    import os
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    ion.lib()                                                  # make sure the library has been built
+    exe = tmp_path / "io_abi_check"
+    lib_dir = ROOT / "fadtk_b200" / "csrc"
+    build = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", str(ROOT / "tests" / "c" / "io_abi_check.c"),
+                            "-o", str(exe), f"-L{lib_dir}", "-lfadtk_io", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    work = tmp_path / "files"
+    work.mkdir()
+    run = subprocess.run([str(exe), str(work)], capture_output=True, text=True, env=dict(os.environ))
+    assert run.returncode == 0 and run.stdout.strip() == "ok v1", (run.returncode, run.stdout, run.stderr)
+    a = np.load(work / "b.npy")                                # and numpy reads what the C program wrote
+    assert a.dtype == np.float16 and a.shape == (4, 4)
+    assert a.view(np.uint16).ravel().tolist() == [0x3c00 + i for i in range(8, 24)]
