@@ -28,8 +28,10 @@ from .model_loader import ModelLoader
 
 # clips per GPU launch sequence: bounded by audio seconds so ragged sets keep batches even
 _BATCH_AUDIO_SECONDS = 4096.0
-# files decoded ahead per round of host I/O (bounds the pinned staging buffer: 2048 x 10 s x 48 kHz = 2 GB)
+# files decoded ahead per round of host I/O, bounded both by count and by samples: the pinned staging buffer of a
+# chunk never exceeds 1 GB unless a single file does (2048 x 10 s x 16 kHz = 0.66 GB; 5-minute songs at 48 kHz: 37 per chunk)
 _CHUNK_FILES = 2048
+_CHUNK_SAMPLES = 512 * 1024 * 1024
 
 
 def _batches(files, lengths_s, limit_s):
@@ -72,6 +74,24 @@ def _host_buffer(n_samples: int, slot: int) -> np.ndarray:
     if _staging[slot] is None or _staging[slot].numel() < n_samples:
         _staging[slot] = torch.empty(max(1, n_samples), dtype=torch.int16, pin_memory=torch.cuda.is_available())
     return _staging[slot].numpy()[:max(1, n_samples)]
+
+
+def _plan_chunks(files, ml: ModelLoader, workers: int):
+    """Consecutive runs of ``files`` holding at most _CHUNK_FILES files and (as far as the WAV headers tell)
+    _CHUNK_SAMPLES samples; other containers are budgeted as one minute at the model rate."""
+    srcs = [os.fspath(f) for f in files]
+    _, _, frames, st = _io_native.wav_probe(srcs, workers)
+    frames = np.where(st == _io_native.OK, frames, 60 * ml.sr)
+    chunks, cur, tot = [], [], 0
+    for f, n in zip(files, frames):
+        if cur and (len(cur) >= _CHUNK_FILES or tot + int(n) > _CHUNK_SAMPLES):
+            chunks.append(cur)
+            cur, tot = [], 0
+        cur.append(f)
+        tot += int(n)
+    if cur:
+        chunks.append(cur)
+    return chunks
 
 
 def _read_native(part, ml: ModelLoader, workers: int, slot: int):
@@ -167,7 +187,7 @@ def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, 
     fad = FrechetAudioDistance(ml, **kwargs)
     workers = max(1, int(workers))
 
-    chunks = [files[s:s + _CHUNK_FILES] for s in range(0, len(files), _CHUNK_FILES)]
+    chunks = _plan_chunks(files, ml, workers)
     with ThreadPoolExecutor(workers) as pool, ThreadPoolExecutor(1) as reader:
         writer = None                                          # embedding writes of batch k overlap the forward of batch k+1
         ahead = reader.submit(_read_native, chunks[0], ml, workers, 0)

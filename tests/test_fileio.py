@@ -203,8 +203,14 @@ def test_cache_embedding_files_with_a_stub_model(tmp_path):
     try:
         monkey_chunk = fad_batch._CHUNK_FILES
         fad_batch._CHUNK_FILES = 3                             # several chunks: exercises the read-ahead and both staging slots
+        assert [len(c) for c in fad_batch._plan_chunks(sorted(tmp_path.glob("*.wav")), ml, 2)] == [3, 3, 2]
         fad_batch.cache_embedding_files(tmp_path, ml, workers=3, load_model=False)
         fad_batch._CHUNK_FILES = monkey_chunk
+        budget = fad_batch._CHUNK_SAMPLES
+        fad_batch._CHUNK_SAMPLES = 40000                       # chunks are also bounded by samples (long files)
+        sizes = [sum(len(clips[f.name]) if f.name in clips else 16000 for f in c) for c in fad_batch._plan_chunks(sorted(tmp_path.glob("*.wav")), ml, 2)]
+        fad_batch._CHUNK_SAMPLES = budget
+        assert max(sizes) <= 48000 and sum(sizes) == sum(len(v) for v in clips.values()) + 16000 and len(sizes) >= 4
         assert calls == ["stereo.wav"]
         for name, pcm in clips.items():
             e = np.load(tmp_path / "embeddings" / "stub" / (Path(name).stem + ".npy"))
