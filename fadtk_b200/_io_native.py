@@ -139,6 +139,24 @@ def npy_read_f16(paths, rows, d: int, out: np.ndarray, row_offsets=None, threads
     return row_offsets, st
 
 
+def plan_embedding_chunks(files, max_bytes: int = 1 << 30, max_files: int = 4096, threads: int = 0):
+    """Consecutive runs of ``files`` whose payloads (as far as the .npy headers tell) stay below ``max_bytes`` each -
+    a single larger file gets a run of its own."""
+    files = list(files)
+    rows, cols, _, dt, st = npy_probe(files, threads)
+    size = np.where(st == OK, rows * cols * np.maximum(dt, 1), 0)
+    chunks, cur, tot = [], [], 0
+    for f, b in zip(files, size):
+        if cur and (len(cur) >= max_files or tot + int(b) > max_bytes):
+            chunks.append(cur)
+            cur, tot = [], 0
+        cur.append(f)
+        tot += int(b)
+    if cur:
+        chunks.append(cur)
+    return chunks
+
+
 def load_embedding_files(files, threads: int = 0):
     """Ragged concatenation of fp16 2-D ``.npy`` embedding caches: -> (fp16 [N, d], row offsets int64[n+1]).
     Files that are not C-ordered fp16 2-D arrays of one common width are read with np.load and converted the

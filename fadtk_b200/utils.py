@@ -153,9 +153,9 @@ def calculate_embd_statistics_online(files: list[PathLike]) -> tuple[np.ndarray,
     st = None
     m_in, m64, counts = [], [], []
     quirk = True
-    for s in range(0, len(files), _FILES_PER_READ):
-        # one native batched read per chunk of files (libfadtk_io.so), one Gram accumulation per chunk
-        flat, off = _io_native.load_embedding_files(files[s:s + _FILES_PER_READ])
+    for chunk in _io_native.plan_embedding_chunks(files, _BYTES_PER_READ):
+        # one native batched read per chunk of files (libfadtk_io.so, at most ~1 GB), one Gram accumulation per chunk
+        flat, off = _io_native.load_embedding_files(chunk)
         if st is None:
             st = DeviceStatistics(flat.shape[-1])
         st.add(flat)
@@ -170,7 +170,7 @@ def calculate_embd_statistics_online(files: list[PathLike]) -> tuple[np.ndarray,
     return mirror_file_mean_rounding(mu, cov, float(counts.sum()), np.concatenate(m_in), np.concatenate(m64), counts)
 
 
-_FILES_PER_READ = 2048
+_BYTES_PER_READ = 1 << 30
 
 
 def per_file_means(flat: np.ndarray, off: np.ndarray):

@@ -377,3 +377,15 @@ def test_c_abi_is_usable_from_plain_c(tmp_path):
     a = np.load(work / "b.npy")                                # and numpy reads what the C program wrote
     assert a.dtype == np.float16 and a.shape == (4, 4)
     assert a.view(np.uint16).ravel().tolist() == [0x3c00 + i for i in range(8, 24)]
+
+
+def test_embedding_chunks_are_bounded_by_bytes(tmp_path):
+    paths = []
+    for i, n in enumerate((10, 10, 300, 10, 10, 10)):
+        p = tmp_path / f"e{i}.npy"
+        np.save(p, np.zeros((n, 64), dtype=np.float16))
+        paths.append(p)
+    chunks = ion.plan_embedding_chunks(paths, max_bytes=3000)            # 10 x 64 x 2 = 1280 B, 300 rows = 38 400 B
+    assert [[p.name for p in c] for c in chunks] == [["e0.npy", "e1.npy"], ["e2.npy"], ["e3.npy", "e4.npy"], ["e5.npy"]]
+    assert [len(c) for c in ion.plan_embedding_chunks(paths, max_files=4)] == [4, 2]
+    assert ion.plan_embedding_chunks([]) == []
