@@ -389,3 +389,36 @@ def test_embedding_chunks_are_bounded_by_bytes(tmp_path):
     assert [[p.name for p in c] for c in chunks] == [["e0.npy", "e1.npy"], ["e2.npy"], ["e3.npy", "e4.npy"], ["e5.npy"]]
     assert [len(c) for c in ion.plan_embedding_chunks(paths, max_files=4)] == [4, 2]
     assert ion.plan_embedding_chunks([]) == []
+
+
+def test_statistics_from_files_match_the_reference_merge(tmp_path, golden_dir, monkeypatch):
+    """utils.calculate_embd_statistics_online end to end on the CPU: files -> native chunked reads -> per-file means
+    -> mirrored fp16-mean rounding, with the GPU Gram accumulator replaced by exact numpy; the result must equal
+    what the REAL reference's calculate_embd_statistics_online returned for the same files (tests/golden)."""
+    import torch
+    from fadtk_b200 import utils
+
+    class ExactStatistics:                                     # stands in for DeviceStatistics (the GPU kernel is tested with -m gpu)
+        def __init__(self, d):
+            self.rows = []
+
+        def add(self, rows):
+            self.rows.append(np.asarray(rows, dtype=np.float64))
+
+        def finalize(self):
+            x = np.concatenate(self.rows)
+            return torch.from_numpy(x.mean(0)), torch.from_numpy(np.cov(x, rowvar=False))
+
+    monkeypatch.setattr(utils, "DeviceStatistics", ExactStatistics)
+    monkeypatch.setattr(utils, "_BYTES_PER_READ", 2000)        # several chunks
+    g = np.load(golden_dir / "stats_cases.npz")
+    cat, sizes = g["cat"], g["sizes"]
+    files = []
+    for i, a in enumerate(np.split(cat, np.cumsum(sizes)[:-1])):
+        p = tmp_path / f"f{i:03d}.npy"
+        np.save(p, a)
+        files.append(p)
+    assert len(ion.plan_embedding_chunks(files, 2000)) > 1
+    mu, cov = utils.calculate_embd_statistics_online(files)
+    assert np.allclose(mu, g["mu_online"], rtol=1e-13, atol=1e-15)
+    assert np.allclose(cov, g["cov_online"], rtol=1e-10, atol=1e-13)
