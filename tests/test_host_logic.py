@@ -249,3 +249,38 @@ def test_acceptance_harness_comparison_rule(tmp_path):
     assert ok["pass"] and abs(ok["max_abs_diff"] - 0.4) < 1e-12 and abs(ok["mad%"] - 0.4 / (35.4 / 3) * 100) < 1e-9
     bad = t.compare({"samples/all": 5.0, "samples/mg-1": 21.0}, ref["vggish"])
     assert not bad["pass"]                                      # 1.0 / 13.0 = 7.7 %
+
+
+def test_packaged_statistics_resolve_as_a_named_baseline(tmp_path, monkeypatch):
+    """python -m fadtk_b200.package writes '<model>.mu' / '<model>.cov' keys (fadtk/package.py:33-42); the file is
+    accepted by load_stats as a path and, from $FADTK_STATS_DIR, as a baseline name (fad.py:249-266)."""
+    import numpy as np
+    from fadtk_b200 import fad as fad_mod, package
+
+    class _ML:
+        def __init__(self, name):
+            self.name, self.model = name, None
+
+    rng = np.random.default_rng(3)
+    data = tmp_path / "set"
+    want = {}
+    for name, d in (("vggish", 4), ("clap-laion-audio", 6)):   # statistics already cached: no embedding pass needed
+        s = data / "stats" / name
+        s.mkdir(parents=True)
+        a = rng.standard_normal((d, d))
+        want[name] = (rng.standard_normal(d), a @ a.T)
+        np.save(s / "mu.npy", want[name][0])
+        np.save(s / "cov.npy", want[name][1])
+    out = package.pack_statistics(data, tmp_path / "stats_dir" / "my_set.npz", [_ML("vggish"), _ML("clap-laion-audio")])
+    with np.load(out) as z:
+        assert sorted(z.files) == ["clap-laion-audio.cov", "clap-laion-audio.mu", "vggish.cov", "vggish.mu"]
+    f = fad_mod.FrechetAudioDistance.__new__(fad_mod.FrechetAudioDistance)
+    f.ml = _ML("clap-laion-audio")
+    mu, cov = f.load_stats(out)                                 # as a file
+    np.testing.assert_array_equal(mu, want["clap-laion-audio"][0])
+    monkeypatch.setenv("FADTK_STATS_DIR", str(out.parent))
+    mu, cov = f.load_stats("My_Set")                            # as a (case-insensitive) name
+    np.testing.assert_array_equal(cov, want["clap-laion-audio"][1])
+    f.ml = _ML("encodec-emb")
+    with pytest.raises(ValueError):
+        f.load_stats(out)                                       # fad.py:265: the file lacks that model
