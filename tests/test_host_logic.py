@@ -284,3 +284,34 @@ def test_packaged_statistics_resolve_as_a_named_baseline(tmp_path, monkeypatch):
     f.ml = _ML("encodec-emb")
     with pytest.raises(ValueError):
         f.load_stats(out)                                       # fad.py:265: the file lacks that model
+
+
+def test_score_command_line_appends_the_reference_csv_row(tmp_path, monkeypatch, capsys):
+    """cli.score_main with statistics files on both sides (no embedding, Frechet swapped for the CPU oracle):
+    the result row and header are the reference's (fadtk/__main__.py:62-68), a second run appends."""
+    import numpy as np
+    from fadtk_b200 import cli, fad as fad_mod
+    from oracle import fad_oracle as fo
+
+    class _ML:
+        name, model, sr = "vggish", None, 16000
+
+    monkeypatch.setattr(cli, "_registry", lambda: {"vggish": _ML()})
+    monkeypatch.setattr(fad_mod, "calc_frechet_distance", fo.frechet_distance)
+    rng = np.random.default_rng(0)
+    for name in ("base", "eval"):
+        x = rng.standard_normal((200, 8)) * (1.0 if name == "base" else 1.3)
+        np.savez(tmp_path / f"{name}.npz", **{"vggish.mu": x.mean(0), "vggish.cov": np.cov(x, rowvar=False)})
+    out = tmp_path / "results" / "scores.csv"
+    argv = ["vggish", str(tmp_path / "base.npz"), str(tmp_path / "eval.npz"), str(out), "-w", "2"]
+    assert cli.score_main(argv) == 0
+    assert cli.score_main(argv) == 0
+    lines = out.read_text().splitlines()
+    assert lines[0] == "model,baseline,eval,score,inf_r2,time" and len(lines) == 3
+    model, base, ev, score, r2, stamp = lines[1].split(",")
+    with np.load(tmp_path / "base.npz") as b, np.load(tmp_path / "eval.npz") as e:
+        want = fo.frechet_distance(b["vggish.mu"], b["vggish.cov"], e["vggish.mu"], e["vggish.cov"])
+    assert (model, base, ev, r2) == ("vggish", str(tmp_path / "base.npz"), str(tmp_path / "eval.npz"), "None")
+    assert abs(float(score) - want) < 1e-9 * abs(want) and float(stamp) > 1.6e9
+    with pytest.raises(SystemExit):                             # unknown model: argparse rejects it like the reference's choices=
+        cli.score_main(["no-such-model", "a", "b"])
