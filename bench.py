@@ -114,6 +114,33 @@ MODELS = {
 }
 
 
+def cpu_scoring_indiv(mu_b, cov_b, songs):
+    """cpu_baseline leg of benchmarks/scoring.py --mode indiv: the reference arithmetic (oracle) per song.
+    -> (scores, seconds)"""
+    from oracle import fad_oracle as fo
+    t0 = time.perf_counter()
+    want = [fo.frechet_distance(mu_b, cov_b, *fo.embd_statistics(s)) for s in songs]
+    return want, time.perf_counter() - t0
+
+
+def cpu_scoring_inf(mu_b, cov_b, rows, steps, k):
+    """cpu_baseline leg of benchmarks/scoring.py --mode inf: the first k bootstrap sizes on the oracle, consuming the
+    global numpy RNG exactly like the reference (seeded 0 here).  -> (scores, seconds in gather+cov, seconds in Frechet, sizes)"""
+    from oracle import fad_oracle as fo
+    sizes = fo.inf_sample_sizes(len(rows), steps, 500)
+    np.random.seed(0)
+    pts, t_stats, t_fr = [], 0.0, 0.0
+    for n in sizes[:k]:
+        t0 = time.perf_counter()
+        pick = np.random.choice(rows.shape[0], size=n, replace=True)
+        st = fo.embd_statistics(rows[pick])
+        t1 = time.perf_counter()
+        pts.append(fo.frechet_distance(mu_b, cov_b, *st))
+        t_stats += t1 - t0
+        t_fr += time.perf_counter() - t1
+    return pts, t_stats, t_fr, sizes
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():

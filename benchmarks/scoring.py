@@ -25,7 +25,7 @@ sys.path.insert(0, str(ROOT))
 
 import fadtk_b200 as fk                      # noqa: E402
 from fadtk_b200 import _native               # noqa: E402
-from oracle import fad_oracle as fo          # noqa: E402  (CPU baseline leg only)
+from bench import cpu_scoring_indiv, cpu_scoring_inf   # noqa: E402  (the CPU-oracle baseline legs live in bench.py)
 
 
 class CachedLoader(fk.ModelLoader):
@@ -43,6 +43,12 @@ class CachedLoader(fk.ModelLoader):
 
 def synth_rows(rng, n, d, mix, gain=1.0, shift=0.0):
     return ((rng.standard_normal((n, d), dtype=np.float32) @ mix) * gain + shift).astype(np.float16)
+
+
+def baseline_statistics(rows):
+    """fp64 mean / covariance of the synthetic baseline (what load_stats hands out, fad.py:286-288)."""
+    x = rows.astype(np.float64)
+    return x.mean(0), np.cov(x, rowvar=False)
 
 
 def main():
@@ -64,8 +70,7 @@ def main():
         d = args.dim or 128
         mix = (rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
         base_rows = synth_rows(rng, 20000, d, mix)
-        mu_b, cov_b = fo.embd_statistics(base_rows)
-        mu_b = mu_b.astype(np.float64)          # baselines come from load_stats as fp64 (fad.py:286-288)
+        mu_b, cov_b = baseline_statistics(base_rows)
         songs = [synth_rows(rng, args.rows, d, mix, 0.7 + 0.6 * rng.random(), 0.2 * rng.random()) for _ in range(args.songs)]
         # ---- device-resident: one ragged batch
         base = _native.Baseline(eng, mu_b, cov_b)
@@ -94,9 +99,7 @@ def main():
             rows = csv.read_text().splitlines()
         # ---- CPU oracle (reference arithmetic) on a bounded sample
         k = args.cpu_sample or min(args.songs, 24)
-        t0 = time.perf_counter()
-        want = [fo.frechet_distance(mu_b, cov_b, *fo.embd_statistics(s)) for s in songs[:k]]
-        cpu_s = time.perf_counter() - t0
+        want, cpu_s = cpu_scoring_indiv(mu_b, cov_b, songs[:k])
         got = out[:k, 0].cpu().numpy()
         rel = float(np.max(np.abs(got - np.array(want)) / np.abs(want)))
         print(json.dumps({
@@ -110,8 +113,7 @@ def main():
         d = args.dim or 768
         mix = (rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
         base_rows = synth_rows(rng, args.n, d, mix)
-        mu_b, cov_b = fo.embd_statistics(base_rows)
-        mu_b = mu_b.astype(np.float64)
+        mu_b, cov_b = baseline_statistics(base_rows)
         rows = synth_rows(rng, args.n, d, mix, 1.1, 0.05)
         with tempfile.TemporaryDirectory() as td:
             td = Path(td)
@@ -128,17 +130,7 @@ def main():
             res = fad.score_inf(td / "base.npz", files, steps=args.steps)
             api_s = time.perf_counter() - t0
         k = args.cpu_sample or 2
-        sizes = fo.inf_sample_sizes(len(rows), args.steps, 500)
-        np.random.seed(0)
-        cpu_pts, t_stats, t_fr = [], 0.0, 0.0
-        for n in sizes[:k]:
-            t0 = time.perf_counter()
-            pick = np.random.choice(rows.shape[0], size=n, replace=True)
-            st = fo.embd_statistics(rows[pick])
-            t1 = time.perf_counter()
-            cpu_pts.append(fo.frechet_distance(mu_b, cov_b, *st))
-            t_stats += t1 - t0
-            t_fr += time.perf_counter() - t1
+        cpu_pts, t_stats, t_fr, sizes = cpu_scoring_inf(mu_b, cov_b, rows, args.steps, k)
         cpu_s = t_stats + t_fr
         gpu_pts = [p[1] for p in res.points[:k]]
         rel = float(np.max(np.abs(np.array(gpu_pts) - np.array(cpu_pts)) / np.abs(cpu_pts)))
