@@ -37,6 +37,34 @@ sox_path = os.environ.get('SOX_PATH', 'sox')
 
 
 _RESAMPLE_LOCK = threading.Lock()
+ffmpeg_path = os.environ.get('FFMPEG_PATH', 'ffmpeg')
+
+
+def decode_container(f: Path):
+    """Compressed / non-WAV audio -> (float32 tensor [channels, T], sample rate), DECODE ONLY - mono mix-down and
+    resampling stay on the GPU path.  torchaudio.load first (the reference's default branch, fad.py:147); when it has no
+    decoder backend (TorchCodec missing), ffmpeg - the tool the reference's other branch shells out to for formats
+    SoX cannot read (fad.py:168-176) - unpacks the stream to a float32 WAV at its native rate and channel count."""
+    try:
+        import torchaudio
+        x, sr = torchaudio.load(str(f))
+        return x, int(sr)
+    except Exception as first:                                  # noqa: BLE001 - any backend failure: try ffmpeg
+        import shutil
+        import subprocess
+        import tempfile
+        exe = shutil.which(ffmpeg_path)
+        if exe is None:
+            raise RuntimeError(f"cannot decode {f}: torchaudio has no working backend ({first}) and ffmpeg "
+                               f"('{ffmpeg_path}', $FFMPEG_PATH) is not installed") from first
+        with tempfile.TemporaryDirectory() as tmp:
+            wav = Path(tmp) / "decoded.wav"
+            done = subprocess.run([exe, "-hide_banner", "-loglevel", "error", "-y", "-i", str(f), "-f", "wav",
+                                   "-acodec", "pcm_f32le", str(wav)], capture_output=True, text=True)
+            if done.returncode != 0 or not wav.exists():
+                raise RuntimeError(f"ffmpeg could not decode {f}: {done.stderr.strip()[-500:]}") from first
+            x, sr = synth.read_wav_float(wav)
+        return torch.from_numpy(x), int(sr)
 
 
 class FADInfResults(NamedTuple):
@@ -153,8 +181,7 @@ class FrechetAudioDistance:
                 x, sr = synth.read_wav_float(f)  # float32 [channels, T], torchaudio.load's normalisation
                 x, pcm = torch.from_numpy(x), None
         else:
-            import torchaudio                    # container decode only (needs a backend; absent in this image)
-            x, sr = torchaudio.load(str(f))      # float32 [channels, T]
+            x, sr = decode_container(f)          # float32 [channels, T] at the file's own rate
             pcm = None
         if pcm is not None and pcm.ndim == 1 and sr == self.ml.sr:
             out = pcm                            # already mono PCM16 at the model rate: bit-exact copy

@@ -5,6 +5,8 @@ import io
 import re
 import struct
 import wave
+
+import torch
 from pathlib import Path
 
 import numpy as np
@@ -422,3 +424,34 @@ def test_statistics_from_files_match_the_reference_merge(tmp_path, golden_dir, m
     mu, cov = utils.calculate_embd_statistics_online(files)
     assert np.allclose(mu, g["mu_online"], rtol=1e-13, atol=1e-15)
     assert np.allclose(cov, g["cov_online"], rtol=1e-10, atol=1e-13)
+
+
+def test_decode_container_falls_back_to_ffmpeg(tmp_path, monkeypatch):
+    """Non-WAV inputs: torchaudio.load first; without a decoder backend the stream is unpacked by ffmpeg (float32 WAV at
+    the native rate) and read by synth.read_wav_float.  ffmpeg is stood in for by a script that honours the same
+    command line."""
+    import stat
+    import sys
+    from scipy.io import wavfile
+    from fadtk_b200 import fad as fad_mod
+    rng = np.random.default_rng(4)
+    audio = rng.uniform(-1, 1, size=(500, 2)).astype(np.float32)
+    decoded = tmp_path / "what_ffmpeg_would_produce.wav"
+    wavfile.write(decoded, 44100, audio)
+    fake = tmp_path / "ffmpeg"
+    fake.write_text("\n".join([
+        f"#!{sys.executable}",
+        "import shutil, sys",
+        "args = sys.argv[1:]",
+        "assert args[args.index('-acodec') + 1] == 'pcm_f32le' and args[args.index('-i') + 1].endswith('.mp3')",
+        f"shutil.copy({str(decoded)!r}, args[-1])", ""]))
+    fake.chmod(fake.stat().st_mode | stat.S_IXUSR)
+    src = tmp_path / "song.mp3"
+    src.write_bytes(b"ID3 not really an mp3")                   # torchaudio cannot decode it (and has no backend here)
+    monkeypatch.setattr(fad_mod, "ffmpeg_path", str(fake))
+    x, sr = fad_mod.decode_container(src)
+    assert sr == 44100 and tuple(x.shape) == (2, 500) and x.dtype == torch.float32
+    np.testing.assert_array_equal(x.numpy(), audio.T)
+    monkeypatch.setattr(fad_mod, "ffmpeg_path", str(tmp_path / "no-such-binary"))
+    with pytest.raises(RuntimeError, match="ffmpeg"):
+        fad_mod.decode_container(src)
