@@ -67,6 +67,7 @@ SIGNATURES = {
     "fad_resample_bank": (C.c_int, [C.c_int, C.c_int, c_vp]),
     "fad_resample": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_batched": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
+    "fad_bench_dmma_peak": (C.c_int, [c_vp, C.c_int, c_vp]),
     "fad_launch_count": (c_ll, [c_vp]),
     "fad_profile_enable": (C.c_int, [c_vp, C.c_int]),
     "fad_profile_collect": (C.c_int, [c_vp, c_vp, c_vp, C.c_int]),
@@ -142,6 +143,12 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(lib().fad_launch_count(self._h))
+
+    def dmma_peak_tflops(self, iters: int = 0) -> float:
+        """measured fp64 tensor-pipe (DMMA) rate, TFLOP/s: roofline denominator of the fp64 kernels"""
+        out = C.c_double(0.0)
+        _check(lib().fad_bench_dmma_peak(self._h, int(iters), C.byref(out)))
+        return float(out.value)
 
     def profile(self, on: bool):
         _check(lib().fad_profile_enable(self._h, int(on)))

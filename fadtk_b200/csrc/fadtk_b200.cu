@@ -650,12 +650,49 @@ int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, i
     cudaStream_t st = (cudaStream_t)stream;
     const __half* E = reinterpret_cast<const __half*>(emb_f16);
     const __half* shift = reinterpret_cast<const __half*>(shift_f16);
-    if (!tensor_core) {
+    // mode 0 (default): exact fp64 Gram on the FP64 tensor pipe (DMMA); 1: tcgen05 fp16 hi/lo (fp32 accumulation,
+    // full-rank well-conditioned sets only); 2: fp64 CUDA-core kernel (verification).  FADTK_STATS overrides.
+    static const int forced = [] {
+        const char* e = getenv("FADTK_STATS");
+        if (!e) return -1;
+        const std::string v(e);
+        return v == "dmma" ? 0 : v == "umma" ? 1 : v == "simt" ? 2 : -1;
+    }();
+    if (forced >= 0) tensor_core = forced;
+    if (tensor_core == 2) {
         if (d % 64 != 0) return fail("d must be a multiple of 64");
         dim3 grid((unsigned)((n_rows + fad::kSimtRows - 1) / fad::kSimtRows), d / 64, d / 64);
         fad::stats_simt_kernel<<<grid, 256, 0, st>>>(E, n_rows, d, shift, acc);
         CK(cudaGetLastError());
         h->launches++;
+        return 0;
+    }
+    if (tensor_core == 0) {
+        if (d % 64 != 0) return fail("d must be a multiple of 64");
+        fad::StatsDmmaParams p;
+        p.n_rows = n_rows; p.d = d; p.n_tiles = d / fad::kSdTile;
+        p.n_pairs = p.n_tiles * (p.n_tiles + 1) / 2;
+        const long long stages = (n_rows + fad::kSdRows - 1) / fad::kSdRows;
+        long long want = (4LL * h->num_sms + p.n_pairs - 1) / p.n_pairs;       // ~2 waves at 2 CTAs per SM
+        if (want < 1) want = 1;
+        long long per = (stages + want - 1) / want;                             // 16-row stages per split
+        if (per < 4) per = 4;
+        p.n_splits = (int)((stages + per - 1) / per);
+        p.rows_per_split = per * fad::kSdRows;
+        p.shift = shift;
+        const size_t jobs = (size_t)p.n_pairs * p.n_splits;
+        if (ensure((void**)&h->ws_tiles, &h->ws_tiles_cap, jobs * fad::kSdTile * fad::kSdTile * 8)) return 1;
+        if (ensure((void**)&h->ws_sums, &h->ws_sums_cap, (size_t)p.n_tiles * p.n_splits * fad::kSdTile * 8)) return 1;
+        p.ws_tiles = h->ws_tiles; p.ws_sums = h->ws_sums;
+        size_t ev = prof_begin(h, st);
+        fad::stats_dmma_kernel<<<(unsigned)jobs, 256, 0, st>>>(E, p);
+        CK(cudaGetLastError());
+        prof_end(h, FAD_PROF_STATS, ev, st);
+        ev = prof_begin(h, st);
+        fad::stats_dmma_reduce_kernel<<<p.n_pairs, 256, 0, st>>>(p, acc);
+        CK(cudaGetLastError());
+        prof_end(h, FAD_PROF_STATS_REDUCE, ev, st);
+        h->launches += 2;
         return 0;
     }
     if (d % 128 != 0) return fail("d must be a multiple of 128 for the tensor-core statistics kernel");
@@ -722,6 +759,49 @@ int fad_stats_finalize(fad_handle* h, const double* acc, const void* shift_f16, 
         acc, reinterpret_cast<const __half*>(shift_f16), d, mu_out, cov_out);
     CK(cudaGetLastError());
     h->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------- fp64 tensor-pipe peak
+// Roofline denominator of the DMMA kernels (exact Gram, Newton-Schulz): MEASURED_PEAKS.json only
+// carries the bf16 GEMM and HBM copy rates, so the fp64 tensor-pipe rate is measured here - every warp
+// of a full grid issues independent m8n8k4 DMMAs from registers, nothing else.
+namespace {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x; c[i][1] = -1.0 * threadIdx.x; }
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fad::dmma_884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) sink[0] = s;                       // keeps the chain alive, never true
+}
+}  // namespace
+
+extern "C" int fad_bench_dmma_peak(fad_handle* h, int iters, double* tflops_out_host) {
+    if (!h || !tflops_out_host) return fail("null argument");
+    CK(cudaSetDevice(h->device));
+    if (iters <= 0) iters = 20000;
+    double* sink = h->fr_scal + 30;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int blocks = h->num_sms * 4;
+    dmma_peak_kernel<<<blocks, 256>>>(iters / 10, sink);            // warm-up
+    CK(cudaEventRecord(e0));
+    dmma_peak_kernel<<<blocks, 256>>>(iters, sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double flop = (double)blocks * 8 /*warps*/ * (double)iters * 8 /*DMMAs*/ * 512.0;
+    *tflops_out_host = flop / (ms * 1e-3) / 1e12;
+    h->launches += 2;
     return 0;
 }
 

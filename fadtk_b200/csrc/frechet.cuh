@@ -20,7 +20,7 @@ namespace fad {
 
 // C = alpha * A * B + beta_diag * I   (row-major d x d, fp64), optional trace(C) accumulation.
 // Up to two independent problems per launch (blockIdx.z): the Y <- Y W and Z <- W Z updates of
-// one Newton-Schulz iteration run side by side.  64 x 32 tile / 256 threads (dgemm_tile below).
+// one Newton-Schulz iteration run side by side.  64 x 64 tile / 256 threads on DMMA (dgemm_tile below).
 //
 // Convergence control without host round trips: a launch whose `dev_in` (max |W - I| of the previous
 // iteration) is below `tol` returns immediately, so a fixed-length launch sequence costs only
@@ -32,43 +32,74 @@ struct DgemmBatch {
     const float* dev_in; float* dev_out; float* dev_clear; float tol;
 };
 
-// One 64 x 32 tile of C = alpha A B + beta_diag I per 256-thread CTA; returns max |C - I| over this thread's
-// outputs and its share of tr C (both zero for threads that hold no final outputs).
-// Layout: 4 k-groups x 2 warps.  A warp owns 32 x 32 outputs (4 x 8 threads of 8 x 4 each: 32 DFMAs per
-// 6 LDS.128, so the fp64 pipe and not shared memory is the limit); the four k-groups split every 16-wide
-// K chunk between them (in-CTA split-K keeps 8 warps per CTA busy although a d = 768 problem has only 288
-// tiles) and are summed through shared memory in a fixed order.  Global loads of chunk c+1 are issued
-// before the FMAs of chunk c (register staging, two smem buffers, one barrier per chunk).
-constexpr int kDgTileM = 64, kDgTileN = 32, kDgKC = 16;
+// One 64 x 64 tile of C = alpha A B + beta_diag I per 256-thread CTA on the FP64 TENSOR pipe
+// (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4, the only fp64 MMA shape sm_100a has; tcgen05 has no f64 kind).
+// Returns max |C - I| over this thread's outputs and its share of tr C.
+// Layout: 8 warps as 2 (M) x 4 (N); a warp owns 32 x 16 outputs = 4 x 2 DMMA blocks (16 fp64 accumulators
+// per thread).  Per 4-wide k-step a warp issues 6 conflict-free LDS.64 (4 A + 2 B fragments) for 8 DMMAs,
+// so the tensor pipe and not shared memory is the limit (the CUDA-core tile this replaces needed 6 LDS.128
+// per 32 DFMAs and reached 3 TFLOP/s).  Operand tiles keep their global orientation in shared memory -
+// A as [m][k] with pitch 20, B as [k][n] with pitch 68 doubles: for the m8n8k4 fragments (A: lane -> row
+// lane/4, k lane%4; B: k lane%4, col lane/4) both pitches are = 4 mod 16, i.e. every half-warp touches 16
+// distinct 8-byte banks.  Global loads of chunk c+1 are issued before the DMMAs of chunk c (register
+// staging, two smem buffers, one barrier per 16-wide K chunk).  Accumulation order is fixed: results are
+// bit-reproducible run to run.
+constexpr int kDgTileM = 64, kDgTileN = 64, kDgKC = 16;
+constexpr int kDgPitchA = kDgKC + 4, kDgPitchB = kDgTileN + 4;
+
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, const double* __restrict__ B,
                                            double* __restrict__ C, int d, double alpha, double beta_diag,
                                            float& dev, double& tr)
 {
-    __shared__ __align__(16) double As[2][kDgKC][kDgTileM + 2];
-    __shared__ __align__(16) double Bs[2][kDgKC][kDgTileN + 2];
+    __shared__ __align__(16) double As[2][kDgTileM][kDgPitchA];
+    __shared__ __align__(16) double Bs[2][kDgKC][kDgPitchB];
     const int bi = blockIdx.y * kDgTileM, bj = blockIdx.x * kDgTileN;
-    const int t = threadIdx.x, kg = t >> 6, lane = t & 31;
-    const int r0 = ((t >> 5) & 1) * 32 + (lane >> 3) * 8, c0 = (lane & 7) * 4;
-    // loader roles: A chunk = 64 rows x 16 k (4 consecutive k per thread), B chunk = 16 k x 32 cols (2 cols per thread)
-    const int la_row = t >> 2, la_k = (t & 3) * 4, lb_k = t >> 4, lb_c = (t & 15) * 2;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;      // warp tile origin inside the CTA tile
+    const int fr = lane >> 2, fk = lane & 3;                    // fragment coordinates
+    // loader roles: A chunk = 64 rows x 16 k (4 consecutive k per thread), B chunk = 16 k x 64 cols (4 cols per thread)
+    const int la_row = t >> 2, la_k = (t & 3) * 4, lb_k = t >> 4, lb_c = (t & 15) * 4;
+    // 16-B vector path: 4-groups are then entirely inside or outside the matrix
+    const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+                                       reinterpret_cast<uintptr_t>(C)) & 15) == 0;
     const bool a_row_ok = bi + la_row < d;
     const double* a_src = A + (size_t)(bi + la_row) * d + la_k;
-    double ra[4], rb[2];
+    double ra[4], rb[4];
     auto fetch = [&](int k0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) ra[e] = (a_row_ok && k0 + la_k + e < d) ? a_src[k0 + e] : 0.0;
-        const bool kok = k0 + lb_k < d;
         const double* b_src = B + (size_t)(k0 + lb_k) * d + bj + lb_c;
-        rb[0] = (kok && bj + lb_c < d) ? b_src[0] : 0.0;
-        rb[1] = (kok && bj + lb_c + 1 < d) ? b_src[1] : 0.0;
+        const bool kok = k0 + lb_k < d;
+        if (vec) {
+            double2 v0 = make_double2(0.0, 0.0), v1 = v0, w0 = v0, w1 = v0;
+            if (a_row_ok && k0 + la_k < d) {
+                v0 = *reinterpret_cast<const double2*>(a_src + k0);
+                v1 = *reinterpret_cast<const double2*>(a_src + k0 + 2);
+            }
+            if (kok && bj + lb_c < d) {
+                w0 = *reinterpret_cast<const double2*>(b_src);
+                w1 = *reinterpret_cast<const double2*>(b_src + 2);
+            }
+            ra[0] = v0.x; ra[1] = v0.y; ra[2] = v1.x; ra[3] = v1.y;
+            rb[0] = w0.x; rb[1] = w0.y; rb[2] = w1.x; rb[3] = w1.y;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                ra[e] = (a_row_ok && k0 + la_k + e < d) ? a_src[k0 + e] : 0.0;
+                rb[e] = (kok && bj + lb_c + e < d) ? b_src[e] : 0.0;
+            }
+        }
     };
     auto stage = [&](int buf) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) As[buf][la_k + e][la_row] = ra[e];
+        *reinterpret_cast<double2*>(&As[buf][la_row][la_k]) = make_double2(ra[0], ra[1]);
+        *reinterpret_cast<double2*>(&As[buf][la_row][la_k + 2]) = make_double2(ra[2], ra[3]);
         *reinterpret_cast<double2*>(&Bs[buf][lb_k][lb_c]) = make_double2(rb[0], rb[1]);
+        *reinterpret_cast<double2*>(&Bs[buf][lb_k][lb_c + 2]) = make_double2(rb[2], rb[3]);
     };
-    double c[8][4] = {};
+    double c[4][2][2] = {};
     const int chunks = (d + kDgKC - 1) / kDgKC;
     fetch(0);
     stage(0);
@@ -77,65 +108,45 @@ __device__ __forceinline__ void dgemm_tile(const double* __restrict__ A, const d
         const int buf = ch & 1;
         if (ch + 1 < chunks) fetch((ch + 1) * kDgKC);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int k = kg * 4 + kk;
-            double a[8], b[4];
+        for (int kk = 0; kk < kDgKC; kk += 4) {
+            double a[4], b[2];
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(&As[buf][k][r0 + u]);
-                a[u] = v.x; a[u + 1] = v.y;
-            }
+            for (int i = 0; i < 4; ++i) a[i] = As[buf][wm + i * 8 + fr][kk + fk];
 #pragma unroll
-            for (int v = 0; v < 4; v += 2) {
-                const double2 w = *reinterpret_cast<const double2*>(&Bs[buf][k][c0 + v]);
-                b[v] = w.x; b[v + 1] = w.y;
-            }
+            for (int j = 0; j < 2; ++j) b[j] = Bs[buf][kk + fk][wn + j * 8 + fr];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) c[u][v] = fma(a[u], b[v], c[u][v]);
+                for (int j = 0; j < 2; ++j) dmma_884(c[i][j][0], c[i][j][1], a[i], b[j]);
         }
         if (ch + 1 < chunks) stage(buf ^ 1);
         __syncthreads();
     }
-    // sum the k-groups: groups 1..3 hand their partial tiles to group 0 one after the other
-    double* red = &As[0][0][0];                                 // 64 x 32 doubles <= sizeof(As)
-    static_assert(sizeof(double) * kDgTileM * kDgTileN <= sizeof(As), "reduction scratch");
-    const int slot = (t & 63) * 32;                             // 32 doubles per thread, thread-major
-    for (int g = 1; g < 4; ++g) {
-        if (kg == g) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) red[slot + ((u * 4 + v + (t & 31)) & 31)] = c[u][v];
-        }
-        __syncthreads();
-        if (kg == 0) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) c[u][v] += red[slot + ((u * 4 + v + (t & 31)) & 31)];
-        }
-        __syncthreads();
-    }
+    // accumulator fragment: lane holds rows lane/4, columns 2 (lane%4) + {0, 1} of each 8 x 8 block
     tr = 0.0;
     dev = 0.0f;
-    if (kg != 0) return;
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int gi = bi + r0 + u, gj = bj + c0 + v;
-            if (gi < d && gj < d) {
-                double val = alpha * c[u][v];
-                if (gi == gj) { val += beta_diag; tr += val; }
-                C[(size_t)gi * d + gj] = val;
-                dev = fmaxf(dev, (float)fabs(val - (gi == gj ? 1.0 : 0.0)));
+        for (int j = 0; j < 2; ++j) {
+            const int gi = bi + wm + i * 8 + fr, gj = bj + wn + j * 8 + 2 * fk;
+            if (gi >= d) continue;
+            double v0 = alpha * c[i][j][0], v1 = alpha * c[i][j][1];
+            if (gi == gj) { v0 += beta_diag; tr += v0; }
+            if (gi == gj + 1) { v1 += beta_diag; tr += v1; }
+            double* dst = C + (size_t)gi * d + gj;
+            if (vec) {
+                if (gj < d) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            } else {
+                if (gj < d) dst[0] = v0;
+                if (gj + 1 < d) dst[1] = v1;
             }
+            if (gj < d) dev = fmaxf(dev, (float)fabs(v0 - (gi == gj ? 1.0 : 0.0)));
+            if (gj + 1 < d) dev = fmaxf(dev, (float)fabs(v1 - (gi == gj + 1 ? 1.0 : 0.0)));
         }
 }
 
-// grid (ceil(d / 32), ceil(d / 64), problems)
+// grid (ceil(d / 64), ceil(d / 64), problems)
 __global__ void __launch_bounds__(256, 2)
 dgemm_kernel(const DgemmBatch batch, int d)
 {
@@ -150,7 +161,7 @@ dgemm_kernel(const DgemmBatch batch, int d)
         for (int o = 16; o > 0; o >>= 1) dev = fmaxf(dev, __shfl_xor_sync(0xffffffffu, dev, o));
         if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(batch.dev_out), __float_as_uint(dev));
     }
-    if (pr.trace_out != nullptr && (blockIdx.x >> 1) == blockIdx.y) {
+    if (pr.trace_out != nullptr && blockIdx.x == blockIdx.y) {
         // tiles that meet the diagonal only; reduce inside the block, one atomic per block
         __shared__ double red[256];
         red[threadIdx.x] = tr;

@@ -322,7 +322,168 @@ __global__ void stats_reduce_kernel(StatsJobParams p, double* __restrict__ acc)
 }
 
 // --------------------------------------------------------------------------------------
-// fp64 CUDA-core version (verification path).  grid = (row chunks, d/64, d/64) upper tiles only.
+// stats_dmma_kernel: the product default.  EXACT Gram matrix on the FP64 tensor pipe.
+//   y = x - s is exact in fp64 for any two fp16 values (<= 22 significant bits), every product
+//   y_a y_b is exact (<= 44 bits), and mma.sync m8n8k4 f64 (SASS DMMA.8x8x4) accumulates in fp64 in
+//   a fixed order: the result is the Gram matrix of the data to ~1e-16 - positive semi-definite, which
+//   is what Newton-Schulz on cond-1e9 / rank-deficient covariances needs (see the header) - at the
+//   tensor-pipe rate instead of the CUDA-core DFMA rate, with no atomics (bit-reproducible).
+// One CTA = one job = (64 x 64 output tile (ti <= tj), row range).  256 threads = 8 warps as 2 x 4,
+// a warp owns 32 x 16 outputs (4 x 2 DMMA blocks).  E is row-major [row][col]: for E^T E both operand
+// fragments read smem as Y[k = row][m or n = col] with pitch 68 doubles (= 4 mod 16: the m8n8k4
+// fragment pattern k = lane%4, m = lane/4 touches 16 distinct 8-byte banks per half-warp).
+// Loads: 8 bytes (4 fp16) per thread and panel, coalesced 128-B row segments, converted and shifted on
+// the way into shared memory; the next 16-row stage is in flight while the current one is multiplied.
+// Column sums of y come from the loader's own registers (no extra smem reads).
+// Jobs write their fp64 tile to a workspace; stats_dmma_reduce_kernel sums row splits in a fixed order.
+constexpr int kSdTile = 64, kSdRows = 16, kSdPitch = kSdTile + 4;
+
+struct StatsDmmaParams {
+    long long n_rows;
+    int d, n_tiles, n_pairs, n_splits;
+    long long rows_per_split;      // multiple of kSdRows
+    const __half* shift;           // [d]
+    double* ws_tiles;              // [n_pairs * n_splits][64 (row of the tile)][64 (col)]
+    double* ws_sums;               // [n_tiles * n_splits][64]
+};
+
+__device__ __forceinline__ void stats_dmma_884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2)
+stats_dmma_kernel(const __half* __restrict__ E, const StatsDmmaParams p)
+{
+    __shared__ __align__(16) double Ys[2][2][kSdRows][kSdPitch];     // [panel i | j][buffer][row][col]
+    const int job = blockIdx.x;
+    const int pair = job / p.n_splits, split = job % p.n_splits;
+    int ti, tj;
+    pair_to_tiles(pair, p.n_tiles, ti, tj);
+    const bool diag = ti == tj;
+    const long long row_begin = (long long)split * p.rows_per_split;
+    const long long row_end = min(p.n_rows, row_begin + p.rows_per_split);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int lrow = t >> 4, lcol = (t & 15) * 4;               // loader: row of the stage, first of 4 columns
+
+    double si[4], sj[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        si[e] = (double)__half2float(p.shift[ti * kSdTile + lcol + e]);
+        sj[e] = (double)__half2float(p.shift[tj * kSdTile + lcol + e]);
+    }
+    const __half* src_i = E + (size_t)ti * kSdTile + lcol;
+    const __half* src_j = E + (size_t)tj * kSdTile + lcol;
+    uint2 ri = make_uint2(0, 0), rj = make_uint2(0, 0);
+    bool rok = false;
+    auto fetch = [&](long long r0) {
+        const long long r = r0 + lrow;
+        rok = r < row_end;
+        if (rok) {
+            ri = __ldg(reinterpret_cast<const uint2*>(src_i + (size_t)r * p.d));
+            if (!diag) rj = __ldg(reinterpret_cast<const uint2*>(src_j + (size_t)r * p.d));
+        }
+    };
+    double colsum[4] = {0.0, 0.0, 0.0, 0.0};
+    auto unpack = [](uint2 v, const double (&s)[4], bool ok, double (&y)[4]) {
+        const __half2 h0 = *reinterpret_cast<const __half2*>(&v.x), h1 = *reinterpret_cast<const __half2*>(&v.y);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        y[0] = ok ? (double)f0.x - s[0] : 0.0;  y[1] = ok ? (double)f0.y - s[1] : 0.0;
+        y[2] = ok ? (double)f1.x - s[2] : 0.0;  y[3] = ok ? (double)f1.y - s[3] : 0.0;
+    };
+    auto stage = [&](int buf) {
+        double y[4];
+        unpack(ri, si, rok, y);
+        *reinterpret_cast<double2*>(&Ys[0][buf][lrow][lcol]) = make_double2(y[0], y[1]);
+        *reinterpret_cast<double2*>(&Ys[0][buf][lrow][lcol + 2]) = make_double2(y[2], y[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) colsum[e] += y[e];
+        if (!diag) {
+            unpack(rj, sj, rok, y);
+            *reinterpret_cast<double2*>(&Ys[1][buf][lrow][lcol]) = make_double2(y[0], y[1]);
+            *reinterpret_cast<double2*>(&Ys[1][buf][lrow][lcol + 2]) = make_double2(y[2], y[3]);
+        }
+    };
+
+    double c[4][2][2] = {};
+    const int stages = row_end > row_begin ? (int)((row_end - row_begin + kSdRows - 1) / kSdRows) : 0;
+    if (stages > 0) {
+        fetch(row_begin);
+        stage(0);
+    }
+    __syncthreads();
+    for (int st = 0; st < stages; ++st) {
+        const int buf = st & 1;
+        if (st + 1 < stages) fetch(row_begin + (long long)(st + 1) * kSdRows);
+        const int bp = diag ? 0 : 1;
+#pragma unroll
+        for (int kk = 0; kk < kSdRows; kk += 4) {
+            double a[4], b[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Ys[0][buf][kk + fk][wm + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[j] = Ys[bp][buf][kk + fk][wn + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) stats_dmma_884(c[i][j][0], c[i][j][1], a[i], b[j]);
+        }
+        if (st + 1 < stages) stage(buf ^ 1);
+        __syncthreads();
+    }
+    double* dst = p.ws_tiles + (size_t)job * kSdTile * kSdTile;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<double2*>(dst + (wm + i * 8 + fr) * kSdTile + wn + j * 8 + 2 * fk) =
+                make_double2(c[i][j][0], c[i][j][1]);
+    if (diag) {
+        // column sums: 16 loader rows per column group -> one fixed-order sum per column
+        double* red = &Ys[0][0][0][0];                          // 16 x 64 doubles, the stages are done with it
+        red[lrow * kSdTile + lcol + 0] = colsum[0]; red[lrow * kSdTile + lcol + 1] = colsum[1];
+        red[lrow * kSdTile + lcol + 2] = colsum[2]; red[lrow * kSdTile + lcol + 3] = colsum[3];
+        __syncthreads();
+        if (t < kSdTile) {
+            double v = 0.0;
+            for (int k = 0; k < 16; ++k) v += red[k * kSdTile + t];
+            p.ws_sums[((size_t)ti * p.n_splits + split) * kSdTile + t] = v;
+        }
+    }
+}
+
+// acc += sum over row splits of the job tiles, fixed order.  grid = (n_pairs), block = 256
+__global__ void stats_dmma_reduce_kernel(StatsDmmaParams p, double* __restrict__ acc)
+{
+    const int pair = blockIdx.x;
+    int ti, tj;
+    pair_to_tiles(pair, p.n_tiles, ti, tj);
+    const int d = p.d;
+    double* outer = acc + 1 + d;
+    for (int e = threadIdx.x; e < kSdTile * kSdTile; e += blockDim.x) {
+        const int row = e / kSdTile, col = e % kSdTile;
+        double v = 0.0;
+        for (int s = 0; s < p.n_splits; ++s)
+            v += p.ws_tiles[((size_t)pair * p.n_splits + s) * kSdTile * kSdTile + e];
+        const int I = ti * kSdTile + row, J = tj * kSdTile + col;
+        outer[(size_t)I * d + J] += v;
+        if (ti != tj) outer[(size_t)J * d + I] += v;
+    }
+    if (ti == tj) {
+        for (int cidx = threadIdx.x; cidx < kSdTile; cidx += blockDim.x) {
+            double v = 0.0;
+            for (int s = 0; s < p.n_splits; ++s) v += p.ws_sums[((size_t)ti * p.n_splits + s) * kSdTile + cidx];
+            acc[1 + ti * kSdTile + cidx] += v;                                        // sum(x - s), exact
+            acc[1 + (size_t)d + (size_t)d * d + ti * kSdTile + cidx] += v;            // centring term: same y
+        }
+    }
+    if (pair == 0 && threadIdx.x == 0) acc[0] += (double)p.n_rows;
+}
+
+// --------------------------------------------------------------------------------------
+// fp64 CUDA-core version (verification path only: FADTK_STATS=simt / mode 2).  grid = (row chunks, d/64, d/64) upper tiles only.
 constexpr int kSimtRows = 1024;
 __global__ void __launch_bounds__(256)
 stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,

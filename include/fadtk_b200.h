@@ -158,16 +158,18 @@ int fad_w2v_forward(fad_handle* h, const int16_t* pcm, long long n_clips, int L,
  * _process_file / calculate_embd_statistics_online (fadtk/utils.py:13-46) ----------------
  * Packed fp64 accumulator of length fad_stats_acc_len(d):
  *   acc[0] = n, acc[1..d] = sum(x - shift) (exact), acc[1+d..1+d+d*d) = sum y y^T (d x d),
- *   acc[1+d+d*d..] = sum y,   y = fp16(x - shift)
+ *   acc[1+d+d*d..] = sum y,   y = x - shift (exact modes) or its fp16 hi/lo pair (mode 1)
  * It is additive: accumulate batches into it, all-reduce (sum) it across GPUs, then finalize.
  * `shift` (fp16 [d], device) must be identical for every contribution to one accumulator. */
 size_t fad_stats_acc_len(int d);
-/* tensor_core = 0 (default everywhere in the product): fp64 accumulation on the CUDA cores -
- * the products (x - s)(x - s)^T of fp16 data are exact in fp64, so the result is the Gram matrix
- * of the data to ~1e-16 and stays positive semi-definite (rank-deficient per-song sets and
- * covariances with cond ~1e9 need that).
- * tensor_core = 1: tcgen05 hi/lo-split E^T E (fp32 accumulation, ~1e-6 relative) for
- * well-conditioned, full-rank sets. */
+/* tensor_core = 0 (default everywhere in the product): E^T E on the FP64 TENSOR pipe (mma.sync
+ * m8n8k4 f64 -> DMMA): the products (x - s)(x - s)^T of fp16 data are exact in fp64 and the
+ * accumulation is fp64 in a fixed order, so the result is the Gram matrix of the data to ~1e-16,
+ * positive semi-definite and bit-reproducible (rank-deficient per-song sets and covariances with
+ * cond ~1e9 need that).
+ * tensor_core = 1: tcgen05 kind::f16 hi/lo-split E^T E (fp32 accumulation in TMEM, ~1e-6 relative)
+ * for well-conditioned, full-rank sets.
+ * tensor_core = 2: the same exact arithmetic on the CUDA cores (DFMA + fp64 atomics): verification. */
 int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, int d,
                          const void* shift_f16, double* acc, int tensor_core, void* stream);
 /* rows emb[idx[i]] for i < n_idx (FAD-inf bootstrap, fadtk/fad.py:333-336) */
@@ -236,6 +238,12 @@ int fad_profile_collect(fad_handle* h, double* ms_out, long long* count_out, int
 
 /* Number of CUDA kernels this library has launched through `h` (bench.py's gpu_launches). */
 long long fad_launch_count(fad_handle* h);
+
+/* ---- measurement utility -------------------------------------------------------------
+ * fp64 tensor-pipe (DMMA m8n8k4) rate of this GPU in TFLOP/s, measured with a register-only
+ * issue loop: the roofline denominator of the exact-Gram and Newton-Schulz kernels, which
+ * MEASURED_PEAKS.json (bf16 GEMM, HBM copy) does not carry.  Synchronous; iters <= 0 = default. */
+int fad_bench_dmma_peak(fad_handle* h, int iters, double* tflops_out_host);
 
 #ifdef __cplusplus
 }

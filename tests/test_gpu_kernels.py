@@ -122,7 +122,7 @@ def test_vggish_embeddings_match_fp32_oracle(vgg_engine, vgg_state):
 
 
 @pytest.mark.parametrize("n,d", [(5000, 128), (3000, 512), (257, 128), (63, 128), (2, 128), (777, 384)])
-@pytest.mark.parametrize("tensor_core", [False, True])
+@pytest.mark.parametrize("tensor_core", [0, 1, 2], ids=["dmma", "umma", "simt"])
 def test_statistics_match_numpy_float64(engine, n, d, tensor_core):
     rng = np.random.default_rng(n + d)
     emb = (rng.normal(0.0, 1.0, (n, d)) * rng.uniform(0.2, 3.0, d) + rng.normal(0, 4.0, d)).astype(np.float16)
@@ -141,9 +141,10 @@ def test_statistics_match_numpy_float64(engine, n, d, tensor_core):
     assert acc[0].item() == n
     assert np.abs(mu.cpu().numpy() - mu_ref).max() < 1e-9 * (1 + np.abs(mu_ref).max())
     err = np.abs(cov.cpu().numpy() - cov_ref).max() / np.abs(cov_ref).max()
-    # exact path: fp64 Gram matrix of exact (x - shift) values.  tensor-core path: y carried as an fp16
-    # hi/lo pair (2^-22), fp32 accumulation cut every 256 rows -> ~1e-6 of the largest entry
-    assert err < (5e-6 if tensor_core else 1e-12), f"cov rel err {err}"
+    # exact paths (0 = DMMA on the fp64 tensor pipe, the default; 2 = CUDA-core fp64): Gram matrix of exact
+    # (x - shift) values.  tcgen05 path (1): y carried as an fp16 hi/lo pair (2^-22), fp32 accumulation cut
+    # every 256 rows -> ~1e-6 of the largest entry
+    assert err < (5e-6 if tensor_core == 1 else 1e-12), f"cov rel err {err}"
 
 
 def test_statistics_umma_equals_simt_bitwise_inputs(engine):
@@ -153,12 +154,18 @@ def test_statistics_umma_equals_simt_bitwise_inputs(engine):
     dev = engine.torch_device
     e = torch.from_numpy(emb).to(dev)
     shift = e.float().mean(0).to(torch.float16)
-    a = engine.stats_accumulate(e, shift, engine.stats_new(256), tensor_core=True)
-    b = engine.stats_accumulate(e, shift, engine.stats_new(256), tensor_core=False)
+    a = engine.stats_accumulate(e, shift, engine.stats_new(256), tensor_core=1)
+    b = engine.stats_accumulate(e, shift, engine.stats_new(256), tensor_core=2)
+    c = engine.stats_accumulate(e, shift, engine.stats_new(256), tensor_core=0)
+    c2 = engine.stats_accumulate(e, shift, engine.stats_new(256), tensor_core=0)
     torch.cuda.synchronize()
     num = (a - b).abs().max().item()
     den = b.abs().max().item()
     assert num / den < 5e-6, f"umma vs simt accumulators differ by {num / den}"
+    # DMMA and CUDA-core fp64 sum the same exact products in different orders: 1e-16-level agreement;
+    # the DMMA path has no atomics, so two runs are bit-identical
+    assert (c - b).abs().max().item() / den < 1e-13
+    assert torch.equal(c, c2)
 
 
 def test_gather_statistics(engine):
