@@ -19,6 +19,8 @@ from pathlib import Path
 import numpy as np
 import torch
 
+import os as _os
+_os.environ.setdefault("FADTK_SYNTHETIC", "1")      # benchmarks run the real architectures on seeded random weights (no checkpoints offline)
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 

@@ -124,6 +124,7 @@ class Engine:
         _check(lib().fad_create(self.device, self.max_examples, C.byref(h)))
         self._h = h
         self._keep = []
+        self.owners = {}          # weight slot -> token of the loader whose weights it holds (model_loader._DeviceBatch)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -163,6 +164,7 @@ class Engine:
     # ------------------------------------------------------------------ VGGish
     def vggish_load(self, packed: dict):
         """``packed`` comes from fadtk_b200.weights.pack_vggish (CPU tensors)."""
+        self.owners.pop("vggish", None)          # whoever loads claims the slot afterwards (model_loader._DeviceBatch)
         w = VggishWeights()
         keep = {k: v.contiguous() for k, v in packed.items() if hasattr(v, "contiguous")}
         w.conv1_w_host = keep["conv1.w"].data_ptr()
@@ -222,6 +224,7 @@ class Engine:
     # -------------------------------------------------------------------- CLAP
     def clap_load(self, tensors: list, max_chunks: int = 32):
         """``tensors`` comes from fadtk_b200.weights_clap.pack_clap (CPU tensors, fixed order)."""
+        self.owners.pop("clap", None)          # whoever loads claims the slot afterwards (model_loader._DeviceBatch)
         keep = [t.contiguous() for t in tensors]
         arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
         _check(lib().fad_clap_load(self._h, arr, len(keep), int(max_chunks)))
@@ -282,6 +285,7 @@ class Engine:
     # ------------------------------------------------------------------ Whisper
     def whisper_load(self, cfg: tuple, tensors: list, max_clips: int = 16):
         """cfg = (d_model, heads, enc_layers, dec_layers, ffn); tensors from weights_whisper.pack_whisper."""
+        self.owners.pop("whisper", None)          # whoever loads claims the slot afterwards (model_loader._DeviceBatch)
         keep = [t.contiguous() for t in tensors]
         arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
         c = (C.c_int * 5)(*[int(v) for v in cfg])
@@ -310,6 +314,7 @@ class Engine:
     # ------------------------------------------------------- wav2vec 2.0 / HuBERT / MERT
     def w2v_load(self, cfg: tuple, tensors: list, max_clips: int = 8, max_len: int = 16000 * 30):
         """cfg = weights_w2v.config_of(state); tensors from weights_w2v.pack_w2v."""
+        self.owners.pop("w2v", None)          # whoever loads claims the slot afterwards (model_loader._DeviceBatch)
         keep = [t.contiguous() for t in tensors]
         arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
         c = (C.c_int * 7)(*[int(v) for v in cfg])
@@ -333,6 +338,7 @@ class Engine:
 
     # ------------------------------------------------------------------ Encodec
     def encodec_load(self, tensors: list, max_chunk_samples: int = 16 * 240000, variant: str = "24k"):
+        self.owners.pop("encodec", None)          # whoever loads claims the slot afterwards (model_loader._DeviceBatch)
         keep = [t.contiguous() for t in tensors]
         arr = (c_vp * len(keep))(*[t.data_ptr() for t in keep])
         _check(lib().fad_encodec_load(self._h, arr, len(keep), int(max_chunk_samples), 0 if variant == "24k" else 1))

@@ -71,6 +71,15 @@ def allgather_objects(obj):
     return out
 
 
+def broadcast_object(obj, src: int = 0):
+    """a picklable object from rank ``src`` to every rank (the list of files still to embed)"""
+    if not is_distributed():
+        return obj
+    box = [obj if rank() == src else None]
+    td.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def broadcast_int64(arr, src: int = 0):
     """numpy int64 array from rank ``src`` to every rank (FAD-inf bootstrap indices: one RNG stream)."""
     if not is_distributed():

@@ -265,8 +265,24 @@ class FrechetAudioDistance:
 
         cache_dir = path / "stats" / self.ml.name
         emb_dir = path / "embeddings" / self.ml.name
-        if cache_dir.exists():
-            # The reference trusts this cache forever (fad.py:279-283): adding or re-embedding files silently
+        # Under torchrun every rank asks for the same statistics: rank 0 alone decides whether the cache is current,
+        # computes and writes it (atomically); the others wait at the barrier and then read the finished files -
+        # never a half-written mu.npy / cov.npy, never N concurrent writers of the same cache.
+        from . import dist
+        if dist.is_distributed() and dist.rank() != 0:
+            dist.barrier()
+            if not (cache_dir / "mu.npy").exists():
+                log.error(f"The dataset you want to use ({path}) is not a directory nor a file.")
+                exit(1)
+            return np.load(cache_dir / "mu.npy"), np.load(cache_dir / "cov.npy")
+        try:
+            return self._load_or_compute_dir_stats(path, cache_dir, emb_dir)
+        finally:
+            dist.barrier()
+
+    def _load_or_compute_dir_stats(self, path: Path, cache_dir: Path, emb_dir: Path):
+        if (cache_dir / "mu.npy").exists() and (cache_dir / "cov.npy").exists():
+            # The reference trusts this cache forever (fad.py:268-274): adding or re-embedding files silently
             # keeps the old statistics.  Caches written here carry a fingerprint of the embedding files they
             # were computed from; a cache without one (written by the reference) is loaded as the reference does.
             if self._stats_cache_is_current(cache_dir, emb_dir):
@@ -283,9 +299,14 @@ class FrechetAudioDistance:
         log.info("> Embeddings statistics calculated.")
 
         cache_dir.mkdir(parents=True, exist_ok=True)
-        np.save(cache_dir / "mu.npy", mu)
-        np.save(cache_dir / "cov.npy", cov)
-        (cache_dir / "source.json").write_text(json.dumps(self._embedding_fingerprint(emb_dir)))
+        for name, arr in (("mu.npy", mu), ("cov.npy", cov)):          # write-then-rename: readers never see a partial file
+            tmp = cache_dir / (name + f".tmp{os.getpid()}")
+            with open(tmp, "wb") as fh:
+                np.save(fh, arr)
+            os.replace(tmp, cache_dir / name)
+        tmp = cache_dir / f"source.json.tmp{os.getpid()}"
+        tmp.write_text(json.dumps(self._embedding_fingerprint(emb_dir)))
+        os.replace(tmp, cache_dir / "source.json")
         return mu, cov
 
     @staticmethod

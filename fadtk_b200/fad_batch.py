@@ -172,18 +172,27 @@ def cache_embedding_files(files: Union[list[Path], str, Path], ml: ModelLoader, 
         files = list(Path(files).glob('*.*'))
 
     files = [Path(f) for f in files]
-    emb_paths, _ = _derived_paths(files, ml.name, ml.sr)
-    done = {d: _names_in(d) for d in {os.path.dirname(p) for p in emb_paths}}
-    files = [f for f, p in zip(files, emb_paths) if os.path.basename(p) not in done[os.path.dirname(p)]]
+    if dist.rank() == 0:
+        emb_paths, _ = _derived_paths(files, ml.name, ml.sr)
+        done = {d: _names_in(d) for d in {os.path.dirname(p) for p in emb_paths}}
+        files = sorted(f for f, p in zip(files, emb_paths) if os.path.basename(p) not in done[os.path.dirname(p)])
+    # ONE listing decides what is left to do: rank 0 filters the already-embedded files and every rank shards that
+    # same list (a rank that lists the directory after another has started writing would see a different set)
+    files = dist.broadcast_object(files)
     if len(files) == 0:
         log.info("All files already have embeddings, skipping.")
         return
 
-    files = list(dist.shard(sorted(files)))
+    files = list(dist.shard(files))
     log.info(f"[Frechet Audio Distance] Loading {len(files)} audio files...")
+    if len(files) == 0:                                        # fewer new files than ranks: nothing for this one
+        dist.barrier()
+        return
 
     kwargs.setdefault("audio_load_worker", workers)
-    kwargs.setdefault("load_model", ml.model is None)         # a model loaded by an earlier call (baseline dir, then eval dir) is reused
+    # a model loaded by an earlier call (baseline dir, then eval dir) is reused - unless another loader has taken the
+    # engine's weight slot of this family in between (w2v2-base, then hubert-base, then w2v2-base again)
+    kwargs.setdefault("load_model", ml.model is None or not getattr(ml, "owns_engine", lambda: True)())
     fad = FrechetAudioDistance(ml, **kwargs)
     workers = max(1, int(workers))
 

@@ -89,7 +89,35 @@ class ModelLoader(ABC):
 
 
 class _DeviceBatch:
-    """Shared by the native embedders: ``_embed_device(clips)`` returns one cuda fp16 tensor per clip."""
+    """Shared by the native embedders: ``_embed_device(clips)`` returns one cuda fp16 tensor per clip.
+
+    Weight ownership.  All loaders of a process share one native engine per GPU, and the engine holds ONE set of
+    weights per model family (``_SLOT``): loading hubert-base replaces w2v2-base, HTSAT-base replaces HTSAT-tiny.
+    The reference keeps every loader's model alive independently (two live FrechetAudioDistance objects, a
+    dirs-outer / models-inner loop), so a loader records a token on the engine when it loads and checks it before
+    every forward; if another loader took the slot in between, it reloads its own weights instead of silently
+    embedding with the other model's."""
+
+    _SLOT = None
+
+    def _owner_token(self):
+        return (type(self).__name__, getattr(self, "family", None), getattr(self, "size", None),
+                getattr(self, "variant", None), getattr(self, "type", None),
+                str(getattr(self, "checkpoint", None)), getattr(self, "seed", 0))
+
+    def _claim(self):
+        self._engine.owners[self._SLOT] = self._owner_token()
+
+    def owns_engine(self) -> bool:
+        eng = getattr(self, "_engine", None)
+        return eng is not None and eng.owners.get(self._SLOT) == self._owner_token()
+
+    def _ensure_loaded(self):
+        if getattr(self, "_engine", None) is None:
+            raise RuntimeError("load_model() has not been called")
+        if not self.owns_engine():
+            log.info(f"{self.name}: the engine's {self._SLOT} weights were replaced by another loader - reloading")
+            self.load_model()
 
     def embed_pcm_batch(self, clips):
         return [t.cpu().numpy() for t in self._embed_device(clips)]
@@ -148,6 +176,8 @@ class VGGishModel(_DeviceBatch, ModelLoader):
     reference does (:100-103); enabling either is not supported by the native path.
     """
 
+    _SLOT = "vggish"
+
     def __init__(self, use_pca=False, use_activation=False, checkpoint=None, seed: int = 0):
         super().__init__("vggish", 128, 16000, min_len=1)
         if use_pca or use_activation:
@@ -171,6 +201,7 @@ class VGGishModel(_DeviceBatch, ModelLoader):
         self._engine.vggish_load(weights.pack_vggish(state))
         self.model = self._engine
         self.device = self._engine.torch_device
+        self._claim()
 
     def _get_embedding(self, audio: np.ndarray):
         return self._embed_flat([_as_pcm16(audio)])[0]
@@ -187,8 +218,7 @@ class VGGishModel(_DeviceBatch, ModelLoader):
 
     def _embed_flat(self, clips):
         """list of int16 arrays -> list of fp16 cuda tensors [n_i, 128]."""
-        if self._engine is None:
-            raise RuntimeError("load_model() has not been called")
+        self._ensure_loaded()
         eng = self._engine
         offsets = np.zeros(len(clips) + 1, dtype=np.int64)
         offsets[1:] = np.cumsum([len(c) for c in clips])
@@ -210,6 +240,8 @@ class CLAPLaionModel(_DeviceBatch, ModelLoader):
     The reference's per-window loop at batch one (model_loader.py:402-407) becomes one batched
     launch sequence over all 10-s windows of all clips.
     """
+
+    _SLOT = "clap"
 
     def __init__(self, type: str = 'audio', checkpoint=None, seed: int = 0):
         super().__init__(f"clap-laion-{type}", 512, 48000)
@@ -233,6 +265,7 @@ class CLAPLaionModel(_DeviceBatch, ModelLoader):
         self._engine.clap_load(weights_clap.pack_clap(state))
         self.model = self._engine
         self.device = self._engine.torch_device
+        self._claim()
 
     def _get_embedding(self, audio: np.ndarray):
         return self._embed_flat([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
@@ -241,8 +274,7 @@ class CLAPLaionModel(_DeviceBatch, ModelLoader):
         return self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])
 
     def _embed_flat(self, clips):
-        if self._engine is None:
-            raise RuntimeError("load_model() has not been called")
+        self._ensure_loaded()
         eng = self._engine
         offsets = np.zeros(len(clips) + 1, dtype=np.int64)
         offsets[1:] = np.cumsum([len(c) for c in clips])
@@ -261,6 +293,8 @@ class WhisperModel(_DeviceBatch, ModelLoader):
     ``WhisperModel`` forward with ``decoder_input_ids = [[sot, sot]]`` and ``last_hidden_state`` - are one
     batched launch sequence (fad_whisper_forward); every clip yields 2 rows of ``d_model`` features.
     """
+
+    _SLOT = "whisper"
 
     DIMS = {'tiny': 384, 'base': 512, 'small': 768, 'medium': 1024, 'large': 1280}
 
@@ -285,6 +319,7 @@ class WhisperModel(_DeviceBatch, ModelLoader):
         self._engine.whisper_load(weights_whisper.config_of(state), weights_whisper.pack_whisper(state, start), self.max_clips)
         self.model = self._engine
         self.device = self._engine.torch_device
+        self._claim()
 
     def _get_embedding(self, audio: np.ndarray):
         return self._embed_flat([_as_pcm16(np.asarray(audio).reshape(-1))])[0]
@@ -293,8 +328,7 @@ class WhisperModel(_DeviceBatch, ModelLoader):
         return self._embed_flat([np.asarray(c, dtype=np.int16) for c in clips])
 
     def _embed_flat(self, clips):
-        if self._engine is None:
-            raise RuntimeError("load_model() has not been called")
+        self._ensure_loaded()
         eng = self._engine
         lens = np.array([len(c) for c in clips], dtype=np.int32)
         starts = np.zeros(len(clips), dtype=np.int64)
@@ -313,6 +347,8 @@ class EncodecEmbModel(_DeviceBatch, ModelLoader):
     (``encodec-emb-48k``): the non-causal GroupNorm encoder of ``encodec_model_48khz()`` on 1-s segments with
     stride = segment (:139-152), the mono file duplicated to stereo as ``convert_audio`` does.
     """
+
+    _SLOT = "encodec"
 
     def __init__(self, variant: str = '24k', checkpoint=None, seed: int = 0, max_chunk_samples: int = 16 * 240000):
         super().__init__('encodec-emb' if variant == '24k' else f"encodec-emb-{variant}", 128,
@@ -336,6 +372,7 @@ class EncodecEmbModel(_DeviceBatch, ModelLoader):
         self._engine.encodec_load(weights_encodec.pack_encodec(state), self.max_chunk_samples, self.variant)
         self.model = self._engine
         self.device = self._engine.torch_device
+        self._claim()
 
     def load_wav(self, wav_file):
         """The reference cuts files longer than 3 minutes (model_loader.py:171-173)."""
@@ -358,8 +395,7 @@ class EncodecEmbModel(_DeviceBatch, ModelLoader):
         return out
 
     def embed_equal_length(self, clips):
-        if self._engine is None:
-            raise RuntimeError("load_model() has not been called")
+        self._ensure_loaded()
         eng = self._engine
         pcm = torch.from_numpy(flat_pcm(clips).reshape(len(clips), -1)).pin_memory().to(eng.torch_device, non_blocking=True)
         if self.variant == '24k':
@@ -385,6 +421,8 @@ class Wav2VecFamilyModel(_DeviceBatch, ModelLoader):
     ``hidden_states[layer]`` is one launch sequence that stops after ``layer`` transformer layers.
     Files longer than ``limit_minutes`` are truncated like the reference does.
     """
+
+    _SLOT = "w2v"
 
     def __init__(self, family: str, name: str, layer: int, sr: int, checkpoint=None, seed: int = 0, limit_minutes: int = 6,
                  max_clips: int = 8, size: str = 'base'):
@@ -417,6 +455,7 @@ class Wav2VecFamilyModel(_DeviceBatch, ModelLoader):
         self._engine.w2v_load(*self._packed, self.max_clips, max_len=self._max_len)
         self.model = self._engine
         self.device = self._engine.torch_device
+        self._claim()
 
     def _get_embedding(self, audio: np.ndarray):
         pcm = _as_pcm16(np.asarray(audio).reshape(-1))
@@ -437,8 +476,7 @@ class Wav2VecFamilyModel(_DeviceBatch, ModelLoader):
         return out
 
     def embed_equal_length(self, clips):
-        if self._engine is None:
-            raise RuntimeError("load_model() has not been called")
+        self._ensure_loaded()
         eng = self._engine
         L = len(clips[0])
         if L > self._max_len:                                  # a long file (up to limit_minutes): one clip at a time

@@ -47,11 +47,43 @@ def synthetic_vggish_state(seed: int = 0) -> dict:
     return sd
 
 
-def load_vggish_state(path=None, seed: int = 0) -> dict:
-    """Real checkpoint if ``path`` (or $FADTK_VGGISH_CKPT) exists, else synthetic."""
+class MissingCheckpoint(RuntimeError):
+    """No pretrained checkpoint could be resolved and synthetic weights were not explicitly allowed."""
+
+
+_warned = set()
+
+
+def resolve_checkpoint(path, env: str, what: str):
+    """-> Path of the real checkpoint to load, or None when seeded SYNTHETIC weights may be used.
+
+    The reference always loads pretrained weights (torch.hub / HF / direct URLs, model_loader.py:99, 301, 657);
+    scores from random weights are meaningless and would be cached under the same ``embeddings/<model>`` and
+    ``stats/<model>`` paths.  So: an explicit path (argument or ``$<env>``) that does not exist is an error, and
+    with no path at all the loader refuses to run unless ``FADTK_SYNTHETIC=1`` (tests, bench.py, smoke) opts in."""
+    import logging
     import os
-    path = path or os.environ.get("FADTK_VGGISH_CKPT")
-    if path and Path(path).exists():
+    path = path or os.environ.get(env)
+    if path:
+        if Path(path).exists():
+            return Path(path)
+        raise MissingCheckpoint(f"{what}: checkpoint {path!r} (argument or ${env}) does not exist")
+    if os.environ.get("FADTK_SYNTHETIC", "") == "1":
+        if what not in _warned:
+            _warned.add(what)
+            logging.getLogger("fadtk_b200").warning(
+                "%s: FADTK_SYNTHETIC=1 - running on SEEDED RANDOM weights (real architecture); "
+                "scores are not comparable with pretrained-model FAD", what)
+        return None
+    raise MissingCheckpoint(
+        f"{what}: no pretrained checkpoint - pass checkpoint=... or set ${env} (there is no network to download it); "
+        "set FADTK_SYNTHETIC=1 to run on seeded random weights (tests / benchmarks only)")
+
+
+def load_vggish_state(path=None, seed: int = 0) -> dict:
+    """Real checkpoint ``path`` (or $FADTK_VGGISH_CKPT); seeded synthetic only under FADTK_SYNTHETIC=1."""
+    path = resolve_checkpoint(path, "FADTK_VGGISH_CKPT", "vggish")
+    if path is not None:
         sd = torch.load(path, map_location="cpu")
         sd = sd.get("state_dict", sd)
         return {k: v.float().contiguous() for k, v in sd.items()

@@ -83,8 +83,10 @@ def synthetic_clap_state(seed: int = 0, variant: str = "tiny") -> dict:
 
 def load_clap_state(path=None, seed: int = 0, variant: str = "tiny") -> dict:
     """HF-format checkpoint if ``path`` (or $FADTK_CLAP_CKPT / $FADTK_CLAP_MUSIC_CKPT) exists, else synthetic."""
-    path = path or os.environ.get("FADTK_CLAP_CKPT" if variant == "tiny" else "FADTK_CLAP_MUSIC_CKPT")
-    if path and Path(path).exists():
+    from .weights import resolve_checkpoint
+    path = resolve_checkpoint(path, "FADTK_CLAP_CKPT" if variant == "tiny" else "FADTK_CLAP_MUSIC_CKPT",
+                              "clap-laion-" + ("audio" if variant == "tiny" else "music"))
+    if path is not None:
         raw = torch.load(path, map_location="cpu")
         raw = raw.get("state_dict", raw)
         out = {}

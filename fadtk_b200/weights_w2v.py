@@ -77,8 +77,9 @@ def synthetic_w2v_state(seed: int = 0, d: int = 768, layers: int = 12, ffn: int 
 
 
 def load_w2v_state(path=None, seed: int = 0, env: str = "FADTK_W2V_CKPT", **cfg) -> dict:
-    path = path or os.environ.get(env)
-    if path and Path(path).exists():
+    from .weights import resolve_checkpoint
+    path = resolve_checkpoint(path, env, env.removeprefix("FADTK_").removesuffix("_CKPT").lower())
+    if path is not None:
         raw = torch.load(path, map_location="cpu")
         raw = raw.get("state_dict", raw)
         drop = ("masked_spec_embed", "lm_head", "quantizer", "project_", "label_embs")

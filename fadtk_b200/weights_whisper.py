@@ -75,8 +75,9 @@ def synthetic_whisper_state(seed: int = 0, size: str = "small") -> dict:
 def load_whisper_state(path=None, seed: int = 0, size: str = "small"):
     """-> (state dict, decoder_start_token_id).  ``path`` / $FADTK_WHISPER_CKPT: a torch-saved
     ``WhisperModel.state_dict()`` (optionally {"state_dict": ..., "decoder_start_token_id": n})."""
-    path = path or os.environ.get("FADTK_WHISPER_CKPT")
-    if path and Path(path).exists():
+    from .weights import resolve_checkpoint
+    path = resolve_checkpoint(path, "FADTK_WHISPER_CKPT", "whisper-" + size)
+    if path is not None:
         raw = torch.load(path, map_location="cpu")
         start = int(raw.get("decoder_start_token_id", 50258)) if isinstance(raw, dict) and "state_dict" in raw else 50258
         raw = raw.get("state_dict", raw)

@@ -10,6 +10,10 @@ if str(ROOT) not in sys.path:
 
 GOLDEN = ROOT / "tests" / "golden"
 
+# no pretrained checkpoints exist offline: the tests run the real architectures on seeded random weights, which the
+# product refuses to do unless asked (weights.resolve_checkpoint)
+os.environ.setdefault("FADTK_SYNTHETIC", "1")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")

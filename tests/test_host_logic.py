@@ -315,3 +315,139 @@ def test_score_command_line_appends_the_reference_csv_row(tmp_path, monkeypatch,
     assert abs(float(score) - want) < 1e-9 * abs(want) and float(stamp) > 1.6e9
     with pytest.raises(SystemExit):                             # unknown model: argparse rejects it like the reference's choices=
         cli.score_main(["no-such-model", "a", "b"])
+
+
+def test_synthetic_weights_are_an_explicit_opt_in(tmp_path, monkeypatch):
+    """The reference always loads pretrained weights; a FAD from random weights is meaningless and would be cached
+    under the same embeddings/<model> paths.  Without a checkpoint the loaders refuse unless FADTK_SYNTHETIC=1, and
+    a path that does not exist is an error in either case."""
+    from fadtk_b200 import weights, weights_clap, weights_encodec, weights_w2v, weights_whisper
+    for var in ("FADTK_SYNTHETIC", "FADTK_VGGISH_CKPT", "FADTK_CLAP_CKPT", "FADTK_ENCODEC_CKPT", "FADTK_WHISPER_CKPT", "FADTK_W2V2_CKPT"):
+        monkeypatch.delenv(var, raising=False)
+    for load in (lambda: weights.load_vggish_state(), lambda: weights_clap.load_clap_state(),
+                 lambda: weights_encodec.load_encodec_state(), lambda: weights_whisper.load_whisper_state(),
+                 lambda: weights_w2v.load_w2v_state(env="FADTK_W2V2_CKPT")):
+        with pytest.raises(weights.MissingCheckpoint):
+            load()
+    monkeypatch.setenv("FADTK_SYNTHETIC", "1")
+    assert "features.0.weight" in weights.load_vggish_state()
+    with pytest.raises(weights.MissingCheckpoint):            # a mistyped path never silently becomes random weights
+        weights.load_vggish_state(tmp_path / "no-such-vggish.pth")
+    monkeypatch.setenv("FADTK_VGGISH_CKPT", str(tmp_path / "typo.pth"))
+    with pytest.raises(weights.MissingCheckpoint):
+        weights.load_vggish_state()
+    import torch
+    real = {k: v + 1.0 for k, v in weights.synthetic_vggish_state(3).items()}
+    torch.save(real, tmp_path / "vggish.pth")
+    got = weights.load_vggish_state(tmp_path / "vggish.pth")
+    assert torch.equal(got["embeddings.4.bias"], real["embeddings.4.bias"])
+
+
+def test_loaders_sharing_an_engine_slot_reload_instead_of_borrowing_weights():
+    """hubert-base, then w2v2-base, then hubert-base again (a dirs-outer / models-inner loop, or two live
+    FrechetAudioDistance objects): the engine holds ONE set of weights per family, so the third use must reload."""
+    from fadtk_b200 import model_loader as mlmod
+
+    class FakeEngine:
+        torch_device = "cpu"
+
+        def __init__(self):
+            self.owners, self.loaded = {}, []
+
+    eng = FakeEngine()
+
+    class Probe(mlmod._DeviceBatch, mlmod.ModelLoader):
+        _SLOT = "w2v"
+
+        def __init__(self, family):
+            super().__init__(family, 768, 16000)
+            self.family, self.size, self.checkpoint, self.seed = family, "base", None, 0
+            self._engine = None
+
+        def load_model(self):
+            self._engine = eng
+            eng.owners.pop(self._SLOT, None)
+            eng.loaded.append(self.family)
+            self.model = eng
+            self._claim()
+
+        def _get_embedding(self, audio):
+            self._ensure_loaded()
+            return eng.loaded[-1]
+
+    a, b = Probe("hubert"), Probe("w2v2")
+    with pytest.raises(RuntimeError):
+        a._ensure_loaded()
+    a.load_model()
+    assert a.owns_engine() and a._get_embedding(None) == "hubert" and eng.loaded == ["hubert"]
+    b.load_model()
+    assert b.owns_engine() and not a.owns_engine()
+    assert a._get_embedding(None) == "hubert" and eng.loaded == ["hubert", "w2v2", "hubert"]   # reloaded, not borrowed
+    assert not b.owns_engine() and b._get_embedding(None) == "w2v2"
+    twin = Probe("w2v2")                                     # same configuration = same weights: no reload needed
+    twin._engine = eng
+    assert twin.owns_engine()
+
+
+_SHARD_WORKER = r"""
+import os, sys, json, numpy as np
+sys.path.insert(0, sys.argv[1])
+os.environ["FADTK_SYNTHETIC"] = "1"
+from pathlib import Path
+from fadtk_b200 import dist, fad as fad_mod, fad_batch, synth
+from fadtk_b200.model_loader import ModelLoader
+dist.init_from_env("gloo")
+r = dist.rank()
+root = Path(sys.argv[2])
+
+class Tiny(ModelLoader):
+    # a plain third-party plugin (no batched extension): 4 features per 0.1 s
+    def __init__(self):
+        super().__init__("tiny", 4, 16000)
+    def load_model(self):
+        self.model = object()
+    def _get_embedding(self, audio):
+        a = np.asarray(audio, dtype=np.float32)[: (len(audio) // 1600) * 1600].reshape(-1, 1600)
+        return np.stack([a.mean(1), a.std(1), a.min(1), a.max(1)], 1).astype(np.float32)
+
+def cpu_stats(files):
+    e = np.concatenate([np.load(f) for f in files]).astype(np.float64)
+    return e.mean(0), np.cov(e, rowvar=False)
+fad_mod.calculate_embd_statistics_online = cpu_stats
+fad_mod.FrechetAudioDistance.convert_audio = lambda self, f: synth.read_wav(f)[0]
+
+ml = Tiny()
+# one new file for two ranks: rank 1's shard is empty and must reach the barrier instead of raising
+fad_batch.cache_embedding_files(root / "one", ml, workers=2)
+assert sorted(p.name for p in (root / "one" / "embeddings" / "tiny").glob("*.npy")) == ["a.npy"]
+fad_batch.cache_embedding_files(root / "many", ml, workers=2)
+names = sorted(p.name for p in (root / "many" / "embeddings" / "tiny").glob("*.npy"))
+assert names == [f"c{i}.npy" for i in range(5)], names
+fad_batch.cache_embedding_files(root / "many", ml, workers=2)          # nothing left: every rank returns
+# statistics of an uncached directory requested by every rank: rank 0 writes, the others read the finished cache
+f = fad_mod.FrechetAudioDistance(ml, audio_load_worker=2, load_model=False)
+mu, cov = f.load_stats(root / "many")
+want = cpu_stats(sorted((root / "many" / "embeddings" / "tiny").glob("*.npy")))
+assert np.array_equal(mu, want[0]) and np.array_equal(cov, want[1])
+assert not list((root / "many" / "stats" / "tiny").glob("*.tmp*"))
+sys.stdout.write(f"[rank{r}:ok]\n"); sys.stdout.flush()
+"""
+
+
+def test_two_rank_file_sharding_and_rank0_statistics_gloo(tmp_path):
+    """an empty shard must not hang the other ranks, the already-embedded filter must come from ONE
+    listing, and directory statistics must have one writer."""
+    from fadtk_b200 import synth
+    (tmp_path / "one").mkdir()
+    (tmp_path / "many").mkdir()
+    synth.write_wav(tmp_path / "one" / "a.wav", synth.musiclike_clip(0, 1.0, 16000), 16000)
+    for i in range(5):
+        synth.write_wav(tmp_path / "many" / f"c{i}.wav", synth.musiclike_clip(i + 1, 1.0, 16000), 16000)
+    script = tmp_path / "worker.py"
+    script.write_text(_SHARD_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), str(ROOT), str(tmp_path)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "rank0:ok" in out.stdout and "rank1:ok" in out.stdout, out.stdout
