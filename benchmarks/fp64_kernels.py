@@ -107,7 +107,7 @@ def main():
 
     if "batched" in what:
         d, rows_per, songs = 128, 750, args.songs
-        mix = rng.standard_normal((d, d)).astype(np.float32) / np.sqrt(d)
+        mix = (rng.standard_normal((d, d)) / np.sqrt(d)).astype(np.float32)
         base_rows = (rng.standard_normal((20000, d)).astype(np.float32) @ mix).astype(np.float64)
         base = _native.Baseline(eng, base_rows.mean(0), np.cov(base_rows, rowvar=False))
         emb = (torch.randn((songs * rows_per, d), device=dev) @ torch.from_numpy(mix).to(dev)).mul_(1.1).to(torch.float16)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "fad_vggish_plan": (c_ll, [c_vp, c_ll, c_vp, c_ll, c_vp]),
     "fad_vggish_forward": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_vggish_logmel": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, C.c_int, c_vp]),
+    "fad_vggish_conv1": (C.c_int, [c_vp, c_vp, c_ll, c_vp, c_vp]),
     "fad_umma_layer": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_clap_load": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int]),
@@ -75,7 +76,7 @@ SIGNATURES = {
 
 PROF_CATEGORIES = 20
 PROF_NAMES = {0: "logmel", 1: "conv1", 2: "conv2", 3: "conv3_1", 4: "conv3_2", 5: "conv4_1", 6: "conv4_2",
-              7: "fc1", 8: "fc2", 9: "fc3", 10: "stats_umma", 11: "stats_reduce", 12: "frechet",
+              7: "fc1", 8: "fc2", 9: "fc3", 10: "stats", 11: "stats_reduce", 12: "frechet",
               13: "clap_front", 14: "clap_gemm", 15: "clap_attn", 16: "clap_other"}
 
 
@@ -206,6 +207,14 @@ class Engine:
         out = torch.empty((n, 96, 64), dtype=torch.float32, device=pcm.device)
         _check(lib().fad_vggish_logmel(self._h, pcm.data_ptr(), ex_start.data_ptr(), n,
                                        out.data_ptr(), int(use_double), _stream()))
+        return out
+
+    def vggish_conv1(self, logmel):
+        """fp32 [n, 96, 64] log-mel examples -> fp16 NHWC [n, 48, 32, 64] (conv1 + ReLU + max-pool, loaded weights)"""
+        assert logmel.dtype == torch.float32 and logmel.is_contiguous() and logmel.shape[1:] == (96, 64)
+        n = logmel.shape[0]
+        out = torch.empty((n, 48, 32, 64), dtype=torch.float16, device=logmel.device)
+        _check(lib().fad_vggish_conv1(self._h, logmel.data_ptr(), n, out.data_ptr(), _stream()))
         return out
 
     def umma_layer(self, x, w, bias, taps, relu, pool, want_f32=False, split_w=False):

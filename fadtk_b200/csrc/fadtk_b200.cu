@@ -616,6 +616,19 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
     return 0;
 }
 
+// Stage entry (parity test): conv1 (3x3, 1 -> 64, pad 1) + bias + ReLU + 2x2 max-pool on fp32 log-mel examples.
+int fad_vggish_conv1(fad_handle* h, const float* logmel, long long n_examples, void* out_f16, void* stream) {
+    if (!h) return fail("null handle");
+    if (!h->vgg_loaded) return fail("fad_vggish_load has not been called");
+    if (n_examples <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    fad::conv1_kernel<<<dim3(6, (unsigned)n_examples), 256, 0, (cudaStream_t)stream>>>(
+        logmel, h->conv1_w, h->conv1_b, reinterpret_cast<__half*>(out_f16), nullptr);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
 int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int Cin,
                    const void* w_f16, const float* bias, int Cout, int taps, int relu, int pool,
                    int split_w, void* out_f16, float* out_f32_or_null, void* stream) {

@@ -147,6 +147,33 @@ def _device_score(baseline, emb_dev, eng, idx_dev=None):
     return float(diff.dot(diff) + out[5] + out[6] - 2 * out[1])
 
 
+def _statistics_dirs():
+    """Where a baseline NAME such as ``fma_pop`` is looked up (fadtk/fad.py:249-255 reads fadtk/stats/<name>.npz):
+    $FADTK_STATS_DIR, this package's stats/ directory, and - when the reference package itself is installed next to
+    this one - its fadtk/stats/ directory, so `fadtk vggish fma_pop <dir>` keeps working after the switch."""
+    dirs = []
+    env = os.environ.get("FADTK_STATS_DIR", "")
+    if env:
+        dirs.append(Path(env))
+    dirs.append(Path(__file__).parent / "stats")
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("fadtk")
+        if spec is not None and spec.submodule_search_locations:
+            dirs += [Path(loc) / "stats" for loc in spec.submodule_search_locations]
+    except (ImportError, ValueError):
+        pass
+    return dirs
+
+
+def _named_statistics(name: str):
+    for bp in _statistics_dirs():
+        stats = bp / (name.lower() + ".npz")
+        if stats.exists():
+            return stats
+    return None
+
+
 class FrechetAudioDistance:
     """Same constructor and methods as fadtk.fad.FrechetAudioDistance (fad.py:123-395)."""
     loaded = False
@@ -249,11 +276,13 @@ class FrechetAudioDistance:
     def load_stats(self, path: PathLike):
         """Embedding statistics of a named set, an .npz file or a directory (fad.py:245-290)."""
         if isinstance(path, str):
-            for bp in (Path(os.environ.get("FADTK_STATS_DIR", "")), Path(__file__).parent / "stats"):
-                stats = bp / (path.lower() + ".npz")
-                if str(bp) != "." and stats.exists():
-                    path = stats
-                    break
+            named = _named_statistics(path)
+            if named is not None:
+                path = named
+            elif not Path(path).exists() and os.sep not in path and not path.endswith(".npz"):
+                log.error(f"'{path}' is neither a path nor a packaged statistics name: no {path.lower()}.npz in "
+                          + ", ".join(str(d) for d in _statistics_dirs()) + " (the reference ships fadtk/stats/fma_pop.npz; "
+                          "copy it into one of these directories or point $FADTK_STATS_DIR at it)")
         path = Path(path)
 
         if path.is_file():

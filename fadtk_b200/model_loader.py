@@ -243,11 +243,12 @@ class CLAPLaionModel(_DeviceBatch, ModelLoader):
 
     _SLOT = "clap"
 
-    def __init__(self, type: str = 'audio', checkpoint=None, seed: int = 0):
+    def __init__(self, type: str = 'audio', checkpoint=None, seed: int = 0, max_chunks: int = 128):
         super().__init__(f"clap-laion-{type}", 512, 48000)
         self.type = type
         self.checkpoint = checkpoint
         self.seed = seed
+        self.max_chunks = max_chunks                      # 10-s windows per launch sequence (~9 MB of workspace each)
         self._engine = None
 
     def __getstate__(self):
@@ -262,7 +263,7 @@ class CLAPLaionModel(_DeviceBatch, ModelLoader):
         from . import _native, weights_clap
         self._engine = _native.engine()
         state = weights_clap.load_clap_state(self.checkpoint, self.seed, "tiny" if self.type == 'audio' else "base")
-        self._engine.clap_load(weights_clap.pack_clap(state))
+        self._engine.clap_load(weights_clap.pack_clap(state), max_chunks=self.max_chunks)
         self.model = self._engine
         self.device = self._engine.torch_device
         self._claim()

@@ -143,6 +143,10 @@ class EvalSetFAD:
             b16 = p16 - torch.outer(mu_ref, s16) - torch.outer(s16, mu_ref) + n * torch.outer(mu_ref, mu_ref)
             cov = (cov * (n - 1) - b64 + b16) / (n - 1)
             mu = mu_ref
+            if r == 1:                                        # one frame per "file": the reference's covariance is NaN (utils.py:16)
+                import os
+                if os.environ.get("FADTK_SINGLE_FRAME_FILES", "") != "keep":
+                    cov = torch.full_like(cov, float("nan"))
         if self._baseline is None:                            # sqrt(C_base) once per baseline, not per eval set
             self._baseline = _native.Baseline(self.eng, self.mu_base, self.cov_base)
         return self._baseline.frechet(mu.contiguous(), cov.contiguous())

@@ -144,8 +144,11 @@ def calculate_embd_statistics_online(files: list[PathLike]) -> tuple[np.ndarray,
 
     All rows go through one exact shifted Gram contraction on the GPU; the reference's habit of
     rounding every per-file mean to fp16 before merging (it moves FAD by ~1e-4 on small sets) is
-    then mirrored from the per-file means.  Deliberate difference: a single-frame file contributes
-    its one row instead of turning the whole covariance into NaN (utils.py:16).
+    then mirrored from the per-file means.  A file with exactly ONE frame makes the reference's
+    covariance all-NaN (``np.cov`` of one row with ddof = 1 is NaN, ``* (n - 1)`` keeps it, the merge
+    spreads it - utils.py:16, 36-45; BASELINE config 1's 1-s VGGish clips hit this) and the score then
+    fails in ``calc_frechet_distance``; that is mirrored: mu as the reference computes it, cov = NaN.
+    ``FADTK_SINGLE_FRAME_FILES=keep`` instead lets such a file contribute its row (an extension).
     """
     assert len(files) > 0, "No files provided"
     from . import _io_native
@@ -167,7 +170,22 @@ def calculate_embd_statistics_online(files: list[PathLike]) -> tuple[np.ndarray,
     if not quirk:
         return mu, cov
     counts = np.concatenate(counts)
-    return mirror_file_mean_rounding(mu, cov, float(counts.sum()), np.concatenate(m_in), np.concatenate(m64), counts)
+    mu_ref, cov_ref = mirror_file_mean_rounding(mu, cov, float(counts.sum()), np.concatenate(m_in), np.concatenate(m64), counts)
+    return mu_ref, poison_single_frame_files(cov_ref, counts)
+
+
+def poison_single_frame_files(cov: np.ndarray, counts) -> np.ndarray:
+    """The reference's result when some file holds a single frame: an all-NaN covariance (utils.py:16)."""
+    import os
+    n_single = int((np.asarray(counts) == 1).sum())
+    if n_single == 0 or os.environ.get("FADTK_SINGLE_FRAME_FILES", "") == "keep":
+        return cov
+    import logging
+    logging.getLogger("fadtk_b200").warning(
+        f"{n_single} embedding file(s) hold a single frame: the reference's per-file np.cov (fadtk/utils.py:16) is NaN "
+        "for them and its merge makes the whole covariance NaN - mirrored. Use longer clips, concatenate the embeddings "
+        "(calc_embd_statistics), or set FADTK_SINGLE_FRAME_FILES=keep to let such files contribute their row.")
+    return np.full_like(cov, np.nan)
 
 
 _BYTES_PER_READ = 1 << 30

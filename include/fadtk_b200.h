@@ -74,6 +74,9 @@ int fad_vggish_forward(fad_handle* h, const int16_t* pcm, const long long* ex_st
 int fad_vggish_logmel(fad_handle* h, const int16_t* pcm, const long long* ex_start,
                       long long n_examples, float* logmel_out /* [n,96,64] */, int use_double,
                       void* stream);
+/* conv1 of the VGG stack alone (3x3, 1 -> 64, pad 1, + bias, ReLU, 2x2 max-pool; CUDA-core fp32 stencil) with the
+ * loaded weights: logmel fp32 [n, 96, 64] -> fp16 NHWC [n, 48, 32, 64]. */
+int fad_vggish_conv1(fad_handle* h, const float* logmel, long long n_examples, void* out_f16, void* stream);
 /* One tensor-core layer: 3x3 conv pad 1 (taps = 9) or fully connected (taps = 1, H = W = 1) on
  * NHWC fp16 input x[NB,H,W,Cin] with fp16 weights w[Cout, taps*Cin]; fused bias, optional ReLU,
  * optional 2x2 max-pool; fp16 NHWC output (and optional fp32 copy of the un-pooled output). */

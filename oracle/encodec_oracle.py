@@ -15,7 +15,32 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from fadtk_b200.weights_encodec import conv_table, effective_weight, LSTM_LAYERS
+# Deliberately NO import from fadtk_b200: the layer table and the weight-norm folding are restated here (torch's own
+# ``torch._weight_norm``), so a bug in the product's weights_encodec.effective_weight / conv_table cannot hide behind
+# an oracle that shares it.
+LSTM_LAYERS = 2
+_RATIOS = (2, 4, 5, 8)                                          # encoder order (encodec SEANetEncoder reverses [8, 5, 4, 2])
+
+
+def conv_table():
+    """(layer index in the Sequential, kind, Cin, Cout, kernel, stride) in execution order: conv(1 -> 32, k7);
+    4 x [residual block, ELU, strided conv k = 2r]; LSTM; ELU; conv(512 -> 128, k7)"""
+    t = [(0, "in", 1, 32, 7, 1)]
+    ch, idx = 32, 1
+    for r in _RATIOS:
+        t += [(idx, "res", ch, ch, 3, 1), (idx + 2, "down", ch, 2 * ch, 2 * r, r)]
+        ch, idx = 2 * ch, idx + 3
+    t.append((idx + 2, "out", ch, 128, 7, 1))
+    return t
+
+
+def effective_weight(sd: dict, prefix: str) -> torch.Tensor:
+    """torch.nn.utils.parametrizations.weight_norm (dim 0): w = g * v / ||v||, norm over every other dimension"""
+    if prefix + ".conv.weight" in sd:                           # 48 kHz model: plain weights + GroupNorm
+        return sd[prefix + ".conv.weight"]
+    g = sd[prefix + ".conv.parametrizations.weight.original0"]
+    v = sd[prefix + ".conv.parametrizations.weight.original1"]
+    return torch._weight_norm(v, g, 0)
 
 
 def _sconv(x, w, b, stride, causal=True):

@@ -222,3 +222,50 @@ def test_directory_flow_for_every_embedder_family(engine, tmp_path, name, second
         assert np.array_equal(e, one), (name, i)
     mu, cov = fk.FrechetAudioDistance(ml, load_model=False).load_stats(d)
     assert mu.shape == (ml.num_features,) and cov.shape == (ml.num_features, ml.num_features) and np.isfinite(cov).all()
+
+
+def test_baseline_config0_sine_vs_noise_one_second_clips(vgg_engine, vgg_state, tmp_path, monkeypatch):
+    """BASELINE.json configs[0]: VGGish FAD of 32 x 1 s sine tones vs 32 x 1 s white noise.  One second = exactly ONE
+    VGGish frame per file, so (a) the DIRECTORY path of the reference yields an all-NaN covariance (np.cov of one row,
+    fadtk/utils.py:16) and the score fails - mirrored; (b) the plumbing check is the CONCATENATED path
+    (calc_embd_statistics on the 32 x 128 matrix, rank <= 31: a singular product for fad.py:88-106), compared with
+    the reference-pinned oracle on the same embeddings and with the full CPU oracle."""
+    monkeypatch.delenv("FADTK_SINGLE_FRAME_FILES", raising=False)
+    sets = {"sine": [synth.sine_clip(i, 1.0, 16000) for i in range(32)],
+            "noise": [synth.noise_clip(i, 1.0, 16000) for i in range(32)]}
+    ml = fk.VGGishModel()
+    ml.load_model()
+    gpu = {k: ml.embed_pcm_batch(v) for k, v in sets.items()}
+    assert all(e.shape == (1, 128) and e.dtype == np.float16 for v in gpu.values() for e in v)
+
+    # (b) concatenated path
+    cat = {k: np.concatenate(v) for k, v in gpu.items()}
+    fad_gpu = fk.calc_frechet_distance(*fk.calc_embd_statistics(cat["sine"]), *fk.calc_embd_statistics(cat["noise"]))
+    fad_same = fo.frechet_distance(*fo.embd_statistics(cat["sine"]), *fo.embd_statistics(cat["noise"]))
+    assert fad_gpu == pytest.approx(fad_same, rel=1e-6)
+    cpu = {k: np.concatenate([vo.embed(vo.load_wav_semantics(c), vgg_state) for c in v]) for k, v in sets.items()}
+    fad_cpu = fo.frechet_distance(*fo.embd_statistics(cpu["sine"]), *fo.embd_statistics(cpu["noise"]))
+    print(f"config0: gpu {fad_gpu:.6f} oracle-on-gpu-embeddings {fad_same:.6f} cpu {fad_cpu:.6f} rel {abs(fad_gpu - fad_cpu) / fad_cpu:.2e}")
+    assert fad_gpu == pytest.approx(fad_cpu, rel=1e-3)            # 32 rows in 128-d: ill-posed, looser than the 1e-4 of real sizes
+
+    # (a) directory path: per-file caches with one row each
+    paths = {}
+    for k, v in gpu.items():
+        d = tmp_path / k / "embeddings" / "vggish"
+        d.mkdir(parents=True)
+        paths[k] = []
+        for i, e in enumerate(v):
+            np.save(d / f"clip{i:03d}.npy", e)
+            paths[k].append(d / f"clip{i:03d}.npy")
+    mu, cov = fk.calculate_embd_statistics_online(paths["sine"])
+    mu_ref, cov_ref = fo.online_statistics(gpu["sine"])
+    assert np.isnan(cov).all() and np.isnan(cov_ref).all()        # the reference's behaviour, utils.py:16
+    assert np.abs(mu - mu_ref).max() < 1e-12
+    fad = fk.FrechetAudioDistance(ml, audio_load_worker=2, load_model=False)
+    with pytest.raises(ValueError):                               # scipy's sqrtm refuses NaN input in the reference too (fad.py:88)
+        fad.score(tmp_path / "sine", tmp_path / "noise")
+    # extension: let single-frame files contribute their row -> the concatenated statistics
+    monkeypatch.setenv("FADTK_SINGLE_FRAME_FILES", "keep")
+    mu_k, cov_k = fk.calculate_embd_statistics_online(paths["sine"])
+    x = cat["sine"].astype(np.float64)
+    assert np.abs(mu_k - x.mean(0)).max() < 1e-12 and np.abs(cov_k - np.cov(x, rowvar=False)).max() < 1e-10 * np.abs(cov_k).max()

@@ -42,9 +42,21 @@ def test_logmel_matches_float64_numpy(engine, use_double):
 
 
 def test_conv1_matches_torch(vgg_engine, vgg_state):
-    # conv1 is reached through the full forward; check it indirectly via a 1-example forward of
-    # the first layer using the stage API is not exposed, so compare act through network test below
-    pass
+    """conv1 stage (CUDA-core fp32 stencil + bias + ReLU + 2x2 max-pool, fp16 NHWC out) vs torch fp32 on real
+    log-mel examples: the only error is the final fp16 rounding of the output."""
+    import torch.nn.functional as F
+    clips = _clips()[:2]
+    pcm, off = _flat(clips)
+    ex, _ = vgg_engine.vggish_plan(off)
+    dev = vgg_engine.torch_device
+    logmel = vgg_engine.vggish_logmel(torch.from_numpy(pcm).to(dev), torch.from_numpy(ex).to(dev), use_double=False)
+    got = vgg_engine.vggish_conv1(logmel.contiguous()).float().cpu()                 # [n, 48, 32, 64]
+    x = logmel.cpu().unsqueeze(1)                                                  # [n, 1, 96, 64]
+    want = F.max_pool2d(F.relu(F.conv2d(x, vgg_state["features.0.weight"], vgg_state["features.0.bias"], padding=1)), 2)
+    want = want.permute(0, 2, 3, 1).contiguous()                                   # NHWC
+    assert got.shape == want.shape
+    err = (got - want).abs().max().item()
+    assert err <= 2.0 ** -11 * want.abs().max().item() + 1e-6, f"conv1 max abs err {err}"
 
 
 LAYERS = [

@@ -451,3 +451,29 @@ def test_two_rank_file_sharding_and_rank0_statistics_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "rank0:ok" in out.stdout and "rank1:ok" in out.stdout, out.stdout
+
+
+def test_named_baseline_resolves_from_an_installed_reference_package(tmp_path, monkeypatch):
+    """`fadtk vggish fma_pop <dir>` must keep working after the switch.  The reference ships its
+    statistics as fadtk/stats/<name>.npz (fad.py:249-255); with that package importable its stats directory is searched
+    after $FADTK_STATS_DIR and this package's own stats/ directory."""
+    import importlib
+    from fadtk_b200 import fad as fad_mod
+    monkeypatch.delenv("FADTK_STATS_DIR", raising=False)
+    assert fad_mod._named_statistics("fma_pop") is None or fad_mod._named_statistics("fma_pop").name == "fma_pop.npz"
+    site = tmp_path / "site"
+    (site / "fadtk" / "stats").mkdir(parents=True)
+    (site / "fadtk" / "__init__.py").write_text("")
+    np.savez(site / "fadtk" / "stats" / "toy_pop.npz", **{"vggish.mu": np.arange(3.0), "vggish.cov": np.eye(3)})
+    monkeypatch.syspath_prepend(str(site))
+    importlib.invalidate_caches()
+    assert fad_mod._named_statistics("Toy_Pop") == site / "fadtk" / "stats" / "toy_pop.npz"
+
+    class _ML:
+        name = "vggish"
+    f = fad_mod.FrechetAudioDistance.__new__(fad_mod.FrechetAudioDistance)
+    f.ml = _ML()
+    mu, cov = f.load_stats("toy_pop")
+    np.testing.assert_array_equal(mu, np.arange(3.0))
+    with pytest.raises(SystemExit):                            # an unknown name: the reference's exit(1) (fad.py:276-278)
+        f.load_stats("no_such_set")
