@@ -69,6 +69,11 @@ SIGNATURES = {
     "fad_resample": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_batched": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_bench_dmma_peak": (C.c_int, [c_vp, C.c_int, c_vp]),
+    "fad_comm_unique_id": (C.c_int, [c_vp]),
+    "fad_comm_init": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int]),
+    "fad_comm_destroy": (C.c_int, [c_vp]),
+    "fad_stats_allreduce": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp]),
+    "fad_allreduce_sum_f64": (C.c_int, [c_vp, c_vp, c_vp, c_ll, c_vp]),
     "fad_launch_count": (c_ll, [c_vp]),
     "fad_profile_enable": (C.c_int, [c_vp, C.c_int]),
     "fad_profile_collect": (C.c_int, [c_vp, c_vp, c_vp, C.c_int]),
@@ -125,6 +130,7 @@ class Engine:
         _check(lib().fad_create(self.device, self.max_examples, C.byref(h)))
         self._h = h
         self._keep = []
+        self.has_comm = False     # fad_comm_init done: the statistics all-reduce goes through the C ABI
         self.owners = {}          # weight slot -> token of the loader whose weights it holds (model_loader._DeviceBatch)
 
     def close(self):
@@ -145,6 +151,26 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(lib().fad_launch_count(self._h))
+
+    # ------------------------------------------------------------ cross-GPU merge
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0: the 128-byte NCCL rendezvous id (fad_comm_unique_id)"""
+        buf = C.create_string_buffer(128)
+        _check(lib().fad_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """join the communicator of the C ABI (fad_comm_init); afterwards allreduce_sum_ runs through it"""
+        assert len(unique_id) == 128
+        _check(lib().fad_comm_init(self._h, C.create_string_buffer(unique_id, 128), int(rank), int(world)))
+        self.has_comm = True
+
+    def allreduce_sum_(self, buf: torch.Tensor) -> torch.Tensor:
+        """in-place sum of an fp64 cuda tensor over the ranks of the handle's communicator (fad_allreduce_sum_f64)"""
+        assert buf.dtype == torch.float64 and buf.is_cuda and buf.is_contiguous()
+        _check(lib().fad_allreduce_sum_f64(self._h, None, buf.data_ptr(), buf.numel(), _stream()))
+        return buf
 
     def dmma_peak_tflops(self, iters: int = 0) -> float:
         """measured fp64 tensor-pipe (DMMA) rate, TFLOP/s: roofline denominator of the fp64 kernels"""

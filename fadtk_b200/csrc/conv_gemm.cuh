@@ -87,15 +87,19 @@ constexpr uint32_t kStagingBytes = 32 * 128;       // per epilogue warp: 32 rows
 // rate and half the operand bytes of a second fp16 MMA - against an E4M3 copy of the activation
 // (written next to the fp16 one by the producing kernel, fetched by its own TMA box), into its own
 // TMEM accumulator that the epilogue adds with the power-of-two scale of the E4M3 weights.
-template <int N_TILE, int WMODE>
+// PAIR: two CTAs (one cluster, the two SMs of a TPC) share every MMA with cta_group::2 - M = 256, each CTA holds its
+// own 128-row A tile and HALF of the weight tile, so a stage carries half the weight bytes per CTA (the kernel is
+// bound by what each SM pulls from L2 per k-step, not by the tensor pipe: ncu, profiles/r2_ncu_conv_gemm_pair.md).
+template <int N_TILE, int WMODE, int PAIR = 0>
 __host__ __device__ constexpr uint32_t conv_gemm_stage_bytes() {
-    return WMODE == 2 ? kABytes + N_TILE * kBlockK * 2 + N_TILE * kBlockK + kTileM * kBlockK
-                      : kABytes + (WMODE == 1 ? 2 : 1) * N_TILE * kBlockK * 2;
+    constexpr int kNLoc = PAIR ? N_TILE / 2 : N_TILE;
+    return WMODE == 2 ? kABytes + kNLoc * kBlockK * 2 + kNLoc * kBlockK + kTileM * kBlockK
+                      : kABytes + (WMODE == 1 ? 2 : 1) * kNLoc * kBlockK * 2;
 }
 
-template <int N_TILE, int STAGES, int WMODE>
+template <int N_TILE, int STAGES, int WMODE, int PAIR = 0>
 __host__ __device__ constexpr uint32_t conv_gemm_smem_bytes() {
-    return STAGES * conv_gemm_stage_bytes<N_TILE, WMODE>() + 1024 /*align slack*/ + 256 /*barriers*/
+    return STAGES * conv_gemm_stage_bytes<N_TILE, WMODE, PAIR>() + 1024 /*align slack*/ + 256 /*barriers*/
          + kEpilogueWarps * kStagingBytes;
 }
 
@@ -139,7 +143,7 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int N_TILE, int STAGES, int WMODE>
+template <int N_TILE, int STAGES, int WMODE, int PAIR = 0>
 __global__ void __launch_bounds__(kConvGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                  const __grid_constant__ CUtensorMap map_w,
@@ -150,14 +154,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     using namespace sm100;
     constexpr bool SPLIT_W = WMODE == 1;
     constexpr bool LO8 = WMODE == 2;
-    constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE, WMODE>();
+    constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE, WMODE, PAIR>();
     constexpr int kBRows = (WMODE != 0 ? 2 : 1) * N_TILE;           // rows of the packed weight tensor per N tile
+    constexpr int kNLoc = PAIR ? N_TILE / 2 : N_TILE;               // weight rows (output channels) THIS CTA stages
     constexpr uint32_t kTmemCols = (LO8 ? 4 : 2) * N_TILE;          // two chunk buffers (+ two low-part buffers)
-    constexpr uint32_t kIdesc = make_idesc(FMT_F16, kTileM, N_TILE);
-    constexpr uint32_t kIdesc8 = make_idesc(FMT_E4M3, kTileM, N_TILE);
-    constexpr uint32_t kWhBytes = N_TILE * kBlockK * 2;
+    constexpr uint32_t kIdesc = make_idesc(FMT_F16, PAIR ? 2 * kTileM : kTileM, N_TILE);
+    constexpr uint32_t kIdesc8 = make_idesc(FMT_E4M3, PAIR ? 2 * kTileM : kTileM, N_TILE);
+    constexpr uint32_t kWhBytes = kNLoc * kBlockK * 2;
     constexpr uint32_t kOffWl8 = kABytes + kWhBytes;                // stage layout (LO8): A16 | Wh | Wl8 | A8
-    constexpr uint32_t kOffA8 = kOffWl8 + N_TILE * kBlockK;
+    constexpr uint32_t kOffA8 = kOffWl8 + kNLoc * kBlockK;
+    static_assert(!PAIR || WMODE != 0, "pairs are built for the split-weight modes");
     constexpr int kColsPerWarp = N_TILE / 2;            // each lane quarter is shared by two warps
     constexpr int kGroups = kColsPerWarp / 32;
 
@@ -178,7 +184,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     const int n_chunks = (ksteps + kChunkSteps - 1) / kChunkSteps;
     const int chunk_len = (ksteps + n_chunks - 1) / n_chunks;       // balanced chunks
     const int m_tiles = p.img_groups * p.tiles_h * p.tiles_w;
-    const int total_tiles = m_tiles * p.n_tiles;
+    // work unit = one N tile x (one M tile | PAIR: two consecutive M tiles, one per CTA of the pair; the second of an
+    // odd count is past the batch: its TMA boxes are zero-filled and its rows masked in the epilogue)
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    const int n_workers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+    const int worker = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+    const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+    const int total_tiles = m_units * p.n_tiles;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_x);
@@ -187,13 +199,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpilogueWarps); }
-        for (int a = 0; a < 2; ++a) mbar_init(&corr_empty[a], kEpilogueWarps);
+        // PAIR: the leader's tmem_empty / corr_empty collect the epilogue warps of BOTH CTAs
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpilogueWarps * (PAIR ? 2 : 1)); }
+        for (int a = 0; a < 2; ++a) mbar_init(&corr_empty[a], kEpilogueWarps * (PAIR ? 2 : 1));
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_base_slot);
+    if (warp == 2) { if (PAIR) tmem_alloc_pair<kTmemCols>(tmem_base_slot); else tmem_alloc<kTmemCols>(tmem_base_slot); }
     tc_fence_before_sync();
-    __syncthreads();
+    if (PAIR) cluster_sync(); else __syncthreads();           // PAIR: the peer's barriers exist before anything signals them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -205,9 +218,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
         // ------------------------------------------------------------ TMA producer
         if (elect_one()) {
             int s = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < total_tiles; tile += n_workers) {
                 const int nt = tile % p.n_tiles;
-                const int m = tile / p.n_tiles;
+                const int m = PAIR ? 2 * (tile / p.n_tiles) + (int)rank : tile / p.n_tiles;
                 const int w0 = (m % p.tiles_w) * p.box_w;
                 const int h0 = ((m / p.tiles_w) % p.tiles_h) * p.box_h;
                 const int n0 = (m / (p.tiles_w * p.tiles_h)) * p.box_n;
@@ -217,25 +230,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     int dh = 0, dw = 0;
                     if (p.taps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], kStageBytes);
                     uint8_t* st = smem + s * kStageBytes;
+                    if (PAIR) {
+                        // both CTAs' bytes land on the LEADER's barrier (the MMA issuer waits there); a peer's bytes may
+                        // complete before the leader arms the phase - the transaction count is signed, that is fine
+                        if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);
+                        const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+                        tma_load_4d_pair(st, &map_x, bar, cb * kBlockK, w0 + dw, h0 + dh, n0);
+                        tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * kNLoc);
+                        if (SPLIT_W)
+                            tma_load_2d_pair(st + kABytes + kWhBytes, &map_w, bar, ks * kBlockK, nt * kBRows + N_TILE + (int)rank * kNLoc);
+                        if (LO8) {
+                            tma_load_2d_pair(st + kOffWl8, &map_wl8, bar, ks * kBlockK, nt * N_TILE + (int)rank * kNLoc);
+                            tma_load_4d_pair(st + kOffA8, &map_x8, bar, cb * kBlockK, w0 + dw, h0 + dh, n0);
+                        }
+                    } else {
+                    mbar_expect_tx(&full[s], kStageBytes);
                     tma_load_4d(st, &map_x, &full[s], cb * kBlockK, w0 + dw, h0 + dh, n0);
                     tma_load_2d(st + kABytes, &map_w, &full[s], ks * kBlockK, nt * kBRows);
                     if (LO8) {
                         tma_load_2d(st + kOffWl8, &map_wl8, &full[s], ks * kBlockK, nt * N_TILE);
                         tma_load_4d(st + kOffA8, &map_x8, &full[s], cb * kBlockK, w0 + dw, h0 + dh, n0);
                     }
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
-      } else if (warp == 1) {
-        // -------------------------------------------------------------- MMA issuer
+      } else if (warp == 1 && rank == 0) {
+        // -------------------------------------------------------------- MMA issuer (PAIR: the leader CTA only)
         if (elect_one()) {
             int s = 0; uint32_t ph = 0;
             int buf = 0; uint32_t buf_ph = 0;
             int cpar = 0; uint32_t cpar_ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < total_tiles; tile += n_workers) {
                 const uint32_t d_corr = tmem_base + 2 * N_TILE + cpar * N_TILE;
                 if (LO8) { mbar_wait(&corr_empty[cpar], cpar_ph ^ 1); tc_fence_after_sync(); }
                 for (int ks0 = 0; ks0 < ksteps; ks0 += chunk_len) {
@@ -252,21 +280,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             // +32 B along K inside the 128-B swizzle atom == +2 in the 16-B address field
+                            if (PAIR) {
+                                umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
+                                if (SPLIT_W) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k + (kNLoc * 128 / 16), kIdesc, 1);
+                            } else {
                             umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
                             if (SPLIT_W)      // lo half of the weights: N_TILE rows (x 128 B) further down the stage
                                 umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k + (N_TILE * 128 / 16), kIdesc, 1);
+                            }
                         }
                         if (LO8) {
                             const uint64_t a8_desc = kmajor_sw64_desc(a_addr + kOffA8);
                             const uint64_t w8_desc = kmajor_sw64_desc(a_addr + kOffWl8);
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 32; ++k)   // K = 32 per kind::f8f6f4 MMA, +32 B inside the 64-B atom
-                                umma_f8(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, (ks > 0) || (k > 0));
+                            for (int k = 0; k < kBlockK / 32; ++k) { // K = 32 per kind::f8f6f4 MMA, +32 B inside the 64-B atom
+                                if (PAIR) umma_f8_pair(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, (ks > 0) || (k > 0));
+                                else      umma_f8(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, (ks > 0) || (k > 0));
+                            }
                         }
-                        umma_commit(&empty[s]);           // smem slot free once these MMAs retire
+                        if (PAIR) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);   // smem slot(s) free once these MMAs retire
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(&tmem_full[buf]);         // chunk complete -> epilogue warps
+                    if (PAIR) umma_commit_pair(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);   // chunk complete -> epilogue warps
                     if (++buf == 2) { buf = 0; buf_ph ^= 1; }
                 }
                 if (++cpar == 2) { cpar = 0; cpar_ph ^= 1; }
@@ -287,8 +322,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
         int cpar = 0;
         // plain row-major GEMM (1x1 "image", 128 rows per tile): no per-tile divisions
         const bool plain = p.tiles_w == 1 && p.tiles_h == 1 && bw == 1 && bh == 1;
-        int nt = blockIdx.x % p.n_tiles, m = blockIdx.x / p.n_tiles;
-        const int step_nt = gridDim.x % p.n_tiles, step_m = gridDim.x / p.n_tiles;
+        // (nt, mu) of this worker's current unit, stepped without divisions; m = the M tile of THIS CTA
+        int nt = worker % p.n_tiles, mu = worker / p.n_tiles;
+        const int step_nt = n_workers % p.n_tiles, step_m = n_workers / p.n_tiles;
+        int m = PAIR ? 2 * mu + (int)rank : mu;
+        const uint32_t te_addr[2] = {PAIR ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u, PAIR ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u};
+        const uint32_t ce_addr[2] = {PAIR ? mapa_u32(smem_u32(&corr_empty[0]), 0) : 0u, PAIR ? mapa_u32(smem_u32(&corr_empty[1]), 0) : 0u};
         // residual rows are read-modify-written in the epilogue: pull the NEXT tile's rows into L2
         // while this tile is computed, so the loads do not pay HBM latency on the critical path
         auto prefetch_resid = [&](int nt_, int m_) {
@@ -300,8 +339,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             for (int c = c0; c < c0 + kColsPerWarp && c < p.resid_C; c += 32)
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(p.resid + tok * p.resid_C + c));
         };
-        if (blockIdx.x < total_tiles) prefetch_resid(nt, m);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (worker < total_tiles) prefetch_resid(nt, m);
+        for (int tile = worker; tile < total_tiles; tile += n_workers) {
             int w, h, n;
             if (plain) { w = 0; h = 0; n = m * kTileM + r; }
             else {
@@ -310,9 +349,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 n = (m / (p.tiles_w * p.tiles_h)) * p.box_n + pn;
             }
             const bool valid = n < p.NB;
-            int nt_next = nt + step_nt, m_next = m + step_m;
-            if (nt_next >= p.n_tiles) { nt_next -= p.n_tiles; ++m_next; }
-            if (tile + (int)gridDim.x < total_tiles) prefetch_resid(nt_next, m_next);
+            int nt_next = nt + step_nt, mu_next = mu + step_m;
+            if (nt_next >= p.n_tiles) { nt_next -= p.n_tiles; ++mu_next; }
+            const int m_next = PAIR ? 2 * mu_next + (int)rank : mu_next;
+            if (tile + n_workers < total_tiles) prefetch_resid(nt_next, m_next);
 
             // sum the K chunks in registers (round-to-nearest adds)
             float acc[kColsPerWarp];
@@ -342,8 +382,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&tmem_empty[buf]);
-                    if (LO8 && c == n_chunks - 1) mbar_arrive(&corr_empty[cpar]);
+                    if (PAIR) {                               // the leader's MMA warp waits for both CTAs' drains
+                        mbar_arrive_cluster(te_addr[buf]);
+                        if (LO8 && c == n_chunks - 1) mbar_arrive_cluster(ce_addr[cpar]);
+                    } else {
+                        mbar_arrive(&tmem_empty[buf]);
+                        if (LO8 && c == n_chunks - 1) mbar_arrive(&corr_empty[cpar]);
+                    }
                 }
                 if (++buf == 2) { buf = 0; buf_ph ^= 1; }
             }
@@ -487,13 +532,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     }
                 }
             }
-            nt = nt_next; m = m_next;
+            nt = nt_next; mu = mu_next; m = m_next;
         }
     }
 
     tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
+    if (PAIR) cluster_sync(); else __syncthreads();           // PAIR: neither CTA may exit while the other still signals it
+    if (warp == 2) { if (PAIR) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base); }
 }
 
 }  // namespace fad

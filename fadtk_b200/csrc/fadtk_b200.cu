@@ -82,6 +82,7 @@ struct LayerGeom {
     int box_w, box_h, box_n, n_tile;
     int split_w;      // 0: fp16 weights; 1: fp16 hi/lo pair (interleaved per 128-row tile), two fp16 MMAs;
                       // 2: same packed tensor, low part applied as E4M3 (kind::f8f6f4) - see conv_gemm.cuh
+    int pair;         // 1: CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile)
 };
 
 // how the low part of split weights is applied: FADTK_WLO=fp16 (two fp16 MMAs) | fp8 (E4M3 correction MMA)
@@ -89,10 +90,16 @@ int wlo_mode() {
     static const int mode = [] { const char* e = getenv("FADTK_WLO"); return (e && std::string(e) == "fp8") ? 2 : 1; }();
     return mode;
 }
+// CTA pairs for the VGGish layers: FADTK_PAIR=0 | 1
+int pair_mode() {
+    static const int mode = [] { const char* e = getenv("FADTK_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
+    return mode;
+}
 
 int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu, int pool, int split_w) {
     g.taps = taps; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.relu = relu; g.pool = pool;
     g.split_w = split_w;                     // 0, 1 or 2 - the caller decides (wlo_mode() for the VGGish pipeline)
+    g.pair = 0;                              // set by the caller after make_geom (split modes only)
     if (Cin % 64 != 0) return fail("Cin must be a multiple of 64");
     if (taps != 1 && taps != 9) return fail("taps must be 1 or 9");
     if (H == 1 && W == 1) { g.box_w = 1; g.box_h = 1; g.box_n = 128; }
@@ -158,6 +165,8 @@ struct fad_handle {
     std::map<const void*, Lo8> lo8;          // E4M3 low parts per packed weight tensor (built on first use)
     double* fr_scal = nullptr;   // 32 doubles
 
+    void* nccl_comm = nullptr;   // ncclComm_t created by fad_comm_init (NCCL is dlopen'ed, never linked)
+
     void* clap_state = nullptr;  // ClapState (clap_host.inc)
     void* whisper_state = nullptr;   // WhisperState (whisper_host.inc)
     void* encodec_state = nullptr;   // EncodecState (encodec_host.inc)
@@ -175,20 +184,34 @@ struct fad_handle {
 
 namespace {
 
-template <int N_TILE, int STAGES, int WMODE>
+template <int N_TILE, int STAGES, int WMODE, int PAIR = 0>
 int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mw8,
                      const CUtensorMap& mx8, const fad::ConvGemmParams& p, cudaStream_t st) {
     static bool attr_set = false;
-    constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES, WMODE>();
-    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, WMODE>;
+    constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES, WMODE, PAIR>();
+    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, WMODE, PAIR>;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int total = p.img_groups * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int m_tiles = p.img_groups * p.tiles_h * p.tiles_w;
+    const int total = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;           // work units (PAIR: two M tiles each)
     if (total == 0) return 0;
-    const int grid = total < h->num_sms ? total : h->num_sms;
-    kern<<<grid, fad::kConvGemmThreads, smem, st>>>(mx, mw, mw8, mx8, p);
+    if (PAIR) {
+        // one cluster of two CTAs per unit in flight: the pair lands on the two SMs of a TPC
+        const int pairs = total < h->num_sms / 2 ? total : h->num_sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(fad::kConvGemmThreads);
+        cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, kern, mx, mw, mw8, mx8, p));
+    } else {
+        const int grid = total < h->num_sms ? total : h->num_sms;
+        kern<<<grid, fad::kConvGemmThreads, smem, st>>>(mx, mw, mw8, mx8, p);
+    }
     CK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -210,11 +233,14 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
     const uint64_t rows_mul = g.split_w ? 2 : 1;
     const uint64_t wd[2] = {K, (uint64_t)g.Cout * rows_mul};
     const uint64_t ws[1] = {K * 2};
-    const uint32_t wb[2] = {64, (uint32_t)(g.n_tile * (g.split_w == 1 ? 2 : 1))};   // mode 2 fetches the hi rows only
+    // rows per weight box: mode 1 fetches hi + lo of a tile at once, mode 2 the hi rows only; a CTA of a pair fetches
+    // its half of the hi rows and its half of the lo rows as two boxes
+    const uint32_t wb[2] = {64, (uint32_t)(g.pair ? g.n_tile / 2 : g.n_tile * (g.split_w == 1 ? 2 : 1))};
     return encode_f16_map(mw, w, 2, wd, ws, wb);
 }
 
 int lo8_for(fad_handle* h, const LayerGeom& g, const void* w, CUtensorMap* mw8, float* inv_scale, cudaStream_t st);
+
 // the E4M3 low parts are cached per weight POINTER: drop the entry whenever that memory is rewritten
 void lo8_forget(fad_handle* h, const void* w) {
     auto it = h->lo8.find(w);
@@ -256,8 +282,10 @@ int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CU
         if (mx8 == nullptr) return fail("fp8 low-part mode needs the E4M3 copy of the activation");
         CUtensorMap mw8;
         if (lo8_for(h, g, w, &mw8, &p.lo_scale, st)) return 1;
+        if (g.pair) return launch_conv_gemm<128, 5, 2, 1>(h, mx, mw, mw8, *mx8, p, st);
         return launch_conv_gemm<128, 4, 2>(h, mx, mw, mw8, *mx8, p, st);
     }
+    if (g.split_w && g.pair) return launch_conv_gemm<128, 6, 1, 1>(h, mx, mw, mw, mx, p, st);
     if (g.split_w) return launch_conv_gemm<128, 4, 1>(h, mx, mw, mw, mx, p, st);
     if (g.n_tile == 256) return launch_conv_gemm<256, 4, 0>(h, mx, mw, mw, mx, p, st);
     return launch_conv_gemm<128, 6, 0>(h, mx, mw, mw, mx, p, st);
@@ -320,7 +348,7 @@ int lo8_for(fad_handle* h, const LayerGeom& g, const void* w, CUtensorMap* mw8, 
     if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)(n_tiles * 128)};
     cuuint64_t gstr[1] = {(cuuint64_t)K};
-    cuuint32_t bdim[2] = {64, 128}, estr[2] = {1, 1};
+    cuuint32_t bdim[2] = {64, (cuuint32_t)(g.pair ? 64 : 128)}, estr[2] = {1, 1};
     CUresult r = fn(mw8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, it->second.w8, gdim, gstr, bdim, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -471,6 +499,7 @@ static void w2v_free_state(void* p);
 int fad_destroy(fad_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    fad_comm_destroy(h);
     clap_free_state(h->clap_state);
     whisper_free_state(h->whisper_state);
     encodec_free_state(h->encodec_state);
@@ -525,6 +554,7 @@ int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
     for (int i = 0; i < 8; ++i) {
         const VggLayer& L = kVgg[i];
         if (make_geom(h->geom[i], L.H, L.W, L.Cin, L.Cout, L.taps, L.relu, L.pool, ((w->split_mask >> i) & 1) ? wlo_mode() : 0)) return 1;
+        h->geom[i].pair = (h->geom[i].split_w && pair_mode()) ? 1 : 0;
         const void* wptr = i < 5 ? (const void*)h->conv_w[i] : (const void*)h->fc_w[i - 5];
         if (encode_layer_maps(h->geom[i], h->act[i], (long long)B, wptr, &h->map_x[i], &h->map_w[i])) return 1;
         if (h->geom[i].split_w == 2) {
@@ -636,6 +666,7 @@ int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int C
     CK(cudaSetDevice(h->device));
     LayerGeom g;
     if (make_geom(g, H, W, Cin, Cout, taps, relu, pool, split_w)) return 1;
+    g.pair = (g.split_w && pair_mode()) ? 1 : 0;
     if (pool && out_f32_or_null) return fail("fp32 copy is only available for un-pooled layers");
     CUtensorMap mx, mw, mx8;
     if (encode_layer_maps(g, x_f16, NB, w_f16, &mx, &mw)) return 1;
@@ -817,6 +848,99 @@ extern "C" int fad_bench_dmma_peak(fad_handle* h, int iters, double* tflops_out_
     h->launches += 2;
     return 0;
 }
+
+// ------------------------------------------------------------------- cross-GPU statistics merge
+// The one exchange step of the path: all-reduce(sum) of the packed fp64 accumulator over
+// NVLink.  NCCL is resolved at run time with dlopen (the process usually has torch's libnccl.so.2 mapped already;
+// $FADTK_NCCL_LIB overrides) so the library keeps loading on hosts without NCCL and links nothing but the C++ runtime.
+#include <dlfcn.h>
+namespace {
+struct NcclId { char bytes[128]; };
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char* env = getenv("FADTK_NCCL_LIB");
+        const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+        void* lib = nullptr;
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { a.why = "libnccl.so.2 not found (set FADTK_NCCL_LIB)"; return a; }
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+        if (!a.ok) a.why = "NCCL library lacks an expected symbol";
+        return a;
+    }();
+    return api;
+}
+int nccl_fail(const char* what, int rc) {
+    return fail(std::string(what) + ": " + (nccl_api().GetErrorString ? nccl_api().GetErrorString(rc) : "NCCL error"));
+}
+}  // namespace
+
+extern "C" {
+int fad_comm_unique_id(void* id_out_host) {
+    if (!id_out_host) return fail("null argument");
+    NcclApi& n = nccl_api();
+    if (!n.ok) return fail(n.why);
+    NcclId id;
+    const int rc = n.GetUniqueId(&id);
+    if (rc != 0) return nccl_fail("ncclGetUniqueId", rc);
+    memcpy(id_out_host, id.bytes, sizeof id.bytes);
+    return 0;
+}
+
+int fad_comm_init(fad_handle* h, const void* id_host, int rank, int world) {
+    if (!h || !id_host) return fail("null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank / world size");
+    NcclApi& n = nccl_api();
+    if (!n.ok) return fail(n.why);
+    CK(cudaSetDevice(h->device));
+    if (h->nccl_comm) { n.CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+    NcclId id;
+    memcpy(id.bytes, id_host, sizeof id.bytes);
+    const int rc = n.CommInitRank(&h->nccl_comm, world, id, rank);
+    if (rc != 0) { h->nccl_comm = nullptr; return nccl_fail("ncclCommInitRank", rc); }
+    return 0;
+}
+
+int fad_comm_destroy(fad_handle* h) {
+    if (h && h->nccl_comm) { nccl_api().CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+    return 0;
+}
+
+int fad_allreduce_sum_f64(fad_handle* h, void* nccl_comm_or_null, double* buf, long long n_values, void* stream) {
+    if (!h || !buf) return fail("null argument");
+    void* comm = nccl_comm_or_null ? nccl_comm_or_null : h->nccl_comm;
+    if (!comm) return fail("no communicator: call fad_comm_init or pass an ncclComm_t");
+    NcclApi& n = nccl_api();
+    if (!n.ok) return fail(n.why);
+    CK(cudaSetDevice(h->device));
+    const int rc = n.AllReduce(buf, buf, (size_t)n_values, /*ncclFloat64*/ 8, /*ncclSum*/ 0, comm, (cudaStream_t)stream);
+    if (rc != 0) return nccl_fail("ncclAllReduce", rc);
+    return 0;
+}
+
+int fad_stats_allreduce(fad_handle* h, void* nccl_comm_or_null, double* acc, int d, void* stream) {
+    if (d <= 0) return fail("bad dimension");
+    return fad_allreduce_sum_f64(h, nccl_comm_or_null, acc, (long long)fad_stats_acc_len(d), stream);
+}
+}  // extern "C"
 
 // ----------------------------------------------------------------------------- Frechet
 namespace {

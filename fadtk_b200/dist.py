@@ -57,9 +57,33 @@ def shard(items, r: int | None = None, w: int | None = None):
     return items[start:start + base + (1 if r < extra else 0)]
 
 
+_native_engine = None
+
+
+def enable_native_allreduce(engine) -> bool:
+    """Create the C ABI's own NCCL communicator (include/fadtk_b200.h: fad_comm_unique_id / fad_comm_init) for this
+    process group and route the statistics all-reduce through it, so that the one collective of the path runs behind
+    the boundary a non-Python host binds - torch.distributed only ships the 128-byte rendezvous id.  No-op (False)
+    single-process, on the gloo backend (CPU tests), or with FADTK_NATIVE_ALLREDUCE=0."""
+    global _native_engine
+    if not is_distributed() or td.get_backend() != "nccl" or os.environ.get("FADTK_NATIVE_ALLREDUCE", "1") == "0":
+        return False
+    if _native_engine is engine and engine.has_comm:
+        return True
+    uid = broadcast_object(engine.comm_unique_id() if rank() == 0 else None)
+    engine.comm_init(uid, rank(), world_size())
+    _native_engine = engine
+    return True
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if is_distributed():
-        td.all_reduce(t, op=td.ReduceOp.SUM)
+        eng = _native_engine
+        if (eng is not None and eng.has_comm and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+                and t.device.index == eng.device):
+            eng.allreduce_sum_(t)                             # ncclAllReduce on the current stream, through the C ABI
+        else:
+            td.all_reduce(t, op=td.ReduceOp.SUM)
     return t
 
 

@@ -68,6 +68,7 @@ class EvalSetFAD:
         self._staging = None
         self._plans = {}
         self._baseline = None
+        dist.enable_native_allreduce(self.eng)               # multi-GPU: the statistics all-reduce runs through the C ABI
 
     def _plan(self, n_clips: int):
         if n_clips not in self._plans:

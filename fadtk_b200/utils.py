@@ -77,6 +77,7 @@ class DeviceStatistics:
     def allreduce(self):
         """Sum the packed accumulator over all ranks (NCCL over NVLink); no-op single-process."""
         from . import dist
+        dist.enable_native_allreduce(self.eng)               # the C ABI's own NCCL communicator when running on GPUs
         dist.allreduce_sum_(self.acc)
 
     def count(self) -> int:

@@ -175,6 +175,24 @@ size_t fad_stats_acc_len(int d);
  * tensor_core = 2: the same exact arithmetic on the CUDA cores (DFMA + fp64 atomics): verification. */
 int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, int d,
                          const void* shift_f16, double* acc, int tensor_core, void* stream);
+/* ---- multi-GPU: the ONE exchange step of the path ----------
+ * Ranks embed disjoint shards of the clips and accumulate with the SAME shift vector; the packed accumulators are
+ * then summed over NVLink and every rank finalises identical statistics.  The reference has no counterpart (it is
+ * single-device); this replaces the pickled per-file scatter matrices of its process map (fadtk/utils.py:35-45).
+ * NCCL is loaded at run time (dlopen of libnccl.so.2, or $FADTK_NCCL_LIB); nothing is linked.
+ *   fad_comm_unique_id   rank 0 creates the 128-byte rendezvous id (ncclGetUniqueId); the host ships it to the
+ *                        other ranks however it likes (file, MPI, torch.distributed, a socket)
+ *   fad_comm_init        every rank joins; the communicator belongs to the handle
+ *   fad_stats_allreduce  in-place sum of acc[fad_stats_acc_len(d)] on `stream`; nccl_comm_or_null = an existing
+ *                        ncclComm_t of the host application, or NULL for the handle's own communicator
+ *   fad_allreduce_sum_f64  the same for any fp64 device buffer (e.g. both datasets packed into one call) */
+#define FAD_COMM_ID_BYTES 128
+int fad_comm_unique_id(void* id_out_host);
+int fad_comm_init(fad_handle* h, const void* id_host, int rank, int world);
+int fad_comm_destroy(fad_handle* h);
+int fad_stats_allreduce(fad_handle* h, void* nccl_comm_or_null, double* acc, int d, void* stream);
+int fad_allreduce_sum_f64(fad_handle* h, void* nccl_comm_or_null, double* buf, long long n_values, void* stream);
+
 /* rows emb[idx[i]] for i < n_idx (FAD-inf bootstrap, fadtk/fad.py:333-336) */
 int fad_stats_accumulate_gather(fad_handle* h, const void* emb_f16, long long n_src_rows,
                                 const long long* idx, long long n_idx, int d,
