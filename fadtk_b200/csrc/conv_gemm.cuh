@@ -40,6 +40,7 @@ struct ConvGemmParams {
     int n_tiles;               // Cout / N_TILE
     int H, W, NB, Cout;
     float lo_scale;            // WMODE 2: 2^-s of the E4M3 low parts
+    int lo8_group;             // WMODE 2: k-steps whose E4M3 MMAs are issued together (1 .. min(4, STAGES - 2))
     int ld_out, n_valid;       // un-pooled outputs: row stride and number of columns actually stored
                                // (Cout is padded to the tile width; columns >= n_valid are dropped)
     int relu, pool;            // relu: 0 = none, 1 = ReLU, 2 = GELU (erf form), 3 = ELU
@@ -263,6 +264,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             int s = 0; uint32_t ph = 0;
             int buf = 0; uint32_t buf_ph = 0;
             int cpar = 0; uint32_t cpar_ph = 0;
+            int pend_stage[4] = {0, 0, 0, 0}; bool pend_first[4] = {false, false, false, false}; int n_pend = 0;
             for (int tile = worker; tile < total_tiles; tile += n_workers) {
                 const uint32_t d_corr = tmem_base + 2 * N_TILE + cpar * N_TILE;
                 if (LO8) { mbar_wait(&corr_empty[cpar], cpar_ph ^ 1); tc_fence_after_sync(); }
@@ -290,15 +292,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                             }
                         }
                         if (LO8) {
-                            const uint64_t a8_desc = kmajor_sw64_desc(a_addr + kOffA8);
-                            const uint64_t w8_desc = kmajor_sw64_desc(a_addr + kOffWl8);
+                            // The E4M3 low-part MMAs of the last `lo8_group` k-steps are issued together, after their
+                            // fp16 MMAs: alternating kind::f16 / kind::f8f6f4 every k-step drains the tensor pipe at
+                            // each switch (ncu: tensor pipe 58-71 % with per-k-step alternation, r2_ncu_wlo8).  A stage
+                            // is released once BOTH its MMAs have been issued, so a group holds `lo8_group` stages.
+                            pend_stage[n_pend] = s; pend_first[n_pend] = (ks == 0); ++n_pend;
+                            if (n_pend == p.lo8_group || ks == ks1 - 1) {
+                                for (int q = 0; q < n_pend; ++q) {
+                                    const uint32_t q_addr = smem_u32(smem + pend_stage[q] * kStageBytes);
+                                    const uint64_t a8_desc = kmajor_sw64_desc(q_addr + kOffA8);
+                                    const uint64_t w8_desc = kmajor_sw64_desc(q_addr + kOffWl8);
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 32; ++k) { // K = 32 per kind::f8f6f4 MMA, +32 B inside the 64-B atom
-                                if (PAIR) umma_f8_pair(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, (ks > 0) || (k > 0));
-                                else      umma_f8(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, (ks > 0) || (k > 0));
+                                    for (int k = 0; k < kBlockK / 32; ++k) { // K = 32 per kind::f8f6f4 MMA, +32 B inside the 64-B atom
+                                        if (PAIR) umma_f8_pair(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, !pend_first[q] || (k > 0));
+                                        else      umma_f8(d_corr, a8_desc + 2 * k, w8_desc + 2 * k, kIdesc8, !pend_first[q] || (k > 0));
+                                    }
+                                    if (PAIR) umma_commit_pair(&empty[pend_stage[q]]); else umma_commit(&empty[pend_stage[q]]);
+                                }
+                                n_pend = 0;
                             }
+                        } else {
+                            if (PAIR) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);   // smem slot(s) free once these MMAs retire
                         }
-                        if (PAIR) umma_commit_pair(&empty[s]); else umma_commit(&empty[s]);   // smem slot(s) free once these MMAs retire
                         if (++s == STAGES) { s = 0; ph ^= 1; }
                     }
                     if (PAIR) umma_commit_pair(&tmem_full[buf]); else umma_commit(&tmem_full[buf]);   // chunk complete -> epilogue warps

@@ -90,10 +90,22 @@ int wlo_mode() {
     static const int mode = [] { const char* e = getenv("FADTK_WLO"); return (e && std::string(e) == "fp8") ? 2 : 1; }();
     return mode;
 }
-// CTA pairs for the VGGish layers: FADTK_PAIR=0 | 1
-int pair_mode() {
-    static const int mode = [] { const char* e = getenv("FADTK_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
-    return mode;
+// CTA pairs (cta_group::2) per VGGish tensor-core layer, bit i = conv2, conv3_1, conv3_2, conv4_1, conv4_2, fc1, fc2, fc3.
+// FADTK_PAIR = auto (default) | 0 | 1 (every layer) | 0x<mask>.  auto = the layers where the pair measured faster
+// (profiles/r2_bench_pair_*.json): K >= 2304 convolutions and the FC layers; conv2 / conv3_1 (K = 576 / 1152, epilogue-
+// heavy: one output tile per 9 / 18 k-steps) lose a little to the lock-step of two SMs and stay single-CTA.
+unsigned pair_mask() {
+    static const unsigned mask = [] {
+        const char* e = getenv("FADTK_PAIR");
+        if (!e || std::string(e) == "auto") return 0x7Cu;
+        if (std::string(e) == "1") return 0xFFu;
+        return (unsigned)strtoul(e, nullptr, 0) & 0xFFu;
+    }();
+    return mask;
+}
+int pair_all() {                    // stage-test entry (fad_umma_layer): pairs only when explicitly forced on
+    const char* e = getenv("FADTK_PAIR");
+    return (e && std::string(e) == "1") ? 1 : 0;
 }
 
 int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu, int pool, int split_w) {
@@ -278,6 +290,11 @@ int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CU
     p.bias = bias; p.out = reinterpret_cast<__half*>(out); p.out_f32 = out_f32; p.out8 = out8;
     p.resid = resid; p.resid_C = resid_C; p.resid_res = resid_res; p.resid_shift = resid_shift;
     p.lo_scale = 0.0f;
+    p.lo8_group = 1;
+    {
+        static const int grp = [] { const char* e = getenv("FADTK_LO8_GROUP"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 3 ? 3 : v); }();
+        p.lo8_group = grp;                                 // <= STAGES - 2 so the producer always has a stage to fill
+    }
     if (g.split_w == 2) {
         if (mx8 == nullptr) return fail("fp8 low-part mode needs the E4M3 copy of the activation");
         CUtensorMap mw8;
@@ -554,7 +571,7 @@ int fad_vggish_load(fad_handle* h, const fad_vggish_weights* w) {
     for (int i = 0; i < 8; ++i) {
         const VggLayer& L = kVgg[i];
         if (make_geom(h->geom[i], L.H, L.W, L.Cin, L.Cout, L.taps, L.relu, L.pool, ((w->split_mask >> i) & 1) ? wlo_mode() : 0)) return 1;
-        h->geom[i].pair = (h->geom[i].split_w && pair_mode()) ? 1 : 0;
+        h->geom[i].pair = (h->geom[i].split_w && ((pair_mask() >> i) & 1)) ? 1 : 0;
         const void* wptr = i < 5 ? (const void*)h->conv_w[i] : (const void*)h->fc_w[i - 5];
         if (encode_layer_maps(h->geom[i], h->act[i], (long long)B, wptr, &h->map_x[i], &h->map_w[i])) return 1;
         if (h->geom[i].split_w == 2) {
@@ -666,7 +683,7 @@ int fad_umma_layer(fad_handle* h, const void* x_f16, int NB, int H, int W, int C
     CK(cudaSetDevice(h->device));
     LayerGeom g;
     if (make_geom(g, H, W, Cin, Cout, taps, relu, pool, split_w)) return 1;
-    g.pair = (g.split_w && pair_mode()) ? 1 : 0;
+    g.pair = (g.split_w && pair_all()) ? 1 : 0;
     if (pool && out_f32_or_null) return fail("fp32 copy is only available for un-pooled layers");
     CUtensorMap mx, mw, mx8;
     if (encode_layer_maps(g, x_f16, NB, w_f16, &mx, &mw)) return 1;
@@ -1114,7 +1131,12 @@ int fad_frechet_batched(fad_handle* h, const double* mu1, const double* sqrt1, c
     const size_t ev = prof_begin(h, st);
     for (long long g0 = 0; g0 < n_items; g0 += G) {
         const int g = (int)((n_items - g0) < G ? (n_items - g0) : G);
-        fad::song_stats_kernel<<<dim3(dt, dt, g), 256, 0, st>>>(reinterpret_cast<const __half*>(emb_f16), offsets + g0, d, mu, cov, ok);
+        if (d % 64 == 0) {                                   // fp64 tensor pipe (DMMA), upper tile triangle per item
+            const int nt = d / 64;
+            fad::song_stats_dmma_kernel<<<dim3(nt * (nt + 1) / 2, g), 256, 0, st>>>(reinterpret_cast<const __half*>(emb_f16), offsets + g0, d, mu, cov, ok);
+        } else {
+            fad::song_stats_kernel<<<dim3(dt, dt, g), 256, 0, st>>>(reinterpret_cast<const __half*>(emb_f16), offsets + g0, d, mu, cov, ok);
+        }
         fad::norm_trace_batched_kernel<<<g, 256, 0, st>>>(cov, d, scalC);
         CK(cudaGetLastError());
         fad::DgemmStrided p = {};

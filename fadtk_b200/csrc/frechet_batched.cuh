@@ -90,6 +90,142 @@ song_stats_kernel(const __half* __restrict__ emb, const long long* __restrict__ 
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ok[z] = 1;
 }
 
+// The same per-item statistics on the FP64 tensor pipe (d a multiple of 64): one CTA = (item, 64 x 64 tile pair
+// ti <= tj), the item's rows streamed 16 at a time through the DMMA tile of stats.cuh (exact products of
+// y = x - first row, fp64 accumulation in a fixed order), covariance written to both triangles from the same
+// accumulators.  5000 x [750, 128]: the CUDA-core kernel above was ~half of the whole per-song pass.
+// grid (n_pairs, items), 256 threads.
+__global__ void __launch_bounds__(256, 2)
+song_stats_dmma_kernel(const __half* __restrict__ emb, const long long* __restrict__ offsets, int d,
+                       double* __restrict__ mu, double* __restrict__ cov, int* __restrict__ ok)
+{
+    constexpr int T = 64, R = 16, P = T + 4;
+    __shared__ __align__(16) double Ys[2][2][R][P];              // [panel i | j][buffer][row][col]
+    __shared__ double s_sum[2][T];
+    const int z = blockIdx.y;
+    const long long r0 = offsets[z], r1 = offsets[z + 1];
+    const long long n = r1 - r0;
+    const int n_tiles = d / T;
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= n_tiles - ti) { rem -= n_tiles - ti; ++ti; }
+    const int tj = ti + rem;
+    const bool diag = ti == tj;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int lrow = t >> 4, lcol = (t & 15) * 4;
+    double* C = cov + (size_t)z * d * d;
+    if (n < 2) {                                                 // the reference asserts (fad.py:46): identity keeps the chain finite
+        for (int e = t; e < T * T; e += 256) {
+            const int gi = ti * T + e / T, gj = tj * T + e % T;
+            C[(size_t)gi * d + gj] = gi == gj ? 1.0 : 0.0;
+            if (!diag) C[(size_t)gj * d + gi] = 0.0;
+        }
+        if (diag && t < T) mu[(size_t)z * d + ti * T + t] = 0.0;
+        if (blockIdx.x == 0 && t == 0) ok[z] = 0;
+        return;
+    }
+    const __half* base = emb + (size_t)r0 * d;
+    double si[4], sj[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        si[e] = (double)__half2float(base[ti * T + lcol + e]);
+        sj[e] = (double)__half2float(base[tj * T + lcol + e]);
+    }
+    const __half* src_i = base + ti * T + lcol;
+    const __half* src_j = base + tj * T + lcol;
+    uint2 ri = make_uint2(0, 0), rj = make_uint2(0, 0);
+    bool rok = false;
+    auto fetch = [&](long long rr) {
+        const long long r = rr + lrow;
+        rok = r < n;
+        if (rok) {
+            ri = __ldg(reinterpret_cast<const uint2*>(src_i + (size_t)r * d));
+            if (!diag) rj = __ldg(reinterpret_cast<const uint2*>(src_j + (size_t)r * d));
+        }
+    };
+    double cs_i[4] = {0.0, 0.0, 0.0, 0.0}, cs_j[4] = {0.0, 0.0, 0.0, 0.0};
+    auto unpack = [](uint2 v, const double (&s)[4], bool okr, double (&y)[4]) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        y[0] = okr ? (double)f0.x - s[0] : 0.0;  y[1] = okr ? (double)f0.y - s[1] : 0.0;
+        y[2] = okr ? (double)f1.x - s[2] : 0.0;  y[3] = okr ? (double)f1.y - s[3] : 0.0;
+    };
+    auto stage = [&](int buf) {
+        double y[4];
+        unpack(ri, si, rok, y);
+        *reinterpret_cast<double2*>(&Ys[0][buf][lrow][lcol]) = make_double2(y[0], y[1]);
+        *reinterpret_cast<double2*>(&Ys[0][buf][lrow][lcol + 2]) = make_double2(y[2], y[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cs_i[e] += y[e];
+        if (!diag) {
+            unpack(rj, sj, rok, y);
+            *reinterpret_cast<double2*>(&Ys[1][buf][lrow][lcol]) = make_double2(y[0], y[1]);
+            *reinterpret_cast<double2*>(&Ys[1][buf][lrow][lcol + 2]) = make_double2(y[2], y[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cs_j[e] += y[e];
+        }
+    };
+    double c[4][2][2] = {};
+    const int stages = (int)((n + R - 1) / R);
+    fetch(0);
+    stage(0);
+    __syncthreads();
+    const int bp = diag ? 0 : 1;
+    for (int st = 0; st < stages; ++st) {
+        const int buf = st & 1;
+        if (st + 1 < stages) fetch((long long)(st + 1) * R);
+#pragma unroll
+        for (int kk = 0; kk < R; kk += 4) {
+            double a[4], b[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Ys[0][buf][kk + fk][wm + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[j] = Ys[bp][buf][kk + fk][wn + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma_884(c[i][j][0], c[i][j][1], a[i], b[j]);
+        }
+        if (st + 1 < stages) stage(buf ^ 1);
+        __syncthreads();
+    }
+    // column sums of y for both panels: 16 loader rows per column group, summed in a fixed order
+    double* red = &Ys[0][0][0][0];                               // 2 x 16 x 64 doubles fit the first panel's two buffers
+    static_assert(2 * R * T <= 2 * R * P, "reduction scratch");
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        red[lrow * T + lcol + e] = cs_i[e];
+        red[R * T + lrow * T + lcol + e] = diag ? cs_i[e] : cs_j[e];
+    }
+    __syncthreads();
+    if (t < 2 * T) {
+        const int which = t >> 6, col = t & 63;
+        double v = 0.0;
+        for (int k = 0; k < R; ++k) v += red[which * R * T + k * T + col];
+        s_sum[which][col] = v;
+    }
+    __syncthreads();
+    const double inv_n = 1.0 / (double)n, inv_n1 = 1.0 / (double)(n - 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int li = wm + i * 8 + fr, lj = wn + j * 8 + 2 * fk + e;
+                const double v = (c[i][j][e] - s_sum[0][li] * s_sum[1][lj] * inv_n) * inv_n1;
+                const int gi = ti * T + li, gj = tj * T + lj;
+                C[(size_t)gi * d + gj] = v;
+                if (!diag) C[(size_t)gj * d + gi] = v;
+            }
+    if (diag && t < T) {
+        const double m = (double)__half2float(base[ti * T + t]) + s_sum[0][t] * inv_n;
+        mu[(size_t)z * d + ti * T + t] = (double)__half2float(__double2half(m));      // fp16 mean (fad.py:48)
+    }
+    if (blockIdx.x == 0 && t == 0) ok[z] = 1;
+}
+
 // C_z = alpha A_z B_z + beta_diag I for two strided families of problems in one launch:
 // blockIdx.z = item + family * items.  A stride of 0 shares the operand between items (the cached
 // baseline root).  flags: per-item float[3] rotating max|W - I| slots as in dgemm_kernel.

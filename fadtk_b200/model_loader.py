@@ -131,6 +131,23 @@ class _DeviceBatch:
         return host.numpy(), rows
 
 
+_host_out = {}
+
+
+def _pinned_like(t: torch.Tensor) -> torch.Tensor:
+    """A pinned host tensor of t's shape from TWO alternating grow-only buffers per dtype: cudaHostAlloc of tens of MB
+    per batch costs more than the copy it serves.  The returned array stays valid until the second next call with that
+    dtype - the batch driver writes batch k to disk while batch k+1 is embedded (fad_batch.cache_embedding_files)."""
+    n = t.numel()
+    slot = _host_out.setdefault(t.dtype, {"turn": 0, "buf": [None, None]})
+    slot["turn"] ^= 1
+    buf = slot["buf"][slot["turn"]]
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
+        slot["buf"][slot["turn"]] = buf
+    return buf[:n].view(t.shape)
+
+
 def flat_pcm(clips) -> np.ndarray:
     """The int16 clips back to back as ONE array.  The batch driver hands over consecutive views of its pinned
     staging buffer (fad_batch._read_native); then the result is a view of that buffer - no host copy, and the
@@ -218,16 +235,77 @@ class VGGishModel(_DeviceBatch, ModelLoader):
 
     def _embed_flat(self, clips):
         """list of int16 arrays -> list of fp16 cuda tensors [n_i, 128]."""
+        emb, rows = self._embed_flat_device(clips)
+        return list(torch.split(emb, [int(r) for r in rows]))
+
+    # sub-batch of one pipelined forward: audio seconds (the copy of sub-batch k+1 overlaps the forward of sub-batch k)
+    _PIPE_SECONDS = 2560.0
+
+    def _embed_flat_device(self, clips):
+        """list of int16 arrays -> (fp16 cuda tensor [sum n_i, 128], rows per clip).  Large batches are cut into
+        sub-batches whose host -> device copies run on a second stream into two staging buffers, so the PCIe transfer
+        of sub-batch k+1 hides behind the forward of sub-batch k (a 1000-clip batch is 320 MB of PCM: ~6 ms of PCIe
+        against ~30 ms of forward)."""
         self._ensure_loaded()
         eng = self._engine
+        dev = eng.torch_device
+        lens = np.fromiter((len(c) for c in clips), dtype=np.int64, count=len(clips))
         offsets = np.zeros(len(clips) + 1, dtype=np.int64)
-        offsets[1:] = np.cumsum([len(c) for c in clips])
+        np.cumsum(lens, out=offsets[1:])
         ex_start, rows = eng.vggish_plan(offsets)
-        flat = torch.from_numpy(flat_pcm(clips))
-        pcm = flat.pin_memory().to(eng.torch_device, non_blocking=True)
-        ex = torch.from_numpy(ex_start).to(eng.torch_device)
-        emb = eng.vggish_forward(pcm, ex)
-        return list(torch.split(emb, [int(r) for r in rows]))
+        total_rows = int(rows.sum())
+        emb = torch.empty((total_rows, 128), dtype=torch.float16, device=dev)
+        limit = int(self._PIPE_SECONDS * self.sr)
+        if offsets[-1] <= limit:                                 # small batch: one copy, one forward
+            pcm = torch.from_numpy(flat_pcm(clips)).pin_memory().to(dev, non_blocking=True)
+            eng.vggish_forward(pcm, torch.from_numpy(ex_start).to(dev), emb)
+            return emb, rows
+        cuts = [0]                                               # clip indices where sub-batches start
+        for i in range(len(clips)):
+            if offsets[i + 1] - offsets[cuts[-1]] > limit and i > cuts[-1]:
+                cuts.append(i)
+        cuts.append(len(clips))
+        if getattr(self, "_pipe", None) is None or self._pipe["dev"] != dev:
+            self._pipe = {"dev": dev, "copy": torch.cuda.Stream(device=dev), "stage": [None, None],
+                          "ready": [torch.cuda.Event(), torch.cuda.Event()], "free": [torch.cuda.Event(), torch.cuda.Event()]}
+        pipe = self._pipe
+        main = torch.cuda.current_stream(dev)
+        row_off = np.zeros(len(clips) + 1, dtype=np.int64)
+        np.cumsum(rows, out=row_off[1:])
+        ex_row = 0
+        for j in range(len(cuts) - 1):
+            a, b_ = cuts[j], cuts[j + 1]
+            slot = j & 1
+            n_samples = int(offsets[b_] - offsets[a])
+            n_ex = int(row_off[b_] - row_off[a])
+            src = torch.from_numpy(flat_pcm(clips[a:b_]))
+            ex_j = torch.from_numpy(ex_start[ex_row:ex_row + n_ex] - offsets[a])
+            if pipe["stage"][slot] is None or pipe["stage"][slot].numel() < n_samples:
+                pipe["stage"][slot] = torch.empty(max(n_samples, limit + 64 * self.sr), dtype=torch.int16, device=dev)
+            with torch.cuda.stream(pipe["copy"]):
+                if j >= 2:
+                    pipe["copy"].wait_event(pipe["free"][slot])
+                stage = pipe["stage"][slot][:n_samples]
+                stage.copy_(src, non_blocking=True)
+                ex_dev = ex_j.to(dev, non_blocking=True)
+                pipe["ready"][slot].record(pipe["copy"])
+            main.wait_event(pipe["ready"][slot])
+            stage.record_stream(main)
+            ex_dev.record_stream(main)
+            eng.vggish_forward(stage, ex_dev, emb[ex_row:ex_row + n_ex])
+            pipe["free"][slot].record(main)
+            ex_row += n_ex
+        return emb, rows
+
+    def embed_pcm_batch_flat(self, clips):
+        """(fp16 [sum n_i, 128] host array, rows per clip): the pipelined device forward, then ONE device -> host copy."""
+        need = self.min_len * self.sr
+        if any(len(c) < need for c in clips):                    # short clips are zero-padded to min_len (model_loader.py:72-86)
+            clips = [np.pad(np.asarray(c, dtype=np.int16), (0, need - len(c))) if len(c) < need else c for c in clips]
+        emb, rows = self._embed_flat_device(clips)
+        host = _pinned_like(emb)
+        host.copy_(emb)                                          # synchronous: pinned destination
+        return host.numpy(), [int(r) for r in rows]
 
 
 class CLAPLaionModel(_DeviceBatch, ModelLoader):
