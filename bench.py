@@ -601,7 +601,7 @@ def main():
         def plugin_step():
             """the reference-facing calls: plugin embeds host PCM and hands fp16 embeddings back on the host (what the
             batch driver writes to .npy), statistics of those host arrays, Frechet distance of host statistics"""
-            st = DeviceStatistics(d, eng)
+            st = DeviceStatistics(d, eng, reduce_ranks=world > 1)
             for part in chunks:
                 flat, _rows = ml.embed_pcm_batch_flat(part)
                 st.add(flat)

@@ -69,6 +69,7 @@ SIGNATURES = {
     "fad_resample": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_batched": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_bench_dmma_peak": (C.c_int, [c_vp, C.c_int, c_vp]),
+    "fad_bench_umma_mode": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "fad_comm_unique_id": (C.c_int, [c_vp]),
     "fad_comm_init": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int]),
     "fad_comm_destroy": (C.c_int, [c_vp]),
@@ -171,6 +172,12 @@ class Engine:
         assert buf.dtype == torch.float64 and buf.is_cuda and buf.is_contiguous()
         _check(lib().fad_allreduce_sum_f64(self._h, None, buf.data_ptr(), buf.numel(), _stream()))
         return buf
+
+    def umma_mode_ms(self, mode: int, ksteps: int = 40000) -> float:
+        """tensor-pipe microbenchmark (csrc/umma_bench.cuh): ms for `ksteps` split-weight K steps per SM under issue pattern `mode`"""
+        out = C.c_double(0.0)
+        _check(lib().fad_bench_umma_mode(self._h, int(mode), int(ksteps), C.byref(out)))
+        return float(out.value)
 
     def dmma_peak_tflops(self, iters: int = 0) -> float:
         """measured fp64 tensor-pipe (DMMA) rate, TFLOP/s: roofline denominator of the fp64 kernels"""

@@ -25,6 +25,7 @@
 #include "whisper.cuh"
 #include "encodec.cuh"
 #include "wav2vec.cuh"
+#include "umma_bench.cuh"
 
 namespace {
 
@@ -843,6 +844,28 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     if (s == 12345.678) sink[0] = s;                       // keeps the chain alive, never true
 }
 }  // namespace
+
+// time (ms) of `ksteps` hi/lo-split K steps per SM under issue pattern `mode` (umma_bench.cuh), every SM busy
+extern "C" int fad_bench_umma_mode(fad_handle* h, int mode, int ksteps, double* ms_out_host) {
+    if (!h || !ms_out_host) return fail("null argument");
+    if (mode < 0 || mode > 5 || ksteps < 16) return fail("bad mode / ksteps");
+    CK(cudaSetDevice(h->device));
+    CK(cudaFuncSetAttribute(fad::umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fad::kUbSmem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    fad::umma_bench_kernel<<<h->num_sms, fad::kUbThreads, fad::kUbSmem>>>(mode, ksteps / 8);     // warm-up
+    CK(cudaEventRecord(e0));
+    fad::umma_bench_kernel<<<h->num_sms, fad::kUbThreads, fad::kUbSmem>>>(mode, ksteps);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_out_host = ms;
+    h->launches += 2;
+    return 0;
+}
 
 extern "C" int fad_bench_dmma_peak(fad_handle* h, int iters, double* tflops_out_host) {
     if (!h || !tflops_out_host) return fail("null argument");

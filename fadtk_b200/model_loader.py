@@ -148,27 +148,33 @@ def _pinned_like(t: torch.Tensor) -> torch.Tensor:
     return buf[:n].view(t.shape)
 
 
+def _data_address(a: np.ndarray) -> int:
+    return a.__array_interface__["data"][0]                  # a.ctypes.data builds a ctypes object per call: 10x slower
+
+
 def flat_pcm(clips) -> np.ndarray:
-    """The int16 clips back to back as ONE array.  The batch driver hands over consecutive views of its pinned
-    staging buffer (fad_batch._read_native); then the result is a view of that buffer - no host copy, and the
-    H2D transfer that follows is a straight DMA from pinned memory.  Anything else is concatenated."""
+    """The int16 clips back to back as ONE array.  When they are consecutive views of one C-contiguous buffer - the
+    batch driver's pinned staging buffer (fad_batch._read_native), the rows of a [clips, samples] array, slices of a
+    long recording - the result is a view of that buffer: no host copy, and the H2D transfer that follows is a
+    straight DMA when the buffer is pinned.  Anything else is concatenated."""
     if len(clips) == 1:
         return np.ascontiguousarray(clips[0])
     first = clips[0]
     owner = first
     while isinstance(owner.base, np.ndarray):
         owner = owner.base
-    if owner.dtype == np.int16 and owner.ndim == 1 and owner.flags.c_contiguous:
-        ptr = first.ctypes.data
-        start = (ptr - owner.ctypes.data) // 2
+    if owner.dtype == np.int16 and owner.flags.c_contiguous and first.dtype == np.int16:
+        flat_owner = owner.reshape(-1)                         # a view: any C-contiguous shape is one run of samples
+        ptr = _data_address(first)
+        start = (ptr - _data_address(flat_owner)) // 2
         total = 0
         for c in clips:
-            if c.dtype != np.int16 or c.ndim != 1 or not c.flags.c_contiguous or c.ctypes.data != ptr + 2 * total:
+            if c.dtype != np.int16 or c.ndim != 1 or not c.flags.c_contiguous or _data_address(c) != ptr + 2 * total:
                 break
             total += c.shape[0]
         else:
-            if 0 <= start and start + total <= owner.shape[0]:
-                return owner[start:start + total]
+            if 0 <= start and start + total <= flat_owner.shape[0]:
+                return flat_owner[start:start + total]
     return np.concatenate(clips)
 
 

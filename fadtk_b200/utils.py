@@ -35,10 +35,13 @@ class DeviceStatistics:
     fp16 hi/lo halves and contracted as a [n, 2d] matrix so nothing is rounded away.
     """
 
-    def __init__(self, d: int, engine=None):
+    def __init__(self, d: int, engine=None, reduce_ranks: bool = False):
+        """``reduce_ranks``: this accumulator will be summed over the ranks (``allreduce``); every rank must then shift
+        by the SAME vector, so the first ``add`` broadcasts rank 0's (a collective call)."""
         from . import _native
         self.eng = engine or _native.engine()
         self.d = d
+        self.reduce_ranks = reduce_ranks
         self.wide = None
         self.shift = None
         self.acc = None
@@ -53,6 +56,12 @@ class DeviceStatistics:
             self.shift = s
         else:
             self.shift = head.float().mean(0).to(torch.float16)
+        if self.reduce_ranks:
+            from . import dist
+            if dist.is_distributed():
+                s32 = self.shift.float()
+                torch.distributed.broadcast(s32, src=0)
+                self.shift = s32.to(torch.float16)
         self.acc = self.eng.stats_new(dd)
 
     def add(self, rows):
@@ -64,7 +73,9 @@ class DeviceStatistics:
         for s in range(0, t.shape[0], _ROWS_PER_UPLOAD):
             part = t[s:s + _ROWS_PER_UPLOAD]
             if not part.is_cuda:
-                part = part.pin_memory().to(self.eng.torch_device, non_blocking=True)
+                # pinned source (what the native embedders hand back): asynchronous DMA.  Pageable source: one staged copy
+                # by the driver - cheaper than pinning a copy first (cudaHostAlloc + memcpy + DMA)
+                part = part.to(self.eng.torch_device, non_blocking=part.is_pinned())
             part = _split_hi_lo(part) if self.wide else part.contiguous()
             self.eng.stats_accumulate(part, self.shift, self.acc)
 
@@ -101,7 +112,7 @@ def statistics_of_arrays(arrays: Iterable[np.ndarray], d: int | None = None, red
     st = None
     for a in arrays:
         if st is None:
-            st = DeviceStatistics(d or a.shape[-1])
+            st = DeviceStatistics(d or a.shape[-1], reduce_ranks=reduce_ranks)
         st.add(a)
     if st is None:
         raise AssertionError("No files provided")

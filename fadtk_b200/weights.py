@@ -80,12 +80,36 @@ def resolve_checkpoint(path, env: str, what: str):
         "set FADTK_SYNTHETIC=1 to run on seeded random weights (tests / benchmarks only)")
 
 
+def load_checkpoint_file(path) -> dict:
+    """A checkpoint as a flat {name: tensor} dict: ``.safetensors`` (what Hugging Face publishes today) or a torch
+    pickle (``pytorch_model.bin`` / ``.pt`` / ``.pth``, optionally wrapped in {"state_dict": ...}).  Published
+    weight-normalised convolutions come in two spellings - ``weight_g`` / ``weight_v`` (torch.nn.utils.weight_norm,
+    every older checkpoint) and ``parametrizations.weight.original0`` / ``original1`` (torch >= 2.1) - the older one is
+    renamed to the newer, which is what the packers read."""
+    path = Path(path)
+    if path.suffix == ".safetensors":
+        from safetensors.torch import load_file
+        raw = load_file(str(path), device="cpu")
+    else:
+        raw = torch.load(path, map_location="cpu")
+        if isinstance(raw, dict) and "state_dict" in raw and isinstance(raw["state_dict"], dict):
+            extra = {k: v for k, v in raw.items() if k != "state_dict" and not isinstance(v, dict)}
+            raw = dict(raw["state_dict"], **{f"__meta__.{k}": v for k, v in extra.items()})
+    out = {}
+    for k, v in raw.items():
+        if k.endswith(".weight_g"):
+            k = k[:-len("weight_g")] + "parametrizations.weight.original0"
+        elif k.endswith(".weight_v"):
+            k = k[:-len("weight_v")] + "parametrizations.weight.original1"
+        out[k] = v
+    return out
+
+
 def load_vggish_state(path=None, seed: int = 0) -> dict:
     """Real checkpoint ``path`` (or $FADTK_VGGISH_CKPT); seeded synthetic only under FADTK_SYNTHETIC=1."""
     path = resolve_checkpoint(path, "FADTK_VGGISH_CKPT", "vggish")
     if path is not None:
-        sd = torch.load(path, map_location="cpu")
-        sd = sd.get("state_dict", sd)
+        sd = load_checkpoint_file(path)
         return {k: v.float().contiguous() for k, v in sd.items()
                 if k.startswith(("features.", "embeddings."))}
     return synthetic_vggish_state(seed)

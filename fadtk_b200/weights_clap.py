@@ -87,8 +87,8 @@ def load_clap_state(path=None, seed: int = 0, variant: str = "tiny") -> dict:
     path = resolve_checkpoint(path, "FADTK_CLAP_CKPT" if variant == "tiny" else "FADTK_CLAP_MUSIC_CKPT",
                               "clap-laion-" + ("audio" if variant == "tiny" else "music"))
     if path is not None:
-        raw = torch.load(path, map_location="cpu")
-        raw = raw.get("state_dict", raw)
+        from .weights import load_checkpoint_file
+        raw = load_checkpoint_file(path)
         out = {}
         for k, v in raw.items():
             k = k.replace("audio_model.audio_encoder.", "")

@@ -73,8 +73,8 @@ def load_encodec_state(path=None, seed: int = 0, variant: str = "24k") -> dict:
     path = resolve_checkpoint(path, "FADTK_ENCODEC_CKPT" if variant == "24k" else "FADTK_ENCODEC48_CKPT",
                               "encodec-emb" + ("" if variant == "24k" else "-48k"))
     if path is not None:
-        raw = torch.load(path, map_location="cpu")
-        raw = raw.get("state_dict", raw)
+        from .weights import load_checkpoint_file
+        raw = load_checkpoint_file(path)
         return {k.removeprefix("encoder."): v.float().contiguous() for k, v in raw.items() if "layers." in k and not k.startswith(("decoder.", "quantizer."))}
     return synthetic_encodec_state(seed, variant)
 

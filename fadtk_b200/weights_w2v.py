@@ -80,8 +80,8 @@ def load_w2v_state(path=None, seed: int = 0, env: str = "FADTK_W2V_CKPT", **cfg)
     from .weights import resolve_checkpoint
     path = resolve_checkpoint(path, env, env.removeprefix("FADTK_").removesuffix("_CKPT").lower())
     if path is not None:
-        raw = torch.load(path, map_location="cpu")
-        raw = raw.get("state_dict", raw)
+        from .weights import load_checkpoint_file
+        raw = load_checkpoint_file(path)                      # .safetensors or torch pickle; weight_g / weight_v renamed
         drop = ("masked_spec_embed", "lm_head", "quantizer", "project_", "label_embs")
         return {k.removeprefix("wav2vec2.").removeprefix("hubert.").removeprefix("wavlm."): v.float().contiguous() for k, v in raw.items()
                 if not any(x in k for x in drop)}

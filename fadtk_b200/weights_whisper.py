@@ -78,9 +78,10 @@ def load_whisper_state(path=None, seed: int = 0, size: str = "small"):
     from .weights import resolve_checkpoint
     path = resolve_checkpoint(path, "FADTK_WHISPER_CKPT", "whisper-" + size)
     if path is not None:
-        raw = torch.load(path, map_location="cpu")
-        start = int(raw.get("decoder_start_token_id", 50258)) if isinstance(raw, dict) and "state_dict" in raw else 50258
-        raw = raw.get("state_dict", raw)
+        from .weights import load_checkpoint_file
+        raw = load_checkpoint_file(path)
+        start = int(raw.pop("__meta__.decoder_start_token_id", 50258))
+        raw = {k: v for k, v in raw.items() if not k.startswith("__meta__.")}
         sd = {k.removeprefix("model."): v.float().contiguous() for k, v in raw.items() if not k.startswith("proj_out")}
         return sd, start
     return synthetic_whisper_state(seed, size), SYNTH_START

@@ -265,6 +265,10 @@ long long fad_launch_count(fad_handle* h);
  * issue loop: the roofline denominator of the exact-Gram and Newton-Schulz kernels, which
  * MEASURED_PEAKS.json (bf16 GEMM, HBM copy) does not carry.  Synchronous; iters <= 0 = default. */
 int fad_bench_dmma_peak(fad_handle* h, int iters, double* tflops_out_host);
+/* Milliseconds that `ksteps` K steps (128 x 128 x 64, hi/lo split weights) take on every SM at once under tcgen05 issue
+ * pattern `mode` (0..5, csrc/umma_bench.cuh): operands resident in shared memory, no TMA, no epilogue - what the
+ * tensor pipe itself (and the power cap) allows for each way of applying the low weight parts. */
+int fad_bench_umma_mode(fad_handle* h, int mode, int ksteps, double* ms_out_host);
 
 #ifdef __cplusplus
 }

@@ -477,3 +477,28 @@ def test_named_baseline_resolves_from_an_installed_reference_package(tmp_path, m
     np.testing.assert_array_equal(mu, np.arange(3.0))
     with pytest.raises(SystemExit):                            # an unknown name: the reference's exit(1) (fad.py:276-278)
         f.load_stats("no_such_set")
+
+
+def test_checkpoint_files_safetensors_and_old_weight_norm_names(tmp_path, monkeypatch):
+    """published wav2vec-family checkpoints spell the positional conv's weight norm ``weight_g`` /
+    ``weight_v`` and ship as .safetensors; both must load into the names the packers read."""
+    from safetensors.torch import save_file
+    from fadtk_b200 import weights, weights_w2v
+    sd = weights_w2v.synthetic_w2v_state(0)
+    old = {}
+    for k, v in sd.items():
+        k = k.replace("parametrizations.weight.original0", "weight_g").replace("parametrizations.weight.original1", "weight_v")
+        old["wav2vec2." + k] = v.contiguous()
+    old["lm_head.weight"] = torch.zeros(4, 4)
+    save_file(old, str(tmp_path / "model.safetensors"))
+    torch.save({"state_dict": old}, tmp_path / "pytorch_model.bin")
+    for name in ("model.safetensors", "pytorch_model.bin"):
+        got = weights_w2v.load_w2v_state(tmp_path / name, env="FADTK_W2V2_CKPT")
+        assert set(got) == set(sd), sorted(set(got) ^ set(sd))[:6]
+        for k in sd:
+            assert torch.equal(got[k], sd[k].float()), k
+    packed = weights_w2v.pack_w2v(weights_w2v.load_w2v_state(tmp_path / "model.safetensors", env="FADTK_W2V2_CKPT"))
+    ref = weights_w2v.pack_w2v(sd)
+    assert len(packed) == len(ref) and all(torch.equal(a, b) for a, b in zip(packed, ref))
+    raw = weights.load_checkpoint_file(tmp_path / "pytorch_model.bin")
+    assert "wav2vec2.encoder.pos_conv_embed.conv.parametrizations.weight.original0" in raw
