@@ -38,8 +38,13 @@ def main():
     embed_cpu = bench.oracle_embed_fn(args.model, state)
     ml = bench.make_loader(args.model, min(args.clips, spec["chunk_clips"]))
     ml.load_model()
-    sets = {"base": [synth.musiclike_clip(i, args.seconds, sr, baseline=True) for i in range(args.clips)],
-            "eval": [synth.musiclike_clip(i, args.seconds, sr) for i in range(args.clips)]}
+    # two clearly different populations (as bench.py builds them): a baseline with low-passed partials and more noise, so
+    # the FAD is not a difference of nearly equal numbers (two draws of the SAME population give FAD ~ 1e-3 with CLAP's
+    # L2-normalised embeddings: 1e-4 relative of that is below the eig-route noise of the reference itself)
+    dev = torch.device("cuda", 0)
+    base = synth.musiclike_device(args.clips, args.seconds, sr, seed=30_000, device=dev, fmax=1500.0, noise=0.08).cpu().numpy()
+    evl = synth.musiclike_device(args.clips, args.seconds, sr, seed=20_000, device=dev).cpu().numpy()
+    sets = {"base": [base[i] for i in range(args.clips)], "eval": [evl[i] for i in range(args.clips)]}
     t0 = time.perf_counter()
     step = spec["chunk_clips"]
     gpu = {k: np.concatenate([e for s in range(0, args.clips, step) for e in ml.embed_pcm_batch(v[s:s + step])]) for k, v in sets.items()}

@@ -22,12 +22,13 @@ FLOP = {0: 2 * 2 * 128 * 128 * 64, 1: 2 * 2 * 128 * 128 * 64, 2: 2 * 2 * 128 * 1
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ksteps", type=int, default=200000)
+    ap.add_argument("--modes", default="0,1,2,3,4,5")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     eng = _native.Engine(0, max_examples=16)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     out = {"ksteps_per_sm": args.ksteps, "sms": sms, "modes": []}
-    for m, name in MODES.items():
+    for m, name in ((int(v), MODES[int(v)]) for v in args.modes.split(",")):
         ms = min(eng.umma_mode_ms(m, args.ksteps) for _ in range(3))
         out["modes"].append({"mode": m, "pattern": name, "ms": ms, "ns_per_kstep": ms * 1e6 / args.ksteps,
                              "issued_tflops_chip": FLOP[m] * args.ksteps * sms / (ms * 1e-3) / 1e12})

@@ -68,6 +68,7 @@ SIGNATURES = {
     "fad_resample_bank": (C.c_int, [C.c_int, C.c_int, c_vp]),
     "fad_resample": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_ll, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_batched": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp]),
+    "fad_attention": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
     "fad_bench_dmma_peak": (C.c_int, [c_vp, C.c_int, c_vp]),
     "fad_bench_umma_mode": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "fad_comm_unique_id": (C.c_int, [c_vp]),
@@ -172,6 +173,14 @@ class Engine:
         assert buf.dtype == torch.float64 and buf.is_cuda and buf.is_contiguous()
         _check(lib().fad_allreduce_sum_f64(self._h, None, buf.data_ptr(), buf.numel(), _stream()))
         return buf
+
+    def attention(self, qkv: torch.Tensor, n_clips: int, legacy: bool = False) -> torch.Tensor:
+        """qkv fp16 [n_clips * S, 3 d] (cuda) -> fp16 [n_clips * S, d]: per-head softmax(q k^T / 8) v, heads of 64 dims"""
+        assert qkv.dtype == torch.float16 and qkv.is_cuda and qkv.is_contiguous() and qkv.shape[0] % n_clips == 0
+        S, d = qkv.shape[0] // n_clips, qkv.shape[1] // 3
+        out = torch.empty((qkv.shape[0], d), dtype=torch.float16, device=qkv.device)
+        _check(lib().fad_attention(self._h, qkv.data_ptr(), n_clips, S, d, out.data_ptr(), int(legacy), _stream()))
+        return out
 
     def umma_mode_ms(self, mode: int, ksteps: int = 40000) -> float:
         """tensor-pipe microbenchmark (csrc/umma_bench.cuh): ms for `ksteps` split-weight K steps per SM under issue pattern `mode`"""

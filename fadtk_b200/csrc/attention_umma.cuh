@@ -1,0 +1,239 @@
+// Encoder self-attention (head dim 64, no mask) on tcgen05: S = Q K^T and O = P V as UMMA tiles with the scores in TMEM.
+//
+// Replaces the mma.sync flash kernel (whisper.cuh) on the Whisper / wav2vec 2.0 / HuBERT / MERT encoder paths - the
+// reference's `WhisperModel(...)` / `AutoModel(...)` forwards (fadtk/model_loader.py:656-672, 254-288, 525-596) spend
+// their attention time in torch SDPA; here one CTA owns a 128-query block of one (clip, head):
+//
+//   warp 0      TMA producer: Q once, then K_j / V_j tiles (128 keys x 64 dims, 128-B swizzle) into a 2-stage ring.
+//               The tensor map is 3-D [clips][S][3 d]: rows past S are zero-filled by the hardware.
+//   warp 1      MMA issuer: S_j = Q K_j^T  (M 128, N 128, K 64; both operands K-major) into one of two TMEM score
+//               buffers, and - one block behind - O_j = P_j V_j (M 128, N 64, K 128; P K-major from shared memory, V as
+//               an MN-major B operand: the TMA tile [keys][dims] IS that layout) into one of two TMEM output buffers.
+//   warps 2-5   softmax, one thread per query row: two passes over the score row straight out of TMEM (row maximum,
+//               then exp2 / row sum), P written as fp16 into the 128-B-swizzled K-major tile the PV MMA reads; the
+//               partial output of the previous block is folded into fp32 registers with the usual rescaling
+//               O <- (O + O_{j-1}) * 2^(m_{j-1} - m_j), so the accumulator never has to be rescaled inside TMEM.
+//
+// The S_{j+1} MMAs run while the softmax warps work on S_j (two score buffers); exp2 is the bound (16 MUFU results per
+// clock and SM: 128 x 128 scores = 1024 clocks per block against 512 of MMA).
+#pragma once
+#include "sm100.cuh"
+
+namespace fad {
+
+constexpr int kAtThreads = 192;
+constexpr uint32_t kAtTile = 128 * 128;                       // bytes of one 128-row x 64-col fp16 tile: 16 KiB
+constexpr uint32_t kAtSmem = kAtTile /*Q*/ + 2 * 2 * kAtTile /*K,V x 2 stages*/ + 2 * 2 * kAtTile /*P x 2*/ + 1024 + 256;
+
+struct AttnParams {
+    int S, d, heads;
+    __half* out;             // [clips * S][d]
+};
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
+{
+    using namespace sm100;
+    extern __shared__ uint8_t at_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_s = smem;
+    uint8_t* kv_s = smem + kAtTile;                            // stage st: K at kv_s + st * 2 tiles, V one tile further
+    uint8_t* p_s = smem + 5 * kAtTile;                         // buffer b: two 64-key blocks of 16 KiB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 9 * kAtTile);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // 2
+    uint64_t* kv_empty = bars + 3;      // 2
+    uint64_t* s_full = bars + 5;        // 2
+    uint64_t* s_empty = bars + 7;       // 2
+    uint64_t* p_full = bars + 9;        // 2
+    uint64_t* p_empty = bars + 11;      // 2
+    uint64_t* o_full = bars + 13;       // 2
+    uint64_t* o_empty = bars + 15;      // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x, h = blockIdx.y, clip = blockIdx.z;
+    const int n_blocks = (p.S + 127) / 128;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&map_qkv);
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 4);
+            mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
+            mbar_init(&o_full[i], 1);  mbar_init(&o_empty[i], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tm_s[2] = {tmem, tmem + 128}, tm_o[2] = {tmem + 256, tmem + 320};
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, kAtTile);
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(smem_u32(q_s)), "l"(reinterpret_cast<uint64_t>(&map_qkv)), "r"(smem_u32(q_full)),
+                           "r"(h * 64), "r"(qb * 128), "r"(clip) : "memory");
+            for (int j = 0; j < n_blocks; ++j) {
+                const int st = j & 1;
+                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[st], 2 * kAtTile);
+                uint8_t* kd = kv_s + st * 2 * kAtTile;
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                             ::"r"(smem_u32(kd)), "l"(reinterpret_cast<uint64_t>(&map_qkv)), "r"(smem_u32(&kv_full[st])),
+                               "r"(p.d + h * 64), "r"(j * 128), "r"(clip) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                             ::"r"(smem_u32(kd + kAtTile)), "l"(reinterpret_cast<uint64_t>(&map_qkv)), "r"(smem_u32(&kv_full[st])),
+                               "r"(2 * p.d + h * 64), "r"(j * 128), "r"(clip) : "memory");
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t kIdS = make_idesc(FMT_F16, 128, 128);
+            constexpr uint32_t kIdO = make_idesc(FMT_F16, 128, 64, /*a MN-major*/ 0, /*b MN-major*/ 1);
+            const uint64_t dq = kmajor_sw128_desc(smem_u32(q_s));
+            auto issue_pv = [&](int j) {                       // O_j = P_j V_j
+                const int b = j & 1, st = j & 1;
+                mbar_wait(&p_full[b], (j >> 1) & 1);
+                mbar_wait(&o_empty[b], ((j >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t pa = smem_u32(p_s + b * 2 * kAtTile);
+                const uint64_t dv = mnmajor_sw128_desc(smem_u32(kv_s + st * 2 * kAtTile + kAtTile), kAtTile, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {               // 16 keys per MMA: P advances 32 B inside its 64-key block, V two 8-key groups
+                    const uint64_t dp = kmajor_sw128_desc(pa + (kk >> 2) * kAtTile) + 2 * (kk & 3);
+                    umma_f16(tm_o[b], dp, dv + 128 * kk, kIdO, kk > 0);
+                }
+                umma_commit(&o_full[b]);
+                umma_commit(&p_empty[b]);
+                umma_commit(&kv_empty[st]);
+            };
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < n_blocks; ++j) {
+                const int b = j & 1, st = j & 1;
+                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint64_t dk = kmajor_sw128_desc(smem_u32(kv_s + st * 2 * kAtTile));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(tm_s[b], dq + 2 * k, dk + 2 * k, kIdS, k > 0);
+                umma_commit(&s_full[b]);
+                if (j > 0) issue_pv(j - 1);
+            }
+            issue_pv(n_blocks - 1);
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax + output accumulation
+        const int quarter = warp & 3;                          // TMEM lanes this warp may read
+        const int row = quarter * 32 + lane;                   // query row of the tile
+        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;         // head_dim^-0.5 and log2(e): softmax in the exp2 domain
+        float o[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) o[c] = 0.f;
+        float m = -3.0e38f, l = 0.f;
+        const uint32_t p_row = row * 128, sw = row & 7;
+        for (int j = 0; j < n_blocks; ++j) {
+            const int b = j & 1;
+            const int valid = min(128, p.S - j * 128);         // keys of this block that exist
+            mbar_wait(&s_full[b], (j >> 1) & 1);
+            tc_fence_after_sync();
+            float mx = m;
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+                uint32_t v[32];
+                tmem_ld_32x32(tm_s[b] + lane_base + g * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (g * 32 + c < valid) mx = fmaxf(mx, __uint_as_float(v[c]) * sc);
+            }
+            const float alpha = exp2f(m - mx);
+            m = mx;
+            mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);        // PV_{j-2} has finished reading this P buffer
+            uint8_t* pb = p_s + b * 2 * kAtTile;
+            float rs = 0.f;
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+                uint32_t v[32];
+                tmem_ld_32x32(tm_s[b] + lane_base + g * 32, v);
+                tmem_ld_wait();
+                uint32_t h2[16];
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const float e0 = (g * 32 + c < valid) ? exp2f(fmaf(__uint_as_float(v[c]), sc, -m)) : 0.f;
+                    const float e1 = (g * 32 + c + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[c + 1]), sc, -m)) : 0.f;
+                    const __half2 hh = __floats2half2_rn(e0, e1);
+                    h2[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                    const float2 back = __half22float2(hh);     // the row sum uses the values the PV MMA will see
+                    rs += back.x + back.y;
+                }
+                // keys g*32 .. g*32+31 = 16-B chunks (g & 1) * 4 .. +3 of the 64-key block g >> 1
+                uint8_t* blk = pb + (g >> 1) * kAtTile + p_row;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t chunk = uint32_t((g & 1) * 4 + q4) ^ sw;
+                    *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+                }
+            }
+            l = l * alpha + rs;
+            tc_fence_before_sync();
+            fence_proxy_async_smem();                          // P stores -> visible to the UMMA (async proxy)
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&s_empty[b]); mbar_arrive(&p_full[b]); }
+            if (j > 0) {                                       // fold in the previous block's P V (relative to the old maximum)
+                const int bp = (j - 1) & 1;
+                mbar_wait(&o_full[bp], ((j - 1) >> 1) & 1);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tm_o[bp] + lane_base + g * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) o[g * 32 + c] = (o[g * 32 + c] + __uint_as_float(v[c])) * alpha;
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_empty[bp]);
+            }
+        }
+        {
+            const int bp = (n_blocks - 1) & 1;
+            mbar_wait(&o_full[bp], ((n_blocks - 1) >> 1) & 1);
+            tc_fence_after_sync();
+            const float inv = 1.0f / l;
+            const int q = qb * 128 + row;
+            __half* dst = p.out + ((size_t)clip * p.S + q) * p.d + h * 64;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint32_t v[32];
+                tmem_ld_32x32(tm_o[bp] + lane_base + g * 32, v);
+                tmem_ld_wait();
+                if (q < p.S) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __half2 hh = __floats2half2_rn((o[g * 32 + c + 2 * e] + __uint_as_float(v[c + 2 * e])) * inv,
+                                                                 (o[g * 32 + c + 2 * e + 1] + __uint_as_float(v[c + 2 * e + 1])) * inv);
+                            w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                        }
+                        *reinterpret_cast<uint4*>(dst + g * 32 + c) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace fad

@@ -26,6 +26,7 @@
 #include "encodec.cuh"
 #include "wav2vec.cuh"
 #include "umma_bench.cuh"
+#include "attention_umma.cuh"
 
 namespace {
 
@@ -253,6 +254,32 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
 }
 
 int lo8_for(fad_handle* h, const LayerGeom& g, const void* w, CUtensorMap* mw8, float* inv_scale, cudaStream_t st);
+
+// Encoder self-attention on tcgen05 (attention_umma.cuh).  qkv: fp16 [clips * S][3 d] (q | k | v, head h at column h * 64),
+// out: fp16 [clips * S][d].  FADTK_ATTN=legacy selects the mma.sync flash kernel (whisper.cuh) instead.
+bool attention_umma_enabled() {
+    static const bool on = [] { const char* e = getenv("FADTK_ATTN"); return !(e && std::string(e) == "legacy"); }();
+    return on;
+}
+int launch_attention_umma(fad_handle* h, const __half* qkv, long long n_clips, int S, int d, int heads, __half* out, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(fad::attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fad::kAtSmem));
+        attr_set = true;
+    }
+    if (heads * 64 != d) return fail("attention_umma: head dimension must be 64");
+    CUtensorMap map;
+    const uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)S, (uint64_t)n_clips};
+    const uint64_t strides[2] = {(uint64_t)3 * d * 2, (uint64_t)S * 3 * d * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    if (encode_f16_map(&map, qkv, 3, dims, strides, box)) return 1;
+    fad::AttnParams p;
+    p.S = S; p.d = d; p.heads = heads; p.out = out;
+    fad::attention_umma_kernel<<<dim3((S + 127) / 128, heads, (unsigned)n_clips), fad::kAtThreads, fad::kAtSmem, st>>>(map, p);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
 
 // the E4M3 low parts are cached per weight POINTER: drop the entry whenever that memory is rewritten
 void lo8_forget(fad_handle* h, const void* w) {
@@ -844,6 +871,21 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
     if (s == 12345.678) sink[0] = s;                       // keeps the chain alive, never true
 }
 }  // namespace
+
+// Stage entry (parity test): encoder self-attention of n_clips sequences of S positions, heads of 64 dims.
+// qkv fp16 [n_clips * S][3 d] (q | k | v), out fp16 [n_clips * S][d]; legacy != 0 runs the mma.sync kernel instead.
+extern "C" int fad_attention(fad_handle* h, const void* qkv_f16, long long n_clips, int S, int d, void* out_f16, int legacy, void* stream) {
+    if (!h || !qkv_f16 || !out_f16) return fail("null argument");
+    if (d % 64 != 0 || S <= 0 || n_clips <= 0) return fail("bad shape");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!legacy) return launch_attention_umma(h, reinterpret_cast<const __half*>(qkv_f16), n_clips, S, d, d / 64, reinterpret_cast<__half*>(out_f16), st);
+    fad::whisper_flash_attention_kernel<<<dim3((S + 63) / 64, d / 64, (unsigned)n_clips), 128, 0, st>>>(
+        reinterpret_cast<const __half*>(qkv_f16), S, d, reinterpret_cast<__half*>(out_f16));
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
 
 // time (ms) of `ksteps` hi/lo-split K steps per SM under issue pattern `mode` (umma_bench.cuh), every SM busy
 extern "C" int fad_bench_umma_mode(fad_handle* h, int mode, int ksteps, double* ms_out_host) {

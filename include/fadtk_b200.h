@@ -260,6 +260,11 @@ int fad_profile_collect(fad_handle* h, double* ms_out, long long* count_out, int
 /* Number of CUDA kernels this library has launched through `h` (bench.py's gpu_launches). */
 long long fad_launch_count(fad_handle* h);
 
+/* Stage entry (parity test / profiling): the encoder self-attention of the Whisper and wav2vec-family forwards alone.
+ * qkv: fp16 [n_clips * S][3 d] (q | k | v, head i at columns i * 64), out: fp16 [n_clips * S][d], softmax(q k^T / 8) v per
+ * head.  legacy = 0: tcgen05 kernel (csrc/attention_umma.cuh); 1: the mma.sync flash kernel it replaced. */
+int fad_attention(fad_handle* h, const void* qkv_f16, long long n_clips, int S, int d, void* out_f16, int legacy, void* stream);
+
 /* ---- measurement utility -------------------------------------------------------------
  * fp64 tensor-pipe (DMMA m8n8k4) rate of this GPU in TFLOP/s, measured with a register-only
  * issue loop: the roofline denominator of the exact-Gram and Newton-Schulz kernels, which

@@ -219,3 +219,22 @@ def test_frechet_golden_fma_pop(engine, golden_dir):
     out = engine.frechet(t(g["mu1"]), t(g["cov1"]), t(g["mu2"]), t(g["cov2"])).cpu().numpy()
     rel = abs(out[0] - float(g["fad"])) / float(g["fad"])
     assert rel < 1e-6, f"FAD {out[0]} vs golden {float(g['fad'])} rel {rel}"
+
+
+@pytest.mark.parametrize("legacy", [False, True], ids=["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("n_clips,S,d", [(2, 1500, 768), (3, 499, 768), (1, 128, 128), (2, 77, 256), (1, 129, 64), (2, 640, 1024)])
+def test_encoder_attention_matches_torch(engine, n_clips, S, d, legacy):
+    """Encoder self-attention stage (Whisper / wav2vec family; heads of 64 dims, scores scaled by 1/8): tcgen05 kernel
+    (S = Q K^T and P V as UMMA tiles, scores in TMEM) and the mma.sync kernel it replaced, against torch in fp32 on the
+    same fp16 inputs.  Ragged sizes exercise the zero-filled key rows of the last 128-key block."""
+    g = torch.Generator(device="cpu").manual_seed(S * 7 + d)
+    qkv = (torch.randn((n_clips * S, 3 * d), generator=g) * 1.5).to(torch.float16)
+    dev = engine.torch_device
+    got = engine.attention(qkv.to(dev), n_clips, legacy=legacy).float().cpu()
+    heads = d // 64
+    x = qkv.float().view(n_clips, S, 3, heads, 64)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))                # [clips, heads, S, 64]
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    want = (p @ v).permute(0, 2, 1, 3).reshape(n_clips * S, d)
+    err = (got - want).abs().max().item()
+    assert err < 4e-3 * want.abs().max().item() + 1e-3, f"attention max abs err {err} (max {want.abs().max().item()})"
