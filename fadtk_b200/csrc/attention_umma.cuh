@@ -6,16 +6,17 @@
 //
 //   warp 0      TMA producer: Q once, then K_j / V_j tiles (128 keys x 64 dims, 128-B swizzle) into a 2-stage ring.
 //               The tensor map is 3-D [clips][S][3 d]: rows past S are zero-filled by the hardware.
-//   warp 1      MMA issuer: S_j = Q K_j^T  (M 128, N 128, K 64; both operands K-major) into one of two TMEM score
-//               buffers, and - one block behind - O_j = P_j V_j (M 128, N 64, K 128; P K-major from shared memory, V as
-//               an MN-major B operand: the TMA tile [keys][dims] IS that layout) into one of two TMEM output buffers.
+//   warp 1      MMA issuer: S_j = Q K_j^T  (M 128, N 128, K 64; both operands K-major) into the TMEM score buffer,
+//               and - one block behind - O_j = P_j V_j (M 128, N 64, K 128; P K-major from shared memory, V as an
+//               MN-major B operand: the TMA tile [keys][dims] IS that layout) into one of two TMEM output buffers.
 //   warps 2-5   softmax, one thread per query row: two passes over the score row straight out of TMEM (row maximum,
 //               then exp2 / row sum), P written as fp16 into the 128-B-swizzled K-major tile the PV MMA reads; the
 //               partial output of the previous block is folded into fp32 registers with the usual rescaling
 //               O <- (O + O_{j-1}) * 2^(m_{j-1} - m_j), so the accumulator never has to be rescaled inside TMEM.
 //
-// The S_{j+1} MMAs run while the softmax warps work on S_j (two score buffers); exp2 is the bound (16 MUFU results per
-// clock and SM: 128 x 128 scores = 1024 clocks per block against 512 of MMA).
+// Two CTAs per SM (7 tiles of 16 KiB of shared memory and 256 TMEM columns each): while one CTA's softmax warps work on
+// S_j the other CTA's MMAs and loads run - the softmax side (exp2: 16 MUFU results per clock and SM, i.e. 1024 clocks per
+// 128 x 128 block against 512 of MMA, plus the TMEM round trips) is the bound, so it is what must stay busy.
 #pragma once
 #include "sm100.cuh"
 
@@ -23,33 +24,36 @@ namespace fad {
 
 constexpr int kAtThreads = 192;
 constexpr uint32_t kAtTile = 128 * 128;                       // bytes of one 128-row x 64-col fp16 tile: 16 KiB
-constexpr uint32_t kAtSmem = kAtTile /*Q*/ + 2 * 2 * kAtTile /*K,V x 2 stages*/ + 2 * 2 * kAtTile /*P x 2*/ + 1024 + 256;
+constexpr uint32_t kAtSmem = kAtTile /*Q*/ + 2 * 2 * kAtTile /*K,V x 2 stages*/ + 2 * kAtTile /*P*/ + 256;   // x 2 CTAs + 2 KiB <= 228 KiB
 
 struct AttnParams {
     int S, d, heads;
     __half* out;             // [clips * S][d]
 };
 
-__global__ void __launch_bounds__(kAtThreads, 1)
+__global__ void __launch_bounds__(kAtThreads, 2)
 attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
 {
     using namespace sm100;
-    extern __shared__ uint8_t at_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_raw) + 1023) & ~uintptr_t(1023));
+    // no static shared memory in this kernel: the dynamic window starts at the CTA's 1 KiB-aligned base, which the
+    // 128-B swizzle needs (checked below - the usual align-up slack would not leave room for two CTAs per SM)
+    extern __shared__ __align__(1024) uint8_t at_raw[];
+    uint8_t* smem = at_raw;
+    if ((smem_u32(smem) & 1023u) != 0) asm volatile("trap;");
     uint8_t* q_s = smem;
     uint8_t* kv_s = smem + kAtTile;                            // stage st: K at kv_s + st * 2 tiles, V one tile further
-    uint8_t* p_s = smem + 5 * kAtTile;                         // buffer b: two 64-key blocks of 16 KiB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 9 * kAtTile);
+    uint8_t* p_s = smem + 5 * kAtTile;                         // two 64-key blocks of 16 KiB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kAtTile);
     uint64_t* q_full = bars;            // 1
     uint64_t* kv_full = bars + 1;       // 2
     uint64_t* kv_empty = bars + 3;      // 2
-    uint64_t* s_full = bars + 5;        // 2
-    uint64_t* s_empty = bars + 7;       // 2
-    uint64_t* p_full = bars + 9;        // 2
-    uint64_t* p_empty = bars + 11;      // 2
-    uint64_t* o_full = bars + 13;       // 2
-    uint64_t* o_empty = bars + 15;      // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* s_full = bars + 5;        // 1
+    uint64_t* s_empty = bars + 6;       // 1
+    uint64_t* p_full = bars + 7;        // 1
+    uint64_t* p_empty = bars + 8;       // 1
+    uint64_t* o_full = bars + 9;        // 2
+    uint64_t* o_empty = bars + 11;      // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, h = blockIdx.y, clip = blockIdx.z;
@@ -58,20 +62,20 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_qkv);
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
+        mbar_init(s_full, 1);  mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);  mbar_init(p_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 4);
-            mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
             mbar_init(&o_full[i], 1);  mbar_init(&o_empty[i], 4);
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (warp == 2) tmem_alloc<256>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_s[2] = {tmem, tmem + 128}, tm_o[2] = {tmem + 256, tmem + 320};
+    const uint32_t tm_s = tmem, tm_o[2] = {tmem + 128, tmem + 192};
 
     if (warp == 0) {
         if (elect_one()) {
@@ -99,10 +103,10 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
             const uint64_t dq = kmajor_sw128_desc(smem_u32(q_s));
             auto issue_pv = [&](int j) {                       // O_j = P_j V_j
                 const int b = j & 1, st = j & 1;
-                mbar_wait(&p_full[b], (j >> 1) & 1);
+                mbar_wait(p_full, j & 1);
                 mbar_wait(&o_empty[b], ((j >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
-                const uint32_t pa = smem_u32(p_s + b * 2 * kAtTile);
+                const uint32_t pa = smem_u32(p_s);
                 const uint64_t dv = mnmajor_sw128_desc(smem_u32(kv_s + st * 2 * kAtTile + kAtTile), kAtTile, 1024);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {               // 16 keys per MMA: P advances 32 B inside its 64-key block, V two 8-key groups
@@ -110,19 +114,19 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                     umma_f16(tm_o[b], dp, dv + 128 * kk, kIdO, kk > 0);
                 }
                 umma_commit(&o_full[b]);
-                umma_commit(&p_empty[b]);
+                umma_commit(p_empty);
                 umma_commit(&kv_empty[st]);
             };
             mbar_wait(q_full, 0);
             for (int j = 0; j < n_blocks; ++j) {
-                const int b = j & 1, st = j & 1;
+                const int st = j & 1;
                 mbar_wait(&kv_full[st], (j >> 1) & 1);
-                mbar_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+                mbar_wait(s_empty, (j & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint64_t dk = kmajor_sw128_desc(smem_u32(kv_s + st * 2 * kAtTile));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(tm_s[b], dq + 2 * k, dk + 2 * k, kIdS, k > 0);
-                umma_commit(&s_full[b]);
+                for (int k = 0; k < 4; ++k) umma_f16(tm_s, dq + 2 * k, dk + 2 * k, kIdS, k > 0);
+                umma_commit(s_full);
                 if (j > 0) issue_pv(j - 1);
             }
             issue_pv(n_blocks - 1);
@@ -139,29 +143,29 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
         float m = -3.0e38f, l = 0.f;
         const uint32_t p_row = row * 128, sw = row & 7;
         for (int j = 0; j < n_blocks; ++j) {
-            const int b = j & 1;
             const int valid = min(128, p.S - j * 128);         // keys of this block that exist
-            mbar_wait(&s_full[b], (j >> 1) & 1);
+            mbar_wait(s_full, j & 1);
             tc_fence_after_sync();
-            float mx = m;
+            float raw = -3.0e38f;
 #pragma unroll 1
             for (int g = 0; g < 4; ++g) {
                 uint32_t v[32];
-                tmem_ld_32x32(tm_s[b] + lane_base + g * 32, v);
+                tmem_ld_32x32(tm_s + lane_base + g * 32, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                    if (g * 32 + c < valid) mx = fmaxf(mx, __uint_as_float(v[c]) * sc);
+                    if (g * 32 + c < valid) raw = fmaxf(raw, __uint_as_float(v[c]));
             }
+            const float mx = fmaxf(m, raw * sc);               // sc > 0: the maximum commutes with the scaling
             const float alpha = exp2f(m - mx);
             m = mx;
-            mbar_wait(&p_empty[b], ((j >> 1) & 1) ^ 1);        // PV_{j-2} has finished reading this P buffer
-            uint8_t* pb = p_s + b * 2 * kAtTile;
+            mbar_wait(p_empty, (j & 1) ^ 1);                   // PV_{j-1} has finished reading the P tile
+            uint8_t* pb = p_s;
             float rs = 0.f;
 #pragma unroll 1
             for (int g = 0; g < 4; ++g) {
                 uint32_t v[32];
-                tmem_ld_32x32(tm_s[b] + lane_base + g * 32, v);
+                tmem_ld_32x32(tm_s + lane_base + g * 32, v);
                 tmem_ld_wait();
                 uint32_t h2[16];
 #pragma unroll
@@ -185,7 +189,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
             tc_fence_before_sync();
             fence_proxy_async_smem();                          // P stores -> visible to the UMMA (async proxy)
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&s_empty[b]); mbar_arrive(&p_full[b]); }
+            if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
             if (j > 0) {                                       // fold in the previous block's P V (relative to the old maximum)
                 const int bp = (j - 1) & 1;
                 mbar_wait(&o_full[bp], ((j - 1) >> 1) & 1);
@@ -233,7 +237,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<512>(tmem);
+    if (warp == 2) tmem_dealloc<256>(tmem);
 }
 
 }  // namespace fad

@@ -158,8 +158,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE, WMODE, PAIR>();
     constexpr int kBRows = (WMODE != 0 ? 2 : 1) * N_TILE;           // rows of the packed weight tensor per N tile
     constexpr int kNLoc = PAIR ? N_TILE / 2 : N_TILE;               // weight rows (output channels) THIS CTA stages
-    constexpr uint32_t kTmemCols = (LO8 ? 4 : 2) * N_TILE;          // two chunk buffers (+ two low-part buffers)
-    constexpr uint32_t kIdesc = make_idesc(FMT_F16, PAIR ? 2 * kTileM : kTileM, N_TILE);
+    // SPLIT_W: hi and lo weight rows are ONE B operand of N = 2 N_TILE rows ([Wh | Wl] is how a stage holds them), the
+    // product lands in two column halves of the accumulator (hi: [0, N_TILE), lo: [N_TILE, 2 N_TILE)) that the epilogue
+    // adds.  One MMA per K slice instead of two: the A tile is fetched from shared memory once, and the tensor pipe's
+    // operand fetch - what limits M128 x N128 MMAs (profiles/r2_umma_issue_patterns.json: 1.89 PFLOP/s issued as 2 x N128
+    // against 2.24 as 1 x N256) - moves 25 % fewer bytes per FLOP.
+    constexpr uint32_t kBufCols = (SPLIT_W ? 2 : 1) * N_TILE;       // TMEM columns of one chunk buffer
+    constexpr uint32_t kTmemCols = LO8 ? 4 * N_TILE : 2 * kBufCols; // two chunk buffers (+ two low-part buffers)
+    constexpr uint32_t kIdesc = make_idesc(FMT_F16, PAIR ? 2 * kTileM : kTileM, SPLIT_W ? 2 * N_TILE : N_TILE);
     constexpr uint32_t kIdesc8 = make_idesc(FMT_E4M3, PAIR ? 2 * kTileM : kTileM, N_TILE);
     constexpr uint32_t kWhBytes = kNLoc * kBlockK * 2;
     constexpr uint32_t kOffWl8 = kABytes + kWhBytes;                // stage layout (LO8): A16 | Wh | Wl8 | A8
@@ -238,9 +244,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                         if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);
                         const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
                         tma_load_4d_pair(st, &map_x, bar, cb * kBlockK, w0 + dw, h0 + dh, n0);
-                        tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * kNLoc);
-                        if (SPLIT_W)
-                            tma_load_2d_pair(st + kABytes + kWhBytes, &map_w, bar, ks * kBlockK, nt * kBRows + N_TILE + (int)rank * kNLoc);
+                        // SPLIT_W: B of the pair's N = 2 N_TILE MMA = [Wh | Wl]; rank 0 stages the hi rows, rank 1 the lo rows
+                        // (one box of N_TILE rows each).  LO8: this CTA's half of the hi rows.
+                        if (SPLIT_W) tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * N_TILE);
+                        else         tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * kNLoc);
                         if (LO8) {
                             tma_load_2d_pair(st + kOffWl8, &map_wl8, bar, ks * kBlockK, nt * N_TILE + (int)rank * kNLoc);
                             tma_load_4d_pair(st + kOffA8, &map_x8, bar, cb * kBlockK, w0 + dw, h0 + dh, n0);
@@ -272,7 +279,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     const int ks1 = min(ks0 + chunk_len, ksteps);
                     mbar_wait(&tmem_empty[buf], buf_ph ^ 1);
                     tc_fence_after_sync();
-                    const uint32_t d_tmem = tmem_base + buf * N_TILE;
+                    const uint32_t d_tmem = tmem_base + buf * kBufCols;
                     for (int ks = ks0; ks < ks1; ++ks) {
                         mbar_wait(&full[s], ph);
                         tc_fence_after_sync();
@@ -282,14 +289,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
                             // +32 B along K inside the 128-B swizzle atom == +2 in the 16-B address field
-                            if (PAIR) {
-                                umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
-                                if (SPLIT_W) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k + (kNLoc * 128 / 16), kIdesc, 1);
-                            } else {
-                            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
-                            if (SPLIT_W)      // lo half of the weights: N_TILE rows (x 128 B) further down the stage
-                                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k + (N_TILE * 128 / 16), kIdesc, 1);
-                            }
+                            if (PAIR) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
+                            else      umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
                         }
                         if (LO8) {
                             // The E4M3 low-part MMAs of the last `lo8_group` k-steps are issued together, after their
@@ -374,12 +375,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&tmem_full[buf], buf_ph);
                 tc_fence_after_sync();
-                const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + buf * N_TILE + half * kColsPerWarp;
+                const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + buf * kBufCols + half * kColsPerWarp;
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     uint32_t v[32];
                     tmem_ld_32x32(t_row + g * 32, v);
-                    tmem_ld_wait();
+                    if (SPLIT_W) {                             // A Wh^T + A Wl^T: the two column halves of the stacked product
+                        uint32_t w[32];
+                        tmem_ld_32x32(t_row + N_TILE + g * 32, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+                    } else {
+                        tmem_ld_wait();
+                    }
                     if (c == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[g * 32 + j] = __uint_as_float(v[j]);

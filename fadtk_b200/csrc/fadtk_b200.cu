@@ -249,7 +249,8 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
     const uint64_t ws[1] = {K * 2};
     // rows per weight box: mode 1 fetches hi + lo of a tile at once, mode 2 the hi rows only; a CTA of a pair fetches
     // its half of the hi rows and its half of the lo rows as two boxes
-    const uint32_t wb[2] = {64, (uint32_t)(g.pair ? g.n_tile / 2 : g.n_tile * (g.split_w == 1 ? 2 : 1))};
+    // (mode 1 pair: one box of n_tile rows - rank 0 the hi rows, rank 1 the lo rows of the stacked N = 2 n_tile operand)
+    const uint32_t wb[2] = {64, (uint32_t)(g.pair ? (g.split_w == 1 ? g.n_tile : g.n_tile / 2) : g.n_tile * (g.split_w == 1 ? 2 : 1))};
     return encode_f16_map(mw, w, 2, wd, ws, wb);
 }
 
@@ -265,6 +266,7 @@ int launch_attention_umma(fad_handle* h, const __half* qkv, long long n_clips, i
     static bool attr_set = false;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(fad::attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fad::kAtSmem));
+        CK(cudaFuncSetAttribute(fad::attention_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   // two CTAs of 112 KiB per SM
         attr_set = true;
     }
     if (heads * 64 != d) return fail("attention_umma: head dimension must be 64");
@@ -778,7 +780,7 @@ int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, i
         CK(cudaGetLastError());
         prof_end(h, FAD_PROF_STATS, ev, st);
         ev = prof_begin(h, st);
-        fad::stats_dmma_reduce_kernel<<<p.n_pairs, 256, 0, st>>>(p, acc);
+        fad::stats_dmma_reduce_kernel<<<dim3(p.n_pairs, fad::kSdTile * fad::kSdTile / 256), 256, 0, st>>>(p, acc);
         CK(cudaGetLastError());
         prof_end(h, FAD_PROF_STATS_REDUCE, ev, st);
         h->launches += 2;

@@ -454,24 +454,33 @@ stats_dmma_kernel(const __half* __restrict__ E, const StatsDmmaParams p)
     }
 }
 
-// acc += sum over row splits of the job tiles, fixed order.  grid = (n_pairs), block = 256
-__global__ void stats_dmma_reduce_kernel(StatsDmmaParams p, double* __restrict__ acc)
+// acc += sum over row splits of the job tiles, fixed order.  grid = (n_pairs, 16): block (pair, y) owns 256 of the
+// tile's 4096 entries (a 3-block grid at d = 128 took 0.33 ms for 12 MB of partial tiles - longer than the Gram itself)
+__global__ void __launch_bounds__(256) stats_dmma_reduce_kernel(StatsDmmaParams p, double* __restrict__ acc)
 {
     const int pair = blockIdx.x;
     int ti, tj;
     pair_to_tiles(pair, p.n_tiles, ti, tj);
     const int d = p.d;
     double* outer = acc + 1 + d;
-    for (int e = threadIdx.x; e < kSdTile * kSdTile; e += blockDim.x) {
+    {
+        const int e = blockIdx.y * 256 + threadIdx.x;
         const int row = e / kSdTile, col = e % kSdTile;
-        double v = 0.0;
-        for (int s = 0; s < p.n_splits; ++s)
-            v += p.ws_tiles[((size_t)pair * p.n_splits + s) * kSdTile * kSdTile + e];
+        const double* src = p.ws_tiles + (size_t)pair * p.n_splits * kSdTile * kSdTile + e;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int s = 0;
+        for (; s + 4 <= p.n_splits; s += 4) {                   // four loads in flight; the order of the sum stays fixed
+            const double a = src[(size_t)(s + 0) * kSdTile * kSdTile], b = src[(size_t)(s + 1) * kSdTile * kSdTile];
+            const double c = src[(size_t)(s + 2) * kSdTile * kSdTile], e4 = src[(size_t)(s + 3) * kSdTile * kSdTile];
+            v0 += a; v1 += b; v2 += c; v3 += e4;
+        }
+        for (; s < p.n_splits; ++s) v0 += src[(size_t)s * kSdTile * kSdTile];
+        const double v = (v0 + v1) + (v2 + v3);
         const int I = ti * kSdTile + row, J = tj * kSdTile + col;
         outer[(size_t)I * d + J] += v;
         if (ti != tj) outer[(size_t)J * d + I] += v;
     }
-    if (ti == tj) {
+    if (ti == tj && blockIdx.y == 0) {
         for (int cidx = threadIdx.x; cidx < kSdTile; cidx += blockDim.x) {
             double v = 0.0;
             for (int s = 0; s < p.n_splits; ++s) v += p.ws_sums[((size_t)ti * p.n_splits + s) * kSdTile + cidx];
@@ -479,7 +488,7 @@ __global__ void stats_dmma_reduce_kernel(StatsDmmaParams p, double* __restrict__
             acc[1 + (size_t)d + (size_t)d * d + ti * kSdTile + cidx] += v;            // centring term: same y
         }
     }
-    if (pair == 0 && threadIdx.x == 0) acc[0] += (double)p.n_rows;
+    if (pair == 0 && blockIdx.y == 0 && threadIdx.x == 0) acc[0] += (double)p.n_rows;
 }
 
 // --------------------------------------------------------------------------------------
