@@ -53,6 +53,9 @@ SIGNATURES = {
     "fad_stats_accumulate": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp, C.c_int, c_vp]),
     "fad_stats_accumulate_gather": (C.c_int, [c_vp, c_vp, c_ll, c_vp, c_ll, C.c_int, c_vp, c_vp, c_vp]),
     "fad_stats_finalize": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp]),
+    "fad_file_means": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "fad_stats_accumulate_f64": (C.c_int, [c_vp, c_vp, c_ll, C.c_int, c_vp, c_vp]),
+    "fad_stats_finalize_mirrored": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "fad_sqrt_psd": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "fad_frechet_presqrt": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
@@ -468,6 +471,27 @@ class Engine:
         cov = torch.empty((d, d), dtype=torch.float64, device=acc.device)
         _check(lib().fad_stats_finalize(self._h, acc.data_ptr(), shift.data_ptr(), d,
                                         mu.data_ptr(), cov.data_ptr(), _stream()))
+        return mu, cov
+
+    def file_means(self, emb: torch.Tensor, rows_per_file: int):
+        """fp16 [n_files * r, d] -> (m64, m16) fp64 [n_files, d]: exact per-file means and the reference's fp16-rounded ones"""
+        n_files, d = emb.shape[0] // rows_per_file, emb.shape[1]
+        m64 = torch.empty((n_files, d), dtype=torch.float64, device=emb.device)
+        m16 = torch.empty_like(m64)
+        _check(lib().fad_file_means(self._h, emb.data_ptr(), n_files, rows_per_file, d, m64.data_ptr(), m16.data_ptr(), _stream()))
+        return m64, m16
+
+    def stats_accumulate_f64(self, rows: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
+        assert rows.dtype == torch.float64 and rows.is_contiguous()
+        _check(lib().fad_stats_accumulate_f64(self._h, rows.data_ptr(), rows.shape[0], rows.shape[1], acc.data_ptr(), _stream()))
+        return acc
+
+    def stats_finalize_mirrored(self, acc, acc64, acc16, shift, rows_per_file: int, d: int):
+        """(mu, cov) as the reference's calculate_embd_statistics_online gives them for equal-length files (utils.py:13-46)"""
+        mu = torch.empty(d, dtype=torch.float64, device=acc.device)
+        cov = torch.empty((d, d), dtype=torch.float64, device=acc.device)
+        _check(lib().fad_stats_finalize_mirrored(self._h, acc.data_ptr(), acc64.data_ptr(), acc16.data_ptr(), shift.data_ptr(),
+                                                 int(rows_per_file), d, mu.data_ptr(), cov.data_ptr(), _stream()))
         return mu, cov
 
     # ----------------------------------------------------------------- Frechet

@@ -776,7 +776,7 @@ int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, i
         if (ensure((void**)&h->ws_sums, &h->ws_sums_cap, (size_t)p.n_tiles * p.n_splits * fad::kSdTile * 8)) return 1;
         p.ws_tiles = h->ws_tiles; p.ws_sums = h->ws_sums;
         size_t ev = prof_begin(h, st);
-        fad::stats_dmma_kernel<<<(unsigned)jobs, 256, 0, st>>>(E, p);
+        fad::stats_dmma_kernel<__half><<<(unsigned)jobs, 256, 0, st>>>(E, p);
         CK(cudaGetLastError());
         prof_end(h, FAD_PROF_STATS, ev, st);
         ev = prof_begin(h, st);
@@ -817,6 +817,65 @@ int fad_stats_accumulate(fad_handle* h, const void* emb_f16, long long n_rows, i
     CK(cudaGetLastError());
     prof_end(h, FAD_PROF_STATS_REDUCE, ev, st);
     h->launches += 2;
+    return 0;
+}
+
+// ---- the reference's per-file statistics semantics for equal-length files, on the device (fadtk/utils.py:13-46) ----
+int fad_file_means(fad_handle* h, const void* emb_f16, long long n_files, int rows_per_file, int d,
+                   double* m64_out, double* m16_out, void* stream) {
+    if (!h) return fail("null handle");
+    if (n_files <= 0) return 0;
+    if (rows_per_file <= 0 || d <= 0) return fail("bad shape");
+    CK(cudaSetDevice(h->device));
+    long long blocks = (n_files * d + 255) / 256;
+    if (blocks > (long long)h->num_sms * 16) blocks = (long long)h->num_sms * 16;
+    fad::file_means_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(emb_f16), n_files, rows_per_file, d, m64_out, m16_out);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// exact Gram statistics of fp64 rows (no shift): acc[0] += n, acc[1..d] += sum x, outer += sum x x^T (DMMA, fixed order)
+int fad_stats_accumulate_f64(fad_handle* h, const double* rows, long long n_rows, int d, double* acc, void* stream) {
+    if (!h) return fail("null handle");
+    if (n_rows <= 0) return 0;
+    if (d % 64 != 0) return fail("d must be a multiple of 64");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    fad::StatsDmmaParams p;
+    p.n_rows = n_rows; p.d = d; p.n_tiles = d / fad::kSdTile;
+    p.n_pairs = p.n_tiles * (p.n_tiles + 1) / 2;
+    const long long stages = (n_rows + fad::kSdRows - 1) / fad::kSdRows;
+    long long want = (4LL * h->num_sms + p.n_pairs - 1) / p.n_pairs;
+    if (want < 1) want = 1;
+    long long per = (stages + want - 1) / want;
+    if (per < 4) per = 4;
+    p.n_splits = (int)((stages + per - 1) / per);
+    p.rows_per_split = per * fad::kSdRows;
+    p.shift = nullptr;
+    const size_t jobs = (size_t)p.n_pairs * p.n_splits;
+    if (ensure((void**)&h->ws_tiles, &h->ws_tiles_cap, jobs * fad::kSdTile * fad::kSdTile * 8)) return 1;
+    if (ensure((void**)&h->ws_sums, &h->ws_sums_cap, (size_t)p.n_tiles * p.n_splits * fad::kSdTile * 8)) return 1;
+    p.ws_tiles = h->ws_tiles; p.ws_sums = h->ws_sums;
+    fad::stats_dmma_kernel<double><<<(unsigned)jobs, 256, 0, st>>>(rows, p);
+    fad::stats_dmma_reduce_kernel<<<dim3(p.n_pairs, fad::kSdTile * fad::kSdTile / 256), 256, 0, st>>>(p, acc);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return 0;
+}
+
+int fad_stats_finalize_mirrored(fad_handle* h, const double* acc, const double* acc_means64, const double* acc_means16,
+                                const void* shift_f16, int rows_per_file, int d, double* mu_out, double* cov_out, void* stream) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    static const int keep = [] { const char* e = getenv("FADTK_SINGLE_FRAME_FILES"); return (e && std::string(e) == "keep") ? 1 : 0; }();
+    const size_t total = (size_t)d * d;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (blocks > (unsigned)h->num_sms * 8) blocks = h->num_sms * 8;
+    fad::stats_finalize_mirrored_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        acc, acc_means64, acc_means16, reinterpret_cast<const __half*>(shift_f16), rows_per_file, d, keep, mu_out, cov_out);
+    CK(cudaGetLastError());
+    h->launches++;
     return 0;
 }
 

@@ -352,9 +352,12 @@ __device__ __forceinline__ void stats_dmma_884(double& c0, double& c1, double a,
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// In = __half (embeddings; shift vector applied) or double (per-file mean rows of the reference's online merge, no shift)
+template <typename In>
 __global__ void __launch_bounds__(256, 2)
-stats_dmma_kernel(const __half* __restrict__ E, const StatsDmmaParams p)
+stats_dmma_kernel(const In* __restrict__ E, const StatsDmmaParams p)
 {
+    constexpr bool kHalf = sizeof(In) == 2;
     __shared__ __align__(16) double Ys[2][2][kSdRows][kSdPitch];     // [panel i | j][buffer][row][col]
     const int job = blockIdx.x;
     const int pair = job / p.n_splits, split = job % p.n_splits;
@@ -368,30 +371,41 @@ stats_dmma_kernel(const __half* __restrict__ E, const StatsDmmaParams p)
     const int fr = lane >> 2, fk = lane & 3;
     const int lrow = t >> 4, lcol = (t & 15) * 4;               // loader: row of the stage, first of 4 columns
 
-    double si[4], sj[4];
+    double si[4] = {0.0, 0.0, 0.0, 0.0}, sj[4] = {0.0, 0.0, 0.0, 0.0};
+    if (kHalf && p.shift != nullptr) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        si[e] = (double)__half2float(p.shift[ti * kSdTile + lcol + e]);
-        sj[e] = (double)__half2float(p.shift[tj * kSdTile + lcol + e]);
+        for (int e = 0; e < 4; ++e) {
+            si[e] = (double)__half2float(p.shift[ti * kSdTile + lcol + e]);
+            sj[e] = (double)__half2float(p.shift[tj * kSdTile + lcol + e]);
+        }
     }
-    const __half* src_i = E + (size_t)ti * kSdTile + lcol;
-    const __half* src_j = E + (size_t)tj * kSdTile + lcol;
-    uint2 ri = make_uint2(0, 0), rj = make_uint2(0, 0);
+    const In* src_i = E + (size_t)ti * kSdTile + lcol;
+    const In* src_j = E + (size_t)tj * kSdTile + lcol;
+    double ri[4] = {0.0, 0.0, 0.0, 0.0}, rj[4] = {0.0, 0.0, 0.0, 0.0};        // the 4 values of this thread, already as fp64
     bool rok = false;
+    auto load4 = [&](const In* ptr, double (&v)[4]) {
+        if constexpr (kHalf) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(ptr));
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            v[0] = (double)f0.x; v[1] = (double)f0.y; v[2] = (double)f1.x; v[3] = (double)f1.y;
+        } else {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(ptr)), b = __ldg(reinterpret_cast<const double2*>(ptr) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        }
+    };
     auto fetch = [&](long long r0) {
         const long long r = r0 + lrow;
         rok = r < row_end;
         if (rok) {
-            ri = __ldg(reinterpret_cast<const uint2*>(src_i + (size_t)r * p.d));
-            if (!diag) rj = __ldg(reinterpret_cast<const uint2*>(src_j + (size_t)r * p.d));
+            load4(src_i + (size_t)r * p.d, ri);
+            if (!diag) load4(src_j + (size_t)r * p.d, rj);
         }
     };
     double colsum[4] = {0.0, 0.0, 0.0, 0.0};
-    auto unpack = [](uint2 v, const double (&s)[4], bool ok, double (&y)[4]) {
-        const __half2 h0 = *reinterpret_cast<const __half2*>(&v.x), h1 = *reinterpret_cast<const __half2*>(&v.y);
-        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        y[0] = ok ? (double)f0.x - s[0] : 0.0;  y[1] = ok ? (double)f0.y - s[1] : 0.0;
-        y[2] = ok ? (double)f1.x - s[2] : 0.0;  y[3] = ok ? (double)f1.y - s[3] : 0.0;
+    auto unpack = [](const double (&v)[4], const double (&s)[4], bool ok, double (&y)[4]) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) y[e] = ok ? v[e] - s[e] : 0.0;
     };
     auto stage = [&](int buf) {
         double y[4];
@@ -550,6 +564,60 @@ stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
         atomicAdd(&acc[1 + (size_t)d + (size_t)d * d + ti * 64 + threadIdx.x], csum);
     }
     if (blockIdx.x == 0 && ti == 0 && tj == 0 && threadIdx.x == 0) atomicAdd(&acc[0], (double)n_rows);
+}
+
+// Per-file means of equal-length files (file f = rows [f r, (f + 1) r) of emb): the exact mean in fp64 and the mean as
+// the reference's _process_file returns it for an fp16 .npy (np.mean of an fp16 array: fp32 accumulation, result rounded
+// to fp16 - fadtk/utils.py:14), both stored as fp64 rows for the Gram kernel.  grid-stride over files x d.
+__global__ void file_means_kernel(const __half* __restrict__ emb, long long n_files, int r, int d,
+                                  double* __restrict__ m64, double* __restrict__ m16)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_files * d; e += (long long)gridDim.x * blockDim.x) {
+        const long long f = e / d;
+        const int c = (int)(e - f * d);
+        const __half* src = emb + ((size_t)f * r) * d + c;
+        double s64 = 0.0;
+        float s32 = 0.f;
+        for (int k = 0; k < r; ++k) { const float v = __half2float(src[(size_t)k * d]); s64 += (double)v; s32 += v; }
+        m64[e] = s64 / (double)r;
+        m16[e] = (double)__half2float(__float2half_rn(s32 / (float)r));
+    }
+}
+
+// mu, cov as the reference's online merge computes them for n_files files of r rows each (fadtk/utils.py:13-46):
+//   mu_ref = sum_f r m16_f / n,   S_ref = S_exact - sum_f r (m64_f - mu)(m64_f - mu)^T + sum_f r (m16_f - mu_ref)(m16_f - mu_ref)^T
+// from the three packed accumulators (rows; exact file means; fp16-rounded file means - the latter two unshifted).
+// r == 1 reproduces the reference's all-NaN covariance (np.cov of a single row) unless keep_single.
+__global__ void stats_finalize_mirrored_kernel(const double* __restrict__ acc, const double* __restrict__ acc64,
+                                               const double* __restrict__ acc16, const __half* __restrict__ shift,
+                                               int r, int d, int keep_single, double* __restrict__ mu_out, double* __restrict__ cov_out)
+{
+    const double n = acc[0];
+    const double* sum_x = acc + 1;
+    const double* outer = acc + 1 + d;
+    const double* sum_y = acc + 1 + (size_t)d + (size_t)d * d;
+    const double* s64f = acc64 + 1;            // sum_f m64_f
+    const double* o64 = acc64 + 1 + d;         // sum_f m64_f m64_f^T
+    const double* s16f = acc16 + 1;
+    const double* o16 = acc16 + 1 + d;
+    const double w = (double)r;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)d * d; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / d), j = (int)(e % d);
+        const double mu_i = (double)__half2float(shift[i]) + (n > 0.0 ? sum_x[i] / n : 0.0);
+        const double mu_j = (double)__half2float(shift[j]) + (n > 0.0 ? sum_x[j] / n : 0.0);
+        const double mr_i = n > 0.0 ? w * s16f[i] / n : 0.0, mr_j = n > 0.0 ? w * s16f[j] / n : 0.0;
+        double c = 0.0;
+        if (n >= 2.0) {
+            const double s_exact = outer[e] - sum_y[i] * sum_y[j] / n;                               // (n - 1) cov_exact
+            const double b64 = w * o64[e] - mu_i * (w * s64f[j]) - (w * s64f[i]) * mu_j + n * mu_i * mu_j;
+            const double b16 = w * o16[e] - mr_i * (w * s16f[j]) - (w * s16f[i]) * mr_j + n * mr_i * mr_j;
+            c = (s_exact - b64 + b16) / (n - 1.0);
+            if (r == 1 && !keep_single) c = nan;
+        }
+        cov_out[e] = c;
+        if (j == 0) mu_out[i] = mr_i;
+    }
 }
 
 // mu = shift + sum(x-s)/n ; cov = (outer - sum(y) sum(y)^T / n) / (n - 1)   (cov = 0 when n < 2,

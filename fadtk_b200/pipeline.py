@@ -118,36 +118,20 @@ class EvalSetFAD:
         d, r = self.d, self.rows_per_clip
         shift = self._shared_shift(emb)
         n_acc = self.eng.stats_acc_len(d)
-        buf = torch.zeros(n_acc + (2 * d * d + d if self.mirror else 0), dtype=torch.float64, device=self.dev)
+        # ONE buffer = ONE all-reduce: [rows | exact per-clip means | fp16-rounded per-clip means], all packed accumulators
+        buf = torch.zeros(n_acc * (3 if self.mirror else 1), dtype=torch.float64, device=self.dev)
         acc = buf[:n_acc]
         self.eng.stats_accumulate(emb, shift, acc)
         if self.mirror:
-            # per-clip means: exact (fp64) and as numpy would return them for an fp16 file (fp16)
-            per = emb.view(-1, r, d)
-            m64 = per.double().mean(1)
-            m16 = per.float().mean(1).to(torch.float16).double()
-            w = float(r)
-            buf[n_acc:n_acc + d * d] = (w * (m64.t() @ m64)).reshape(-1)
-            buf[n_acc + d * d:n_acc + 2 * d * d] = (w * (m16.t() @ m16)).reshape(-1)
-            buf[n_acc + 2 * d * d:] = w * m16.sum(0)
+            # the reference's per-file statistics (one clip = one file): np.mean of an fp16 file is fp16 (utils.py:14)
+            m64, m16 = self.eng.file_means(emb, r)
+            self.eng.stats_accumulate_f64(m64, buf[n_acc:2 * n_acc])
+            self.eng.stats_accumulate_f64(m16, buf[2 * n_acc:])
         dist.allreduce_sum_(buf)                              # the only cross-GPU exchange
-        mu, cov = self.eng.stats_finalize(acc, shift, d)
         if self.mirror:
-            n = acc[0]
-            p64 = buf[n_acc:n_acc + d * d].view(d, d)
-            p16 = buf[n_acc + d * d:n_acc + 2 * d * d].view(d, d)
-            s16 = buf[n_acc + 2 * d * d:]
-            s64 = mu * n                                      # sum of all rows
-            mu_ref = s16 / n
-            # sum_f n_f (m_f - c)(m_f - c)^T = P - c s^T - s c^T + n c c^T
-            b64 = p64 - torch.outer(mu, s64) - torch.outer(s64, mu) + n * torch.outer(mu, mu)
-            b16 = p16 - torch.outer(mu_ref, s16) - torch.outer(s16, mu_ref) + n * torch.outer(mu_ref, mu_ref)
-            cov = (cov * (n - 1) - b64 + b16) / (n - 1)
-            mu = mu_ref
-            if r == 1:                                        # one frame per "file": the reference's covariance is NaN (utils.py:16)
-                import os
-                if os.environ.get("FADTK_SINGLE_FRAME_FILES", "") != "keep":
-                    cov = torch.full_like(cov, float("nan"))
+            mu, cov = self.eng.stats_finalize_mirrored(acc, buf[n_acc:2 * n_acc], buf[2 * n_acc:], shift, r, d)
+        else:
+            mu, cov = self.eng.stats_finalize(acc, shift, d)
         if self._baseline is None:                            # sqrt(C_base) once per baseline, not per eval set
             self._baseline = _native.Baseline(self.eng, self.mu_base, self.cov_base)
         return self._baseline.frechet(mu.contiguous(), cov.contiguous())

@@ -193,6 +193,19 @@ int fad_comm_destroy(fad_handle* h);
 int fad_stats_allreduce(fad_handle* h, void* nccl_comm_or_null, double* acc, int d, void* stream);
 int fad_allreduce_sum_f64(fad_handle* h, void* nccl_comm_or_null, double* buf, long long n_values, void* stream);
 
+/* The reference's DIRECTORY statistics (per-file np.mean rounded to fp16, per-file scatter, Chan merge:
+ * fadtk/utils.py:13-46) for n_files files of rows_per_file rows each, without leaving the device:
+ *   fad_file_means               m64[f], m16[f] (fp64 rows [n_files, d]): the exact mean of file f and its mean as the
+ *                                reference's _process_file returns it (fp32 accumulation rounded to fp16)
+ *   fad_stats_accumulate_f64     exact Gram statistics (DMMA) of fp64 rows, unshifted, into a packed accumulator
+ *   fad_stats_finalize_mirrored  (mu, cov) exactly as calculate_embd_statistics_online returns them, from the packed
+ *                                accumulators of the rows, of m64 and of m16 (all three additive: all-reduce them first);
+ *                                rows_per_file == 1 gives the reference's all-NaN covariance (utils.py:16) */
+int fad_file_means(fad_handle* h, const void* emb_f16, long long n_files, int rows_per_file, int d,
+                   double* m64_out, double* m16_out, void* stream);
+int fad_stats_accumulate_f64(fad_handle* h, const double* rows, long long n_rows, int d, double* acc, void* stream);
+int fad_stats_finalize_mirrored(fad_handle* h, const double* acc, const double* acc_means64, const double* acc_means16,
+                                const void* shift_f16, int rows_per_file, int d, double* mu_out, double* cov_out, void* stream);
 /* rows emb[idx[i]] for i < n_idx (FAD-inf bootstrap, fadtk/fad.py:333-336) */
 int fad_stats_accumulate_gather(fad_handle* h, const void* emb_f16, long long n_src_rows,
                                 const long long* idx, long long n_idx, int d,
