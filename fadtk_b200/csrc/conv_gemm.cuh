@@ -144,7 +144,7 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int N_TILE, int STAGES, int WMODE, int PAIR = 0>
+template <int N_TILE, int STAGES, int WMODE, int PAIR = 0, int STACK = 0>
 __global__ void __launch_bounds__(kConvGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                  const __grid_constant__ CUtensorMap map_w,
@@ -158,14 +158,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
     constexpr uint32_t kStageBytes = conv_gemm_stage_bytes<N_TILE, WMODE, PAIR>();
     constexpr int kBRows = (WMODE != 0 ? 2 : 1) * N_TILE;           // rows of the packed weight tensor per N tile
     constexpr int kNLoc = PAIR ? N_TILE / 2 : N_TILE;               // weight rows (output channels) THIS CTA stages
-    // SPLIT_W: hi and lo weight rows are ONE B operand of N = 2 N_TILE rows ([Wh | Wl] is how a stage holds them), the
-    // product lands in two column halves of the accumulator (hi: [0, N_TILE), lo: [N_TILE, 2 N_TILE)) that the epilogue
-    // adds.  One MMA per K slice instead of two: the A tile is fetched from shared memory once, and the tensor pipe's
-    // operand fetch - what limits M128 x N128 MMAs (profiles/r2_umma_issue_patterns.json: 1.89 PFLOP/s issued as 2 x N128
-    // against 2.24 as 1 x N256) - moves 25 % fewer bytes per FLOP.
-    constexpr uint32_t kBufCols = (SPLIT_W ? 2 : 1) * N_TILE;       // TMEM columns of one chunk buffer
+    // STACKED (SPLIT_W && STACK; measurement variant, off by default): hi and lo weight rows as ONE B operand of N = 2 N_TILE
+    // rows ([Wh | Wl] is how a stage holds them); the product lands in two column halves of the accumulator (hi: [0, N_TILE),
+    // lo: [N_TILE, 2 N_TILE)) that the epilogue adds.  One MMA per K slice instead of two, A fetched from shared memory
+    // once: 16 % faster on the bare tensor pipe (profiles/r2_umma_issue_patterns.json: 2.24 vs 1.89 PFLOP/s issued) - but
+    // not in this kernel, which runs against the power cap, and it costs a second TMEM read per epilogue group
+    // (profiles/r2_ncu_vggish_pair.md); the default accumulates A Wh^T and A Wl^T into the same TMEM tile.
+    constexpr bool STACKED = SPLIT_W && STACK != 0;
+    constexpr uint32_t kBufCols = (STACKED ? 2 : 1) * N_TILE;       // TMEM columns of one chunk buffer
     constexpr uint32_t kTmemCols = LO8 ? 4 * N_TILE : 2 * kBufCols; // two chunk buffers (+ two low-part buffers)
-    constexpr uint32_t kIdesc = make_idesc(FMT_F16, PAIR ? 2 * kTileM : kTileM, SPLIT_W ? 2 * N_TILE : N_TILE);
+    constexpr uint32_t kIdesc = make_idesc(FMT_F16, PAIR ? 2 * kTileM : kTileM, STACKED ? 2 * N_TILE : N_TILE);
     constexpr uint32_t kIdesc8 = make_idesc(FMT_E4M3, PAIR ? 2 * kTileM : kTileM, N_TILE);
     constexpr uint32_t kWhBytes = kNLoc * kBlockK * 2;
     constexpr uint32_t kOffWl8 = kABytes + kWhBytes;                // stage layout (LO8): A16 | Wh | Wl8 | A8
@@ -244,10 +246,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                         if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);
                         const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
                         tma_load_4d_pair(st, &map_x, bar, cb * kBlockK, w0 + dw, h0 + dh, n0);
-                        // SPLIT_W: B of the pair's N = 2 N_TILE MMA = [Wh | Wl]; rank 0 stages the hi rows, rank 1 the lo rows
-                        // (one box of N_TILE rows each).  LO8: this CTA's half of the hi rows.
-                        if (SPLIT_W) tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * N_TILE);
-                        else         tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * kNLoc);
+                        // this CTA's half of the hi rows (and of the lo rows: a second box).  STACKED: B of the pair's N = 2 N_TILE
+                        // MMA is [Wh | Wl]: rank 0 stages all hi rows, rank 1 all lo rows (one box of N_TILE rows each)
+                        if (STACKED) tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * N_TILE);
+                        else {
+                            tma_load_2d_pair(st + kABytes, &map_w, bar, ks * kBlockK, nt * kBRows + (int)rank * kNLoc);
+                            if (SPLIT_W)
+                                tma_load_2d_pair(st + kABytes + kWhBytes, &map_w, bar, ks * kBlockK, nt * kBRows + N_TILE + (int)rank * kNLoc);
+                        }
                         if (LO8) {
                             tma_load_2d_pair(st + kOffWl8, &map_wl8, bar, ks * kBlockK, nt * N_TILE + (int)rank * kNLoc);
                             tma_load_4d_pair(st + kOffA8, &map_x8, bar, cb * kBlockK, w0 + dw, h0 + dh, n0);
@@ -291,6 +297,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                             // +32 B along K inside the 128-B swizzle atom == +2 in the 16-B address field
                             if (PAIR) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
                             else      umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, kIdesc, (ks > ks0) || (k > 0));
+                            if (SPLIT_W && !STACKED) {         // lo rows: kNLoc rows (x 128 B) further down the stage, same accumulator
+                                if (PAIR) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k + (kNLoc * 128 / 16), kIdesc, 1);
+                                else      umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k + (kNLoc * 128 / 16), kIdesc, 1);
+                            }
                         }
                         if (LO8) {
                             // The E4M3 low-part MMAs of the last `lo8_group` k-steps are issued together, after their
@@ -380,7 +390,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 for (int g = 0; g < kGroups; ++g) {
                     uint32_t v[32];
                     tmem_ld_32x32(t_row + g * 32, v);
-                    if (SPLIT_W) {                             // A Wh^T + A Wl^T: the two column halves of the stacked product
+                    if (STACKED) {                             // A Wh^T + A Wl^T: the two column halves of the stacked product
                         uint32_t w[32];
                         tmem_ld_32x32(t_row + N_TILE + g * 32, w);
                         tmem_ld_wait();

@@ -85,6 +85,7 @@ struct LayerGeom {
     int split_w;      // 0: fp16 weights; 1: fp16 hi/lo pair (interleaved per 128-row tile), two fp16 MMAs;
                       // 2: same packed tensor, low part applied as E4M3 (kind::f8f6f4) - see conv_gemm.cuh
     int pair;         // 1: CTA pairs (cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile)
+    int stack;        // 1 (mode 1 only, FADTK_STACK=1): hi | lo rows as one N = 2 n_tile MMA operand (measurement variant)
 };
 
 // how the low part of split weights is applied: FADTK_WLO=fp16 (two fp16 MMAs) | fp8 (E4M3 correction MMA)
@@ -114,6 +115,10 @@ int make_geom(LayerGeom& g, int H, int W, int Cin, int Cout, int taps, int relu,
     g.taps = taps; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.relu = relu; g.pool = pool;
     g.split_w = split_w;                     // 0, 1 or 2 - the caller decides (wlo_mode() for the VGGish pipeline)
     g.pair = 0;                              // set by the caller after make_geom (split modes only)
+    {
+        static const int stk = [] { const char* e = getenv("FADTK_STACK"); return (e && e[0] == '1') ? 1 : 0; }();
+        g.stack = (g.split_w == 1 && stk) ? 1 : 0;
+    }
     if (Cin % 64 != 0) return fail("Cin must be a multiple of 64");
     if (taps != 1 && taps != 9) return fail("taps must be 1 or 9");
     if (H == 1 && W == 1) { g.box_w = 1; g.box_h = 1; g.box_n = 128; }
@@ -198,12 +203,12 @@ struct fad_handle {
 
 namespace {
 
-template <int N_TILE, int STAGES, int WMODE, int PAIR = 0>
+template <int N_TILE, int STAGES, int WMODE, int PAIR = 0, int STACK = 0>
 int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mw8,
                      const CUtensorMap& mx8, const fad::ConvGemmParams& p, cudaStream_t st) {
     static bool attr_set = false;
     constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES, WMODE, PAIR>();
-    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, WMODE, PAIR>;
+    auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, WMODE, PAIR, STACK>;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -250,7 +255,7 @@ int encode_layer_maps(const LayerGeom& g, const void* x, long long nb_dim, const
     // rows per weight box: mode 1 fetches hi + lo of a tile at once, mode 2 the hi rows only; a CTA of a pair fetches
     // its half of the hi rows and its half of the lo rows as two boxes
     // (mode 1 pair: one box of n_tile rows - rank 0 the hi rows, rank 1 the lo rows of the stacked N = 2 n_tile operand)
-    const uint32_t wb[2] = {64, (uint32_t)(g.pair ? (g.split_w == 1 ? g.n_tile : g.n_tile / 2) : g.n_tile * (g.split_w == 1 ? 2 : 1))};
+    const uint32_t wb[2] = {64, (uint32_t)(g.pair ? (g.stack ? g.n_tile : g.n_tile / 2) : g.n_tile * (g.split_w == 1 ? 2 : 1))};
     return encode_f16_map(mw, w, 2, wd, ws, wb);
 }
 
@@ -332,7 +337,9 @@ int run_layer(fad_handle* h, const LayerGeom& g, const CUtensorMap& mx, const CU
         if (g.pair) return launch_conv_gemm<128, 5, 2, 1>(h, mx, mw, mw8, *mx8, p, st);
         return launch_conv_gemm<128, 4, 2>(h, mx, mw, mw8, *mx8, p, st);
     }
+    if (g.split_w && g.pair && g.stack) return launch_conv_gemm<128, 6, 1, 1, 1>(h, mx, mw, mw, mx, p, st);
     if (g.split_w && g.pair) return launch_conv_gemm<128, 6, 1, 1>(h, mx, mw, mw, mx, p, st);
+    if (g.split_w && g.stack) return launch_conv_gemm<128, 4, 1, 0, 1>(h, mx, mw, mw, mx, p, st);
     if (g.split_w) return launch_conv_gemm<128, 4, 1>(h, mx, mw, mw, mx, p, st);
     if (g.n_tile == 256) return launch_conv_gemm<256, 4, 0>(h, mx, mw, mw, mx, p, st);
     return launch_conv_gemm<128, 6, 0>(h, mx, mw, mw, mx, p, st);

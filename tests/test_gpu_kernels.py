@@ -238,3 +238,35 @@ def test_encoder_attention_matches_torch(engine, n_clips, S, d, legacy):
     want = (p @ v).permute(0, 2, 1, 3).reshape(n_clips * S, d)
     err = (got - want).abs().max().item()
     assert err < 4e-3 * want.abs().max().item() + 1e-3, f"attention max abs err {err} (max {want.abs().max().item()})"
+
+
+@pytest.mark.parametrize("n_files,r,d", [(37, 10, 128), (5, 750, 128), (64, 2, 256), (9, 1, 64)])
+def test_mirrored_directory_statistics_match_reference_merge(engine, n_files, r, d, monkeypatch):
+    """fad_file_means + fad_stats_accumulate_f64 + fad_stats_finalize_mirrored == the reference's
+    calculate_embd_statistics_online on the same files (fadtk/utils.py:13-46: np.mean of an fp16 file is fp16, per-file
+    np.cov, Chan merge) - the oracle restatement is pinned to the real reference by tests/test_oracle_golden.py.
+    r = 1: the reference's covariance is all NaN (utils.py:16)."""
+    from oracle import fad_oracle as fo
+    monkeypatch.delenv("FADTK_SINGLE_FRAME_FILES", raising=False)
+    rng = np.random.default_rng(n_files * 100 + r)
+    files = [(rng.normal(0.0, 1.0, (r, d)) * rng.uniform(0.3, 2.0, d) + rng.normal(0, 3.0, d) + 0.2 * f).astype(np.float16)
+             for f in range(n_files)]
+    emb = torch.from_numpy(np.concatenate(files)).to(engine.torch_device)
+    shift = emb[: min(len(emb), 64)].float().mean(0).to(torch.float16)
+    n_acc = engine.stats_acc_len(d)
+    buf = torch.zeros(3 * n_acc, dtype=torch.float64, device=emb.device)
+    engine.stats_accumulate(emb, shift, buf[:n_acc])
+    m64, m16 = engine.file_means(emb, r)
+    want16 = np.stack([np.mean(f, axis=0) for f in files])                        # fp16, as _process_file computes it
+    assert np.array_equal(m16.cpu().numpy(), want16.astype(np.float64))
+    assert np.abs(m64.cpu().numpy() - np.stack([f.astype(np.float64).mean(0) for f in files])).max() < 1e-12
+    engine.stats_accumulate_f64(m64, buf[n_acc:2 * n_acc])
+    engine.stats_accumulate_f64(m16, buf[2 * n_acc:])
+    mu, cov = engine.stats_finalize_mirrored(buf[:n_acc], buf[n_acc:2 * n_acc], buf[2 * n_acc:], shift, r, d)
+    with np.errstate(all="ignore"):
+        mu_ref, cov_ref = fo.online_statistics(files)
+    assert np.abs(mu.cpu().numpy() - mu_ref).max() < 1e-11
+    if r == 1:
+        assert np.isnan(cov.cpu().numpy()).all() and np.isnan(cov_ref).all()
+    else:
+        assert np.abs(cov.cpu().numpy() - cov_ref).max() < 1e-9 * np.abs(cov_ref).max()
