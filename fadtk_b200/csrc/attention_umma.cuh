@@ -147,21 +147,33 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
             mbar_wait(s_full, j & 1);
             tc_fence_after_sync();
             float raw = -3.0e38f;
+            const bool full = valid == 128;                    // every block but the last: no per-key masking
 #pragma unroll 1
             for (int g = 0; g < 4; ++g) {
                 uint32_t v[32];
                 tmem_ld_32x32(tm_s + lane_base + g * 32, v);
                 tmem_ld_wait();
+                if (full) {
+                    float r0 = __uint_as_float(v[0]), r1 = __uint_as_float(v[1]), r2 = __uint_as_float(v[2]), r3 = __uint_as_float(v[3]);
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (g * 32 + c < valid) raw = fmaxf(raw, __uint_as_float(v[c]));
+                    for (int c = 4; c < 32; c += 4) {          // four independent chains
+                        r0 = fmaxf(r0, __uint_as_float(v[c]));     r1 = fmaxf(r1, __uint_as_float(v[c + 1]));
+                        r2 = fmaxf(r2, __uint_as_float(v[c + 2])); r3 = fmaxf(r3, __uint_as_float(v[c + 3]));
+                    }
+                    raw = fmaxf(raw, fmaxf(fmaxf(r0, r1), fmaxf(r2, r3)));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (g * 32 + c < valid) raw = fmaxf(raw, __uint_as_float(v[c]));
+                }
             }
             const float mx = fmaxf(m, raw * sc);               // sc > 0: the maximum commutes with the scaling
             const float alpha = exp2f(m - mx);
             m = mx;
             mbar_wait(p_empty, (j & 1) ^ 1);                   // PV_{j-1} has finished reading the P tile
             uint8_t* pb = p_s;
-            float rs = 0.f;
+            float rs0 = 0.f, rs1 = 0.f;
+            auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };   // one MUFU, x <= 0
 #pragma unroll 1
             for (int g = 0; g < 4; ++g) {
                 uint32_t v[32];
@@ -170,12 +182,14 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                 uint32_t h2[16];
 #pragma unroll
                 for (int c = 0; c < 32; c += 2) {
-                    const float e0 = (g * 32 + c < valid) ? exp2f(fmaf(__uint_as_float(v[c]), sc, -m)) : 0.f;
-                    const float e1 = (g * 32 + c + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[c + 1]), sc, -m)) : 0.f;
+                    float e0 = ex2(fmaf(__uint_as_float(v[c]), sc, -m)), e1 = ex2(fmaf(__uint_as_float(v[c + 1]), sc, -m));
+                    if (!full) {
+                        if (g * 32 + c >= valid) e0 = 0.f;
+                        if (g * 32 + c + 1 >= valid) e1 = 0.f;
+                    }
                     const __half2 hh = __floats2half2_rn(e0, e1);
                     h2[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-                    const float2 back = __half22float2(hh);     // the row sum uses the values the PV MMA will see
-                    rs += back.x + back.y;
+                    rs0 += e0; rs1 += e1;                      // fp32 row sum (as the mma.sync kernel did): 2^-11 per term, unbiased
                 }
                 // keys g*32 .. g*32+31 = 16-B chunks (g & 1) * 4 .. +3 of the 64-key block g >> 1
                 uint8_t* blk = pb + (g >> 1) * kAtTile + p_row;
@@ -185,7 +199,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                     *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
                 }
             }
-            l = l * alpha + rs;
+            l = l * alpha + (rs0 + rs1);
             tc_fence_before_sync();
             fence_proxy_async_smem();                          // P stores -> visible to the UMMA (async proxy)
             __syncwarp();

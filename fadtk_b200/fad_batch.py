@@ -29,9 +29,9 @@ from .model_loader import ModelLoader
 # clips per GPU launch sequence: bounded by audio seconds so ragged sets keep batches even
 _BATCH_AUDIO_SECONDS = 4096.0
 # files decoded ahead per round of host I/O, bounded both by count and by samples: the pinned staging buffer of a
-# chunk never exceeds 1 GB unless a single file does (2048 x 10 s x 16 kHz = 0.66 GB; 5-minute songs at 48 kHz: 37 per chunk)
+# chunk never exceeds 512 MB unless a single file does (1600 x 10 s x 16 kHz; 5-minute songs at 48 kHz: 18 per chunk)
 _CHUNK_FILES = 2048
-_CHUNK_SAMPLES = 512 * 1024 * 1024
+_CHUNK_SAMPLES = 256 * 1024 * 1024
 
 
 def _batches(files, lengths_s, limit_s):
@@ -66,13 +66,17 @@ def _names_in(directory) -> set:
 
 
 _staging = [None, None]
+# samples of one pinned staging slot, allocated ONCE at first use (cudaHostAlloc runs at a few GB/s: growing the buffer call
+# by call put two 0.1 s allocations inside every directory pass); a chunk never holds more than _CHUNK_SAMPLES samples
+# unless a single file does.  $FADTK_STAGING_MB bounds the two slots (default 2 x 512 MB of pinned host memory).
+_STAGING_SAMPLES = min(_CHUNK_SAMPLES, max(1, int(os.environ.get("FADTK_STAGING_MB", "512"))) * 512 * 1024)
 
 
 def _host_buffer(n_samples: int, slot: int) -> np.ndarray:
     """int16 staging buffer of one of the two chunk slots (chunk k+1 is read while chunk k is embedded; a slot is
     reused only after its chunk has been consumed); pinned when a GPU is present so the H2D copy is a straight DMA."""
     if _staging[slot] is None or _staging[slot].numel() < n_samples:
-        _staging[slot] = torch.empty(max(1, n_samples), dtype=torch.int16, pin_memory=torch.cuda.is_available())
+        _staging[slot] = torch.empty(max(1, n_samples, _STAGING_SAMPLES), dtype=torch.int16, pin_memory=torch.cuda.is_available())
     return _staging[slot].numpy()[:max(1, n_samples)]
 
 
@@ -130,7 +134,9 @@ def _read_native(part, ml: ModelLoader, workers: int, slot: int):
             if copy:
                 stw = _io_native.wav_write([conv[idx[j]] for j in copy], buf, off[copy], fr[idx[copy]], ml.sr, workers)
                 for j in np.nonzero(stw != _io_native.OK)[0]:
-                    raise OSError(f"cannot write {conv[idx[copy[j]]]} (status {int(stw[j])})")
+                    # the convert cache is only a memo of the decode step: a file that cannot be written costs a re-read
+                    # next time, it must not abort the rest of the directory
+                    log.error(f"cannot write {conv[idx[copy[j]]]} (status {int(stw[j])}); continuing without the convert cache entry")
     return clips
 
 
@@ -156,7 +162,10 @@ def _save_embeddings(ml: ModelLoader, group, flat: np.ndarray, rows, workers: in
     if flat.dtype == np.float16 and flat.ndim == 2:
         st = _io_native.npy_write_f16(paths, np.ascontiguousarray(flat), off[:-1], rows, workers)
         for i in np.nonzero(st != _io_native.OK)[0]:
-            raise OSError(f"cannot write {paths[i]} (status {int(st[i])})")
+            # the reference writes file by file and a failing np.save stops only that worker's loop (fad_batch.py:20-22);
+            # here one bad path must not lose the embeddings of the other files of the batch: report it and go on - the
+            # file stays without a cache entry and is picked up again by the next run
+            log.error(f"cannot write {paths[i]} (status {int(st[i])}); the other files of the batch were written")
     else:                                                      # a plugin returning another dtype / rank: numpy decides the format
         for i, p in enumerate(paths):
             np.save(p, flat[off[i]:off[i + 1]])
