@@ -9,22 +9,25 @@
 //   warp 1      MMA issuer: S_j = Q K_j^T  (M 128, N 128, K 64; both operands K-major) into the TMEM score buffer,
 //               and - one block behind - O_j = P_j V_j (M 128, N 64, K 128; P K-major from shared memory, V as an
 //               MN-major B operand: the TMA tile [keys][dims] IS that layout) into one of two TMEM output buffers.
-//   warps 2-5   softmax, one thread per query row: two passes over the score row straight out of TMEM (row maximum,
-//               then exp2 / row sum), P written as fp16 into the 128-B-swizzled K-major tile the PV MMA reads; the
-//               partial output of the previous block is folded into fp32 registers with the usual rescaling
+//   warps 2-9   softmax, TWO threads per query row (64 keys and 32 output dims each): two passes over the score row
+//               straight out of TMEM (row maximum - exchanged between the two threads through shared memory -, then
+//               exp2 / row sum), P written as fp16 into the 128-B-swizzled K-major tile the PV MMA reads; the partial
+//               output of the previous block is folded into fp32 registers with the usual rescaling
 //               O <- (O + O_{j-1}) * 2^(m_{j-1} - m_j), so the accumulator never has to be rescaled inside TMEM.
 //
 // Two CTAs per SM (7 tiles of 16 KiB of shared memory and 256 TMEM columns each): while one CTA's softmax warps work on
 // S_j the other CTA's MMAs and loads run - the softmax side (exp2: 16 MUFU results per clock and SM, i.e. 1024 clocks per
 // 128 x 128 block against 512 of MMA, plus the TMEM round trips) is the bound, so it is what must stay busy.
 #pragma once
+#include <cuda_bf16.h>
 #include "sm100.cuh"
 
 namespace fad {
 
-constexpr int kAtThreads = 192;
+constexpr int kAtThreads = 320;                                // TMA warp, MMA warp, 8 softmax warps
 constexpr uint32_t kAtTile = 128 * 128;                       // bytes of one 128-row x 64-col fp16 tile: 16 KiB
-constexpr uint32_t kAtSmem = kAtTile /*Q*/ + 2 * 2 * kAtTile /*K,V x 2 stages*/ + 2 * kAtTile /*P*/ + 256;   // x 2 CTAs + 2 KiB <= 228 KiB
+constexpr uint32_t kAtSmem = kAtTile /*Q*/ + 2 * 2 * kAtTile /*K,V x 2 stages*/ + 2 * kAtTile /*P*/ + 256 /*barriers*/
+                           + 2 * 128 * 2 /*row-maximum exchange, bf16*/;     // 115 456 B: x 2 CTAs + 2 x 1 KiB reserved <= 228 KiB
 
 struct AttnParams {
     int S, d, heads;
@@ -54,6 +57,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
     uint64_t* o_full = bars + 9;        // 2
     uint64_t* o_empty = bars + 11;      // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    __nv_bfloat16* mx_s = reinterpret_cast<__nv_bfloat16*>(smem + 7 * kAtTile + 256);      // [half][row]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, h = blockIdx.y, clip = blockIdx.z;
@@ -62,11 +66,11 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
     if (warp == 0 && lane == 0) tma_prefetch_desc(&map_qkv);
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        mbar_init(s_full, 1);  mbar_init(s_empty, 4);
-        mbar_init(p_full, 4);  mbar_init(p_empty, 1);
+        mbar_init(s_full, 1);  mbar_init(s_empty, 8);
+        mbar_init(p_full, 8);  mbar_init(p_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-            mbar_init(&o_full[i], 1);  mbar_init(&o_empty[i], 4);
+            mbar_init(&o_full[i], 1);  mbar_init(&o_empty[i], 8);
         }
         mbar_fence_init();
     }
@@ -133,25 +137,34 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
         }
     } else {
         // ------------------------------------------------------------------ softmax + output accumulation
+        // TWO threads per query row (warps w and w + 4 share a TMEM lane quarter): thread `half` owns keys
+        // [64 half, 64 half + 64) of every block - i.e. one of the two 64-key blocks of the P tile - and output dims
+        // [32 half, 32 half + 32).  The row maximum is exchanged through shared memory once per block (one named barrier
+        // over the 256 softmax threads, slots double-buffered by block parity); the row sums stay per thread and are added
+        // at the very end (both threads apply the same rescaling factors).
         const int quarter = warp & 3;                          // TMEM lanes this warp may read
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;                   // query row of the tile
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
         const float sc = 0.125f * 1.4426950408889634f;         // head_dim^-0.5 and log2(e): softmax in the exp2 domain
-        float o[64];
+        float o[32];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) o[c] = 0.f;
+        for (int c = 0; c < 32; ++c) o[c] = 0.f;
         float m = -3.0e38f, l = 0.f;
-        const uint32_t p_row = row * 128, sw = row & 7;
+        const uint32_t sw = row & 7;
+        uint8_t* p_blk = p_s + half * kAtTile + row * 128;      // this thread's row of its 64-key block of P
+        const uint32_t s_cols = tm_s + lane_base + half * 64;
+        auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };   // one MUFU, x <= 0
         for (int j = 0; j < n_blocks; ++j) {
-            const int valid = min(128, p.S - j * 128);         // keys of this block that exist
+            const int valid = min(128, p.S - j * 128) - half * 64;   // keys of this thread's 64 that exist (may be <= 0)
+            const bool full = valid >= 64;                      // every block but the last: no per-key masking
             mbar_wait(s_full, j & 1);
             tc_fence_after_sync();
             float raw = -3.0e38f;
-            const bool full = valid == 128;                    // every block but the last: no per-key masking
-#pragma unroll 1
-            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
                 uint32_t v[32];
-                tmem_ld_32x32(tm_s + lane_base + g * 32, v);
+                tmem_ld_32x32(s_cols + g * 32, v);
                 tmem_ld_wait();
                 if (full) {
                     float r0 = __uint_as_float(v[0]), r1 = __uint_as_float(v[1]), r2 = __uint_as_float(v[2]), r3 = __uint_as_float(v[3]);
@@ -167,17 +180,22 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                         if (g * 32 + c < valid) raw = fmaxf(raw, __uint_as_float(v[c]));
                 }
             }
+            // Both threads of a row must use the SAME maximum; any value >= the true one works (softmax is invariant to
+            // it).  Exchanged as bf16 rounded UP (no room for fp32 slots next to two CTAs' tiles).  One slot per thread is
+            // enough: S_{j+1} is only issued after all 8 warps released S_j, i.e. after every partner read this block's slot.
+            const __nv_bfloat16 mine = __float2bfloat16_ru(raw);
+            mx_s[half * 128 + row] = mine;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            raw = fmaxf(__bfloat162float(mine), __bfloat162float(mx_s[(half ^ 1) * 128 + row]));
             const float mx = fmaxf(m, raw * sc);               // sc > 0: the maximum commutes with the scaling
-            const float alpha = exp2f(m - mx);
+            const float alpha = ex2(m - mx);
             m = mx;
             mbar_wait(p_empty, (j & 1) ^ 1);                   // PV_{j-1} has finished reading the P tile
-            uint8_t* pb = p_s;
             float rs0 = 0.f, rs1 = 0.f;
-            auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };   // one MUFU, x <= 0
-#pragma unroll 1
-            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
                 uint32_t v[32];
-                tmem_ld_32x32(tm_s + lane_base + g * 32, v);
+                tmem_ld_32x32(s_cols + g * 32, v);
                 tmem_ld_wait();
                 uint32_t h2[16];
 #pragma unroll
@@ -191,12 +209,11 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                     h2[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
                     rs0 += e0; rs1 += e1;                      // fp32 row sum (as the mma.sync kernel did): 2^-11 per term, unbiased
                 }
-                // keys g*32 .. g*32+31 = 16-B chunks (g & 1) * 4 .. +3 of the 64-key block g >> 1
-                uint8_t* blk = pb + (g >> 1) * kAtTile + p_row;
+                // keys g*32 .. g*32+31 of this thread's block = its 16-B chunks g * 4 .. +3 (XOR-swizzled by the row)
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                    const uint32_t chunk = uint32_t((g & 1) * 4 + q4) ^ sw;
-                    *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+                    const uint32_t chunk = uint32_t(g * 4 + q4) ^ sw;
+                    *reinterpret_cast<uint4*>(p_blk + (chunk << 4)) = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
                 }
             }
             l = l * alpha + (rs0 + rs1);
@@ -208,14 +225,11 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                 const int bp = (j - 1) & 1;
                 mbar_wait(&o_full[bp], ((j - 1) >> 1) & 1);
                 tc_fence_after_sync();
+                uint32_t v[32];
+                tmem_ld_32x32(tm_o[bp] + lane_base + half * 32, v);
+                tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tm_o[bp] + lane_base + g * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) o[g * 32 + c] = (o[g * 32 + c] + __uint_as_float(v[c])) * alpha;
-                }
+                for (int c = 0; c < 32; ++c) o[c] = (o[c] + __uint_as_float(v[c])) * alpha;
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[bp]);
@@ -223,28 +237,29 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
         }
         {
             const int bp = (n_blocks - 1) & 1;
-            mbar_wait(&o_full[bp], ((n_blocks - 1) >> 1) & 1);
+            mbar_wait(&o_full[bp], ((n_blocks - 1) >> 1) & 1);  // the last P V has completed: the P tile is free
             tc_fence_after_sync();
+            // total row sum = the two threads' partial sums, exchanged in fp32 through this row's (now idle) P rows
+            *reinterpret_cast<float*>(p_blk) = l;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            l += *reinterpret_cast<const float*>(p_s + (half ^ 1) * kAtTile + row * 128);
             const float inv = 1.0f / l;
             const int q = qb * 128 + row;
-            __half* dst = p.out + ((size_t)clip * p.S + q) * p.d + h * 64;
+            __half* dst = p.out + ((size_t)clip * p.S + q) * p.d + h * 64 + half * 32;
+            uint32_t v[32];
+            tmem_ld_32x32(tm_o[bp] + lane_base + half * 32, v);
+            tmem_ld_wait();
+            if (q < p.S) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                uint32_t v[32];
-                tmem_ld_32x32(tm_o[bp] + lane_base + g * 32, v);
-                tmem_ld_wait();
-                if (q < p.S) {
+                for (int c = 0; c < 32; c += 8) {
+                    uint32_t w[4];
 #pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __half2 hh = __floats2half2_rn((o[g * 32 + c + 2 * e] + __uint_as_float(v[c + 2 * e])) * inv,
-                                                                 (o[g * 32 + c + 2 * e + 1] + __uint_as_float(v[c + 2 * e + 1])) * inv);
-                            w[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                        }
-                        *reinterpret_cast<uint4*>(dst + g * 32 + c) = make_uint4(w[0], w[1], w[2], w[3]);
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 hh = __floats2half2_rn((o[c + 2 * e] + __uint_as_float(v[c + 2 * e])) * inv,
+                                                             (o[c + 2 * e + 1] + __uint_as_float(v[c + 2 * e + 1])) * inv);
+                        w[e] = *reinterpret_cast<const uint32_t*>(&hh);
                     }
+                    *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
         }
