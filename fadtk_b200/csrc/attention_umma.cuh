@@ -27,7 +27,7 @@ namespace fad {
 constexpr int kAtThreads = 320;                                // TMA warp, MMA warp, 8 softmax warps
 constexpr uint32_t kAtTile = 128 * 128;                       // bytes of one 128-row x 64-col fp16 tile: 16 KiB
 constexpr uint32_t kAtSmem = kAtTile /*Q*/ + 2 * 2 * kAtTile /*K,V x 2 stages*/ + 2 * kAtTile /*P*/ + 256 /*barriers*/
-                           + 2 * 128 * 2 /*row-maximum exchange, bf16*/;     // 115 456 B: x 2 CTAs + 2 x 1 KiB reserved <= 228 KiB
+                           + 128 * 4 /*row-maximum exchange*/;               // 115 456 B: x 2 CTAs + 2 x 1 KiB reserved <= 228 KiB
 
 struct AttnParams {
     int S, d, heads;
@@ -57,7 +57,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
     uint64_t* o_full = bars + 9;        // 2
     uint64_t* o_empty = bars + 11;      // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    __nv_bfloat16* mx_s = reinterpret_cast<__nv_bfloat16*>(smem + 7 * kAtTile + 256);      // [half][row]
+    float* mx_s = reinterpret_cast<float*>(smem + 7 * kAtTile + 256);      // [row]: one slot per query row
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = blockIdx.x, h = blockIdx.y, clip = blockIdx.z;
@@ -180,13 +180,14 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                         if (g * 32 + c < valid) raw = fmaxf(raw, __uint_as_float(v[c]));
                 }
             }
-            // Both threads of a row must use the SAME maximum; any value >= the true one works (softmax is invariant to
-            // it).  Exchanged as bf16 rounded UP (no room for fp32 slots next to two CTAs' tiles).  One slot per thread is
-            // enough: S_{j+1} is only issued after all 8 warps released S_j, i.e. after every partner read this block's slot.
-            const __nv_bfloat16 mine = __float2bfloat16_ru(raw);
-            mx_s[half * 128 + row] = mine;
+            // Both threads of a row need the row maximum.  One fp32 slot per row (there is no room for more next to two
+            // CTAs' tiles), two steps: the thread of the first 64 keys posts its maximum, the other folds its own in and
+            // posts the result back.
+            if (half == 0) mx_s[row] = raw;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            raw = fmaxf(__bfloat162float(mine), __bfloat162float(mx_s[(half ^ 1) * 128 + row]));
+            if (half == 1) { raw = fmaxf(raw, mx_s[row]); mx_s[row] = raw; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0) raw = mx_s[row];
             const float mx = fmaxf(m, raw * sc);               // sc > 0: the maximum commutes with the scaling
             const float alpha = ex2(m - mx);
             m = mx;
@@ -207,7 +208,8 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                     }
                     const __half2 hh = __floats2half2_rn(e0, e1);
                     h2[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-                    rs0 += e0; rs1 += e1;                      // fp32 row sum (as the mma.sync kernel did): 2^-11 per term, unbiased
+                    const float2 back = __half22float2(hh);     // the row sum is taken over the fp16 values the P V MMA reads:
+                    rs0 += back.x; rs1 += back.y;              // the weights of a row then sum to exactly 1
                 }
                 // keys g*32 .. g*32+31 of this thread's block = its 16-B chunks g * 4 .. +3 (XOR-swizzled by the row)
 #pragma unroll
