@@ -498,8 +498,11 @@ def main():
         per_layer_factor = 1.5 if wlo_fp8 else 2.0            # an fp8 low-part MMA takes half the tensor-pipe time of an fp16 one
         issued_factor = sum(UMMA_LAYER_FLOP[k] * (per_layer_factor if (split_mask >> i) & 1 else 1.0)
                             for i, k in enumerate(UMMA_LAYER_FLOP)) / sum(UMMA_LAYER_FLOP.values())
-        kernel = (f"fad::conv_gemm_kernel<128,4,{2 if wlo_fp8 else 1}> (tcgen05 kind::f16, fp16 hi/lo split weights on "
-                  f"{bin(split_mask).count('1')}/8 layers: " + ("low parts as kind::f8f6f4 E4M3 MMAs)" if wlo_fp8 else "2 fp16 MMAs per K step)"))
+        pair_env = os.environ.get("FADTK_PAIR", "auto")
+        pairs = {"auto": "CTA pairs (cta_group::2, M = 256) on conv3_2, conv4_1, conv4_2, fc1, fc2", "1": "CTA pairs (cta_group::2) on every layer",
+                 "0": "single-CTA MMAs"}.get(pair_env, f"CTA pairs mask {pair_env}")
+        kernel = (f"fad::conv_gemm_kernel<128, STAGES, {2 if wlo_fp8 else 1}, PAIR> (tcgen05 kind::f16, {pairs}; fp16 hi/lo split weights on "
+                  f"{bin(split_mask).count('1')}/8 layers: " + ("low parts as kind::f8f6f4 E4M3 MMAs)" if wlo_fp8 else "2 fp16 MMAs per K slice into one TMEM accumulator)"))
     else:
         # the GEMM category does not cover every GEMM of these forwards (front-end convolutions are timed with the
         # front end): rate over the WHOLE forward - a lower bound of the kernel's own rate that cannot exceed the peak

@@ -74,6 +74,15 @@ constexpr int kBlockK = 64;                        // fp16 elements per 128-B sw
 constexpr int kConvGemmThreads = 384;
 constexpr int kEpilogueWarps = 8;
 constexpr int kChunkSteps = 8;                     // k-steps (of 64) per TMEM accumulation chunk
+// The tensor core truncates when it adds into its fp32 accumulator: a sum over T accumulated elements (T = K of the
+// chunk, x 2 when the hi and lo weight MMAs share the accumulator) comes out scaled by (1 - 1.0e-9 T) - measured on
+// B200 for random and post-ReLU operands, shapes K = 384 ... 12288 (tests/diag_accum_bias.py; profiles/
+// r2_gemm_bias_probe_before.json: -8.1e-7 at T = 768, -1.08e-6 at T = 1024, -4.1e-7 at T = 384).  Cutting K into chunks
+// bounds it, but what is left is SYSTEMATIC: through the ~50 GEMMs of a transformer encoder it adds up to a per-
+// dimension offset of the hidden states (wav2vec: 8e-5 of their rms at layer 12, 10x what independent errors would
+// give, and a -2e-4 offset of the FAD, profiles/r2_w2v_layer_bias_before.json).  The epilogue therefore scales every
+// chunk by the inverse of its expected shrink when it sums the chunks in registers (one FMA per element, free).
+constexpr float kAccumShrinkPerElement = 1.0e-9f;
 constexpr uint32_t kABytes = kTileM * kBlockK * 2; // 16 KiB per stage
 constexpr uint32_t kStagingBytes = 32 * 128;       // per epilogue warp: 32 rows x 128 B output staging
 
@@ -380,9 +389,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             const int m_next = PAIR ? 2 * mu_next + (int)rank : mu_next;
             if (tile + n_workers < total_tiles) prefetch_resid(nt_next, m_next);
 
-            // sum the K chunks in registers (round-to-nearest adds)
+            // sum the K chunks in registers (round-to-nearest adds), undoing the expected truncation shrink of each
             float acc[kColsPerWarp];
             for (int c = 0; c < n_chunks; ++c) {
+                const int len_c = min(chunk_len, ksteps - c * chunk_len);
+                const float unshrink = 1.0f + kAccumShrinkPerElement * (float)(len_c * kBlockK * (SPLIT_W ? 2 : 1));
                 mbar_wait(&tmem_full[buf], buf_ph);
                 tc_fence_after_sync();
                 const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + buf * kBufCols + half * kColsPerWarp;
@@ -401,10 +412,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     }
                     if (c == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = __uint_as_float(v[j]) * unshrink;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = fmaf(__uint_as_float(v[j]), unshrink, acc[g * 32 + j]);
                     }
                     if (LO8 && c == n_chunks - 1) {           // + A8 * Wl8^T / 2^s: complete once the last chunk is
                         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + 2 * N_TILE + cpar * N_TILE + half * kColsPerWarp + g * 32, v);
