@@ -81,8 +81,9 @@ constexpr int kChunkSteps = 8;                     // k-steps (of 64) per TMEM a
 // bounds it, but what is left is SYSTEMATIC: through the ~50 GEMMs of a transformer encoder it adds up to a per-
 // dimension offset of the hidden states (wav2vec: 8e-5 of their rms at layer 12, 10x what independent errors would
 // give, and a -2e-4 offset of the FAD, profiles/r2_w2v_layer_bias_before.json).  The epilogue therefore scales every
-// chunk by the inverse of its expected shrink when it sums the chunks in registers (one FMA per element, free).
-constexpr float kAccumShrinkPerElement = 1.0e-9f;
+// chunk by the inverse of its expected shrink when it sums the chunks in registers: v + v * eps as one FMA (1 + eps
+// itself is not representable finely enough in fp32: eps ~ 1e-6 is only 8 ulps of 1).
+constexpr float kAccumShrinkPerElement = 1.06e-9f;
 constexpr uint32_t kABytes = kTileM * kBlockK * 2; // 16 KiB per stage
 constexpr uint32_t kStagingBytes = 32 * 128;       // per epilogue warp: 32 rows x 128 B output staging
 
@@ -393,7 +394,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             float acc[kColsPerWarp];
             for (int c = 0; c < n_chunks; ++c) {
                 const int len_c = min(chunk_len, ksteps - c * chunk_len);
-                const float unshrink = 1.0f + kAccumShrinkPerElement * (float)(len_c * kBlockK * (SPLIT_W ? 2 : 1));
+                const float unshrink = kAccumShrinkPerElement * (float)(len_c * kBlockK * (SPLIT_W ? 2 : 1));
                 mbar_wait(&tmem_full[buf], buf_ph);
                 tc_fence_after_sync();
                 const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + buf * kBufCols + half * kColsPerWarp;
@@ -412,10 +413,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     }
                     if (c == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = __uint_as_float(v[j]) * unshrink;
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = fmaf(__uint_as_float(v[j]), unshrink, __uint_as_float(v[j]));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] = fmaf(__uint_as_float(v[j]), unshrink, acc[g * 32 + j]);
+                        for (int j = 0; j < 32; ++j) acc[g * 32 + j] += fmaf(__uint_as_float(v[j]), unshrink, __uint_as_float(v[j]));
                     }
                     if (LO8 && c == n_chunks - 1) {           // + A8 * Wl8^T / 2^s: complete once the last chunk is
                         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + 2 * N_TILE + cpar * N_TILE + half * kColsPerWarp + g * 32, v);

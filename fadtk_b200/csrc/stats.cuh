@@ -1,37 +1,38 @@
-// Sufficient statistics of an embedding matrix E[N, d] (fp16):   n,  sum(x - s),  sum(y y^T)
-// with s a shared fp16 shift vector and y = x - s carried as an fp16 hi/lo pair (22 bits).
-// Replaces np.mean / np.cov in fadtk/fad.py:42-48 and the per-file scatter + Chan merge in
-// fadtk/utils.py:13-46 with one shifted E^T E contraction on the tensor cores.
+// Sufficient statistics of an embedding matrix E[N, d] (fp16):   n,  sum(x - s),  sum(y y^T)   with y = x - s and
+// s a shared fp16 shift vector.  Replaces np.mean / np.cov in fadtk/fad.py:42-48 and the per-file scatter + Chan
+// merge in fadtk/utils.py:13-46 with one shifted E^T E contraction.
 //
-// Numerics.  x and s are fp16, so x - s is exact in fp32.  Rounding it to ONE fp16 costs
-// 2^-12 |y| per element, i.e. ~2^-11/sqrt(n) relative on a covariance entry (1.5e-4 at n = 1000):
-// not good enough.  Instead yh = fp16(x - s), yl = fp16((x - s) - yh) and
-//     sum y y^T  ~=  sum yh yh^T + yh yl^T + yl yh^T          (yl yl^T ~ 2^-22 is dropped)
-// Every fp16 x fp16 product is exact in the fp32 accumulator; the accumulation itself is cut
-// every 256 rows and drained into an fp64 tile, because tensor-core fp32 adds truncate.
+// Three kernels compute the same packed accumulator (fad_stats_accumulate's `mode`):
 //
-// stats_umma_kernel   One CTA = one job = (128x128 output tile (ti <= tj), row range).
-//   E is row-major, so both operands of E^T E are "MN-major": a TMA box [32 rows x 64 cols] with
-//   128-B swizzle IS the canonical MN-major SWIZZLE_128B UMMA layout (K = row index).
+// stats_dmma_kernel<In>  (mode 0, the product default)   fp64 tensor pipe.  x and s are fp16, so y = x - s is exact
+//   in fp64; products and sums are fp64 (mma.sync m8n8k4.f64 -> SASS DMMA.8x8x4): the result is the Gram matrix of
+//   the data to ~1e-16, hence positive semi-definite.  Parity needs that: a covariance with cond ~1e9 (CLAP/MERT) or
+//   a rank-deficient per-song covariance perturbed at the 1e-6 level of an fp32-accumulating path is indefinite -
+//   Newton-Schulz diverges on it and tr sqrt(C1 C2) moves by percents.  One CTA = (64x64 output tile ti <= tj, row
+//   range); Y tiles are staged in shared memory as doubles with pitch 68 (== 4 mod 16: conflict-free fragment loads)
+//   and double-buffered; each job's tile goes to a workspace and stats_dmma_reduce_kernel sums the jobs in a fixed
+//   order (deterministic).  In = double with no shift is the variant score() feeds with per-file fp16-rounded means
+//   (fad_stats_accumulate_f64).  ncu: profiles/r2_ncu_fp64_dmma.md.
+//
+// stats_umma_kernel  (mode 1, opt-in)   tcgen05 fp16 hi/lo: yh = fp16(y), yl = fp16(y - yh),
+//       sum y y^T ~= sum yh yh^T + yh yl^T + yl yh^T            (yl yl^T ~ 2^-22 is dropped)
+//   Every fp16 x fp16 product is exact in the fp32 accumulator; the accumulation itself is cut every 256 rows and
+//   drained into an fp64 tile, because tensor-core fp32 adds truncate.  One CTA = (128x128 output tile, row range).
+//   E is row-major, so both operands of E^T E are "MN-major": a TMA box [32 rows x 64 cols] with 128-B swizzle IS
+//   the canonical MN-major SWIZZLE_128B UMMA layout (K = row index).
 //     warp 0       TMA producer: per 32-row stage, two 64-column boxes per panel
-//     warps 4-11   transform: in smem, x -> (yh in place, yl into a second panel), zero rows past
-//                  the end, exact column sums of x - s and of yh + yl in fp64 registers
+//     warps 4-11   transform: in smem, x -> (yh in place, yl into a second panel), zero rows past the end, exact
+//                  column sums of x - s and of yh + yl in fp64 registers
 //     warp 1       MMA issuer: per stage 2 k-steps x {hh, hl, lh} tcgen05.mma, fp32 in TMEM
 //     warps 12-15  drain: every 256 rows the TMEM tile is added into an fp64 tile in shared memory
-//   Each job stores its fp64 tile to a workspace; stats_reduce_kernel sums jobs in a fixed
-//   order (deterministic) into the caller's packed accumulator.
-// stats_simt_kernel    fp64 CUDA-core contraction of the EXACT y = x - s (fp32 value, fp64 products
-//   and sums): the result is the Gram matrix of the data to ~1e-16, hence positive semi-definite.
-//   This is the product default.  Parity needs it: a covariance with cond ~1e9 (CLAP/MERT) or a
-//   rank-deficient per-song covariance perturbed at the 1e-6 level of the fp32-accumulating
-//   tensor-core path is indefinite - Newton-Schulz diverges on it and tr sqrt(C1 C2) moves by
-//   percents (eigenvalues below the perturbation are destroyed).  The tensor-core kernel stays
-//   available (tensor_core = 1) for full-rank, well-conditioned sets; cost is irrelevant either
-//   way (3.3 GFLOP for 100 000 x 128, vs 173 TFLOP for the embeddings that produced them).
+//   Good to ~1e-6 relative: fine for full-rank, well-conditioned sets only.
+//
+// stats_simt_kernel  (mode 2)   fp64 CUDA-core contraction of the exact y: the round-1 default, kept as the
+//   independent cross-check of mode 0 (tests/test_gpu_kernels.py compares all three).
 //
 // Packed accumulator (fp64, caller-owned, all-reduced across GPUs as-is):
 //   acc[0] = n,  acc[1 .. d] = sum(x - s) (exact),  acc[1+d .. 1+d+d*d) = sum(y y^T)
-//   (d x d, full, row-major),  acc[1+d+d*d ..] = sum(yh + yl)  (centring term of the covariance)
+//   (d x d, full, row-major),  acc[1+d+d*d ..] = sum(yh + yl)  (centring term of the covariance; = sum y in modes 0, 2)
 #pragma once
 #include "sm100.cuh"
 
