@@ -13,7 +13,8 @@ from pathlib import Path
 import numpy as np
 import torch
 
-_LIB_PATH = Path(__file__).parent / "csrc" / "libfadtk_b200.so"
+# FADTK_B200_LIB: another build of the same library (A/B measurements of a compile-time variant on one box)
+_LIB_PATH = Path(os.environ.get("FADTK_B200_LIB") or Path(__file__).parent / "csrc" / "libfadtk_b200.so")
 _lib = None
 
 c_ll = C.c_longlong

@@ -20,9 +20,16 @@
 // 128 x 128 block against 512 of MMA, plus the TMEM round trips) is the bound, so it is what must stay busy.
 #pragma once
 #include <cuda_bf16.h>
+#include <type_traits>
 #include "sm100.cuh"
 
 namespace fad {
+
+// s0 += lo half, s1 += hi half of a packed fp16 pair, in fp32 (add.rn.f32.f16 -> SASS FHADD: one instruction per value)
+__device__ __forceinline__ void add_f16x2(float& s0, float& s1, uint32_t h2) {
+    asm("{.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;}"
+        : "+f"(s0), "+f"(s1) : "r"(h2));
+}
 
 constexpr int kAtThreads = 320;                                // TMA warp, MMA warp, 8 softmax warps
 constexpr uint32_t kAtTile = 128 * 128;                       // bytes of one 128-row x 64-col fp16 tile: 16 KiB
@@ -192,33 +199,39 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
             const float alpha = ex2(m - mx);
             m = mx;
             mbar_wait(p_empty, (j & 1) ^ 1);                   // PV_{j-1} has finished reading the P tile
-            float rs0 = 0.f, rs1 = 0.f;
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+            // FULL blocks (all but the last) carry no per-key masking: a separate instantiation, not a predicate per key
+            auto exp_and_store = [&](auto full_c) {
+                constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                uint32_t v[32];
-                tmem_ld_32x32(s_cols + g * 32, v);
-                tmem_ld_wait();
-                uint32_t h2[16];
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(s_cols + g * 32, v);
+                    tmem_ld_wait();
+                    uint32_t h2[16];
 #pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    float e0 = ex2(fmaf(__uint_as_float(v[c]), sc, -m)), e1 = ex2(fmaf(__uint_as_float(v[c + 1]), sc, -m));
-                    if (!full) {
-                        if (g * 32 + c >= valid) e0 = 0.f;
-                        if (g * 32 + c + 1 >= valid) e1 = 0.f;
+                    for (int c = 0; c < 32; c += 2) {
+                        float e0 = ex2(fmaf(__uint_as_float(v[c]), sc, -m)), e1 = ex2(fmaf(__uint_as_float(v[c + 1]), sc, -m));
+                        if (!FULL) {
+                            if (g * 32 + c >= valid) e0 = 0.f;
+                            if (g * 32 + c + 1 >= valid) e1 = 0.f;
+                        }
+                        const __half2 hh = __floats2half2_rn(e0, e1);
+                        h2[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                        // the row sum is taken over the fp16 values the P V MMA reads (the weights of a row then sum to
+                        // exactly 1): fp32 += fp16 is one instruction (FHADD) per value
+                        if (c & 2) add_f16x2(rs2, rs3, h2[c >> 1]); else add_f16x2(rs0, rs1, h2[c >> 1]);
                     }
-                    const __half2 hh = __floats2half2_rn(e0, e1);
-                    h2[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-                    const float2 back = __half22float2(hh);     // the row sum is taken over the fp16 values the P V MMA reads:
-                    rs0 += back.x; rs1 += back.y;              // the weights of a row then sum to exactly 1
-                }
-                // keys g*32 .. g*32+31 of this thread's block = its 16-B chunks g * 4 .. +3 (XOR-swizzled by the row)
+                    // keys g*32 .. g*32+31 of this thread's block = its 16-B chunks g * 4 .. +3 (XOR-swizzled by the row)
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const uint32_t chunk = uint32_t(g * 4 + q4) ^ sw;
-                    *reinterpret_cast<uint4*>(p_blk + (chunk << 4)) = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const uint32_t chunk = uint32_t(g * 4 + q4) ^ sw;
+                        *reinterpret_cast<uint4*>(p_blk + (chunk << 4)) = make_uint4(h2[4 * q4], h2[4 * q4 + 1], h2[4 * q4 + 2], h2[4 * q4 + 3]);
+                    }
                 }
-            }
-            l = l * alpha + (rs0 + rs1);
+            };
+            if (full) exp_and_store(std::true_type{}); else exp_and_store(std::false_type{});
+            l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
             tc_fence_before_sync();
             fence_proxy_async_smem();                          // P stores -> visible to the UMMA (async proxy)
             __syncwarp();

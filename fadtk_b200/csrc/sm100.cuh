@@ -62,6 +62,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Watchdog: no wait in this library is legitimately longer than a few milliseconds; a protocol
 // bug traps (-> cudaErrorLaunchFailure on the host) instead of hanging the GPU.  Kept free of
 // function calls (no printf) so ptxas can give each warp role its own setmaxnreg budget.
+// The retry loop is four instructions (try_wait with a suspend-time hint, counter, compare, branch): waiting warps
+// share their scheduler with working ones, and round 1's loop (clock64 read + 64-bit compare per retry) was 22 % of
+// all instructions the attention kernel issued (ncu source page, profiles/r2_attention_umma.md).
+#ifndef FADTK_WAIT_CLOCK_WATCHDOG
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 2000u)) {          // may suspend up to 2 us per try; resumes on completion
+        if (++spins > (1u << 24)) asm volatile("trap;");       // >= 0.3 s of retries
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -69,6 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000LL) asm volatile("trap;");
     }
 }
+#endif
 
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
