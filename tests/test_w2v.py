@@ -108,13 +108,16 @@ def test_wavlm_matches_transformers(engine, size, layer):
 @pytest.mark.gpu
 def test_w2v_fad_parity_on_identical_audio(engine):
     """FAD against the reference CPU path (transformers fp32) on identical audio, 64 + 64 four-second clips (25 472 rows).
-    Measured: -2.0e-4 relative (tcgen05 attention) / -2.3e-4 (mma.sync attention) - a systematic offset of the wav2vec
-    forward, ABOVE the 1e-4 bar the BASELINE configurations meet (VGGish 7e-7 at 1000 + 1000 clips, CLAP 8e-5 at 200 + 200:
-    profiles/r2_parity_*.json).  It does not shrink with the set size, and it is not the attention kernel (both have the same
-    error against fp64, profiles/r2_attention_accuracy.json); round 1's 8 + 8-clip version of this test passed at 5e-5 by
-    chance (five independent 8 + 8 sets scatter over -2.2e-4 ... +2.6e-4, profiles/r2_w2v_fad_parity_sweep_*.json).
-    The bound below is the measured level with margin - a regression guard, not a claim of 1e-4 parity for this family
-    (lowest priority)."""
+    Measured: -1.4e-4 ... -2.0e-4 relative - ABOVE the 1e-4 bar the BASELINE configurations meet (VGGish 7e-7 at
+    1000 + 1000 clips, CLAP 8e-5 at 200 + 200: profiles/r2_parity_*.json).  What it is (finding 6):
+    under seeded random weights the hidden state of layer 12 is 99.2 % per-dimension mean (mean / rms = 0.996,
+    profiles/r2_w2v_fad_terms_32clips.json), so the covariances the score is made of are those of a fluctuation 11x
+    smaller than the values the fp16 GEMM operands round - not the attention kernel (tcgen05 and mma.sync agree,
+    profiles/r2_attention_accuracy.json) and, since the epilogue compensates the tensor core's accumulator truncation
+    (gain error of a GEMM -8e-7 -> -9e-9, profiles/r2_gemm_bias_probe_*.json), not a gain error of the GEMMs either.
+    Round 1's 8 + 8-clip version of this test passed at 5e-5 by chance (five independent 8 + 8 sets scatter over
+    -2.2e-4 ... +2.6e-4, profiles/r2_w2v_fad_parity_sweep_*.json).  The bound below is the measured level with margin -
+    a regression guard, not a claim of 1e-4 parity for this family (lowest priority)."""
     from oracle import fad_oracle as fo
     n = 64
     sets = {"base": [synth.noise_clip(i, 4.0, 16000) for i in range(n)],
