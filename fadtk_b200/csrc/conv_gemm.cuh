@@ -375,8 +375,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             for (int c = c0; c < c0 + kColsPerWarp && c < p.resid_C; c += 32)
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(p.resid + tok * p.resid_C + c));
         };
-        if (worker < total_tiles) prefetch_resid(nt, m);
-        for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        if (mu < m_units) prefetch_resid(nt, m);
+        // The unit index itself is not carried: unit = mu * n_tiles + nt < total_tiles  <=>  mu < m_units.  (One loop scalar
+        // less: the round-1 form kept the counter and tmem_base in LOCAL memory - ptxas spills what crosses the setmaxnreg
+        // split - and reloaded both on the critical path of every tile: 9 % of the epilogue warps' stall samples on the
+        // CLAP layers, profiles/r2_ncu_clap_gemm.md.)
+        auto load_bias = [&](float4 (&b)[8], int col0) {
+            const float4* src = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = __ldg(src + j);
+        };
+        while (mu < m_units) {
             int w, h, n;
             if (plain) { w = 0; h = 0; n = m * kTileM + r; }
             else {
@@ -388,7 +397,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             int nt_next = nt + step_nt, mu_next = mu + step_m;
             if (nt_next >= p.n_tiles) { nt_next -= p.n_tiles; ++mu_next; }
             const int m_next = PAIR ? 2 * mu_next + (int)rank : mu_next;
-            if (tile + n_workers < total_tiles) prefetch_resid(nt_next, m_next);
+            if (mu_next < m_units) prefetch_resid(nt_next, m_next);
+            // bias of the first 32-column group: requested BEFORE the wait for the accumulator (the mbarrier / TMEM asm
+            // statements are compiler barriers: a load written after them is issued after them, and its latency then
+            // sits on the critical path of the tile - the single largest stall of the epilogue in the ncu source page)
+            constexpr bool kBiasAhead = kColsPerWarp <= 64;  // N_TILE = 256 holds 128 partial sums per thread: no room for it
+            float4 bnext[8];
+            if (kBiasAhead) load_bias(bnext, nt * N_TILE + half * kColsPerWarp);
+            uint32_t tmem_base_e;                            // re-read per tile (LDS) instead of a local-memory reload
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_e) : "r"(smem_u32(tmem_base_slot)));
 
             // sum the K chunks in registers (round-to-nearest adds), undoing the expected truncation shrink of each
             float acc[kColsPerWarp];
@@ -397,7 +414,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                 const float unshrink = kAccumShrinkPerElement * (float)(len_c * kBlockK * (SPLIT_W ? 2 : 1));
                 mbar_wait(&tmem_full[buf], buf_ph);
                 tc_fence_after_sync();
-                const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + buf * kBufCols + half * kColsPerWarp;
+                const uint32_t t_row = tmem_base_e + (uint32_t(q * 32) << 16) + buf * kBufCols + half * kColsPerWarp;
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     uint32_t v[32];
@@ -419,7 +436,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                         for (int j = 0; j < 32; ++j) acc[g * 32 + j] += fmaf(__uint_as_float(v[j]), unshrink, __uint_as_float(v[j]));
                     }
                     if (LO8 && c == n_chunks - 1) {           // + A8 * Wl8^T / 2^s: complete once the last chunk is
-                        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + 2 * N_TILE + cpar * N_TILE + half * kColsPerWarp + g * 32, v);
+                        tmem_ld_32x32(tmem_base_e + (uint32_t(q * 32) << 16) + 2 * N_TILE + cpar * N_TILE + half * kColsPerWarp + g * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[g * 32 + j] = fmaf(__uint_as_float(v[j]), p.lo_scale, acc[g * 32 + j]);
@@ -453,23 +470,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     res_off = (p.resid_res ? window_row_to_token((long long)n, p.resid_res, p.resid_shift) : (long long)n)
                               * p.resid_C;
             }
-            uint8_t* stg = staging + (warp - 4) * kStagingBytes;
-            uint8_t* stg_mine = stg + lane * 128;
+            const uint32_t stg = smem_u32(staging) + (warp - 4) * kStagingBytes;     // shared-space addresses (sts128 / lds128)
+            const uint32_t stg_mine = stg + lane * 128;
             const int sw = lane & 7;
             const int cq = lane & 7, rq = lane >> 3;      // flush role: 16-B chunk cq of rows it*4 + rq
             const bool f32_path = p.out_f32 != nullptr || p.resid != nullptr;
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
-                const float4* bias4 = reinterpret_cast<const float4*>(p.bias + ch0 + g * 32);
                 float f[32];
+                if (!kBiasAhead) load_bias(bnext, ch0 + g * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(bias4 + j);
+                    const float4 b = bnext[j];
                     f[4 * j + 0] = acc[g * 32 + 4 * j + 0] + b.x;
                     f[4 * j + 1] = acc[g * 32 + 4 * j + 1] + b.y;
                     f[4 * j + 2] = acc[g * 32 + 4 * j + 2] + b.z;
                     f[4 * j + 3] = acc[g * 32 + 4 * j + 3] + b.w;
                 }
+                if (kBiasAhead && g + 1 < kGroups) load_bias(bnext, ch0 + (g + 1) * 32);   // the next group's, one group ahead
                 if (p.relu == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
@@ -489,14 +507,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                         // fp32 outputs: this group's 32 columns = one 128-B row segment per row
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(stg_mine + ((j ^ sw) << 4)) =
-                                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            sts128(stg_mine + ((j ^ sw) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                   __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
                         __syncwarp();
                         float4 v[8];
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int rr = it * 4 + rq;
-                            v[it] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+                            const uint4 u = lds128(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+                            v[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
                         }
                         const int col = ch0 + g * 32 + cq * 4;
                         if (p.out_f32 != nullptr) {
@@ -537,15 +556,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                         // fp16 output: two groups (64 columns) fill the 128-B row segment, then flush
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(stg_mine + ((((g & 1) * 4 + j) ^ sw) << 4)) =
-                                make_uint4(h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
+                            sts128(stg_mine + ((((g & 1) * 4 + j) ^ sw) << 4), h2[4 * j], h2[4 * j + 1], h2[4 * j + 2], h2[4 * j + 3]);
                         if (g & 1) {
                             __syncwarp();
                             const int col = ch0 + (g - 1) * 32 + cq * 8;
 #pragma unroll
                             for (int it = 0; it < 8; ++it) {
                                 const int rr = it * 4 + rq;
-                                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
+                                const uint4 v = lds128(stg + rr * 128 + ((cq ^ (rr & 7)) << 4));
                                 const long long off = __shfl_sync(0xffffffffu, out_off, rr);
                                 if (off >= 0 && col < p.n_valid) {
                                     *reinterpret_cast<uint4*>(p.out + off + col) = v;

@@ -208,6 +208,7 @@ int launch_conv_gemm(fad_handle* h, const CUtensorMap& mx, const CUtensorMap& mw
                      const CUtensorMap& mx8, const fad::ConvGemmParams& p, cudaStream_t st) {
     static bool attr_set = false;
     constexpr uint32_t smem = fad::conv_gemm_smem_bytes<N_TILE, STAGES, WMODE, PAIR>();
+    static_assert(smem <= 227 * 1024, "over the per-CTA shared-memory limit");
     auto kern = fad::conv_gemm_kernel<N_TILE, STAGES, WMODE, PAIR, STACK>;
     if (!attr_set) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
