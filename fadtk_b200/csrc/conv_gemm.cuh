@@ -137,6 +137,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + copysignf(1.0f - e, x));
 }
 
+// ELU (alpha = 1) in ~10 instructions (expm1f is ~25, in an epilogue that is issue-bound): the negative branch is
+// 2^(x log2 e) - 1 with one MUFU (absolute error 2^-22) below -1/16, and the Taylor polynomial of degree 4 above it, where
+// the subtraction would cancel (truncation < 8e-9, relative error ~1e-7 of a result that is then rounded to fp16).
+__device__ __forceinline__ float elu_ex2(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f) * 1.4426950408889634f));
+    const float t = x * fmaf(x, fmaf(x, fmaf(x, 4.16666667e-2f, 1.66666667e-1f), 0.5f), 1.0f);
+    return x > 0.f ? x : (x > -0.0625f ? t : e - 1.0f);
+}
+
 // 8 halves -> 8 E4M3 bytes (round to nearest, saturate)
 __device__ __forceinline__ uint32_t f16x4_to_e4m3x4(uint32_t a, uint32_t b) {
     __half2_raw h0, h1;
@@ -496,7 +506,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
                     for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
                 } else if (p.relu == 3) {                           // ELU (alpha = 1): SEANet's activation
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : expm1f(f[j]);
+                    for (int j = 0; j < 32; ++j) f[j] = elu_ex2(f[j]);
                 }
                 uint32_t h2[16];
 #pragma unroll
