@@ -79,15 +79,7 @@ def score_main(argv=None) -> int:
 
     fad = FrechetAudioDistance(model, audio_load_worker=args.workers, load_model=False)
     r2 = None
-    if args.indiv:
-        assert Path(args.eval).is_dir(), "Individual FAD requires a directory as the evaluation dataset"
-        table = Path(args.csv or "fad-individual-results.csv")
-        fad.score_individual(args.baseline, args.eval, table)
-        if dist.rank() == 0:
-            log.info(f"Individual FAD scores saved to {table}")
-        dist.shutdown()
-        return 0
-    if args.inf:
+    if args.inf:                                               # --inf wins when both are given (fadtk/__main__.py:45-50)
         assert Path(args.eval).is_dir(), "FAD-inf requires a directory as the evaluation dataset"
         result = fad.score_inf(args.baseline, sorted(Path(args.eval).glob("*.*")))
         if dist.rank() != 0:
@@ -95,6 +87,14 @@ def score_main(argv=None) -> int:
             return 0
         print("FAD-inf Information:", result)
         score, r2 = result.score, result.r2
+    elif args.indiv:
+        assert Path(args.eval).is_dir(), "Individual FAD requires a directory as the evaluation dataset"
+        table = Path(args.csv or "fad-individual-results.csv")
+        fad.score_individual(args.baseline, args.eval, table)
+        if dist.rank() == 0:
+            log.info(f"Individual FAD scores saved to {table}")
+        dist.shutdown()
+        return 0
     else:
         score = fad.score(args.baseline, args.eval)
 

@@ -53,6 +53,12 @@ def main(argv=None) -> int:
         if input().lower() != "y":
             return 1
     chosen = [registry[n] for n in (args.models or registry)]
+    if not args.models:                                        # the default (every model) skips entries without a forward pass
+        from .model_loader import UnbuiltModel
+        skipped = [m.name for m in chosen if isinstance(m, UnbuiltModel)]
+        if skipped:
+            print(f"skipping {', '.join(skipped)}: not built in this package (name them with -m to force)")
+        chosen = [m for m in chosen if not isinstance(m, UnbuiltModel)]
     path = pack_statistics(args.directory, args.out, chosen, workers=args.workers)
     print(f"statistics of {len(chosen)} model(s) written to {path}")
     return 0
