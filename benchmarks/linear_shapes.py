@@ -35,15 +35,16 @@ for name, rows, K, N, act in SHAPES:
         for _ in range(3):
             eng.umma_layer(x, w, bias, 1, act, 0, split_w=split)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 10
-        e0.record()
-        for _ in range(n):
+        n = int(os.environ.get("LINEAR_SHAPES_REPS", "10"))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record()
+        for i in range(n):                                  # one event per launch: a single slow launch must not hide in a mean
             eng.umma_layer(x, w, bias, 1, act, 0, split_w=split)
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
-        rec[label] = {"ms": round(ms, 4), "tflops": round(2.0 * rows * K * N / ms / 1e9, 1)}
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(n))
+        ms = per[n // 2]
+        rec[label] = {"ms": round(ms, 4), "min_ms": round(per[0], 4), "max_ms": round(per[-1], 4), "tflops": round(2.0 * rows * K * N / ms / 1e9, 1)}
     out.append(rec)
     del x, w
 print(json.dumps(out))

@@ -86,7 +86,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_s = tmem, tm_o[2] = {tmem + 128, tmem + 192};
+    const uint32_t tm_s = tmem, tm_o0 = tmem + 128;      // O buffer b at columns 128 + 64 b (arithmetic, not a local array: a runtime index put it in local memory)
 
     if (warp == 0) {
         if (elect_one()) {
@@ -122,7 +122,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {               // 16 keys per MMA: P advances 32 B inside its 64-key block, V two 8-key groups
                     const uint64_t dp = kmajor_sw128_desc(pa + (kk >> 2) * kAtTile) + 2 * (kk & 3);
-                    umma_f16(tm_o[b], dp, dv + 128 * kk, kIdO, kk > 0);
+                    umma_f16(tm_o0 + 64u * b, dp, dv + 128 * kk, kIdO, kk > 0);
                 }
                 umma_commit(&o_full[b]);
                 umma_commit(p_empty);
@@ -241,7 +241,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
                 mbar_wait(&o_full[bp], ((j - 1) >> 1) & 1);
                 tc_fence_after_sync();
                 uint32_t v[32];
-                tmem_ld_32x32(tm_o[bp] + lane_base + half * 32, v);
+                tmem_ld_32x32(tm_o0 + 64u * bp + lane_base + half * 32, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 32; ++c) o[c] = (o[c] + __uint_as_float(v[c])) * alpha;
@@ -262,7 +262,7 @@ attention_umma_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnPar
             const int q = qb * 128 + row;
             __half* dst = p.out + ((size_t)clip * p.S + q) * p.d + h * 64 + half * 32;
             uint32_t v[32];
-            tmem_ld_32x32(tm_o[bp] + lane_base + half * 32, v);
+            tmem_ld_32x32(tm_o0 + 64u * bp + lane_base + half * 32, v);
             tmem_ld_wait();
             if (q < p.S) {
 #pragma unroll

@@ -89,7 +89,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
+#ifdef FADTK_WAIT_NO_HINT
+    while (!mbar_try_wait(bar, parity)) {
+#else
     while (!mbar_try_wait_hint(bar, parity, 2000u)) {          // may suspend up to 2 us per try; resumes on completion
+#endif
         if (++spins > (1u << 24)) asm volatile("trap;");       // >= 0.3 s of retries
     }
 }
