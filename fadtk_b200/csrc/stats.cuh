@@ -524,16 +524,15 @@ stats_simt_kernel(const __half* __restrict__ E, long long n_rows, int d,
     for (long long r0 = r_begin; r0 < r_end; r0 += 32) {
         for (int i = threadIdx.x; i < 32 * 64; i += 256) {
             const int r = i >> 6, cc = i & 63;
-            double a = 0.0, b = 0.0, ax = 0.0;
+            double a = 0.0, b = 0.0;
             if (r0 + r < r_end) {
                 const __half* rowp = E + (size_t)(r0 + r) * d;
                 // x - s in fp64 is exact for any two fp16 values; products of such differences carry
                 // <= 2 x 40 bits, rounded once to fp64: relative error 1e-16 per term
                 a = (double)__half2float(rowp[ti * 64 + cc]) - (double)__half2float(shift[ti * 64 + cc]);
                 b = (double)__half2float(rowp[tj * 64 + cc]) - (double)__half2float(shift[tj * 64 + cc]);
-                ax = a;
             }
-            yi[r][cc] = a; yj[r][cc] = b; (void)ax;
+            yi[r][cc] = a; yj[r][cc] = b;
         }
         __syncthreads();
 #pragma unroll 4

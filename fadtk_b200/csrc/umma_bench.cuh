@@ -42,7 +42,6 @@ umma_bench_kernel(int mode, int ksteps)
         constexpr uint32_t i128 = make_idesc(FMT_F16, 128, 128), i256 = make_idesc(FMT_F16, 128, 256);
         constexpr uint32_t i8 = make_idesc(FMT_E4M3, 128, 128);
         auto f16_hi = [&](uint32_t d) { for (int k = 0; k < 4; ++k) umma_f16(d, da + 2 * k, db + 2 * k, i128, 1); };
-        auto f16_lo = [&](uint32_t d) { for (int k = 0; k < 4; ++k) umma_f16(d, da + 2 * k, db + 2 * k + 1024, i128, 1); };
         auto f16_256 = [&](uint32_t d) { for (int k = 0; k < 4; ++k) umma_f16(d, da + 2 * k, db + 2 * k, i256, 1); };
         auto f8_lo = [&](uint32_t d) { for (int k = 0; k < 2; ++k) umma_f8(d, da8 + 2 * k, db8 + 2 * k, i8, 1); };
         // a commit every 8 K steps, waiting for the one before it: at most 16 K steps in flight
@@ -56,7 +55,6 @@ umma_bench_kernel(int mode, int ksteps)
             else if (mode == 3) { f16_hi(d); if ((ks & 3) == 3) for (int q = 0; q < 4; ++q) f8_lo(d + 128); }
             else if (mode == 4) { f8_lo(d); f8_lo(d + 128); }
             else f16_hi(d);
-            (void)f16_lo;
             if ((ks & 7) == 7) {
                 const int b = (ks >> 3) & 1;
                 umma_commit(&bar[b]);
