@@ -317,6 +317,53 @@ def test_score_command_line_appends_the_reference_csv_row(tmp_path, monkeypatch,
         cli.score_main(["no-such-model", "a", "b"])
 
 
+def test_inf_wins_over_indiv_and_package_default_skips_unbuilt_models(tmp_path, monkeypatch, capsys):
+    """Both flags given: the reference runs FAD-inf (fadtk/__main__.py:45-50, `if args.inf ... elif args.indiv`).
+    `python -m fadtk_b200.package dir out.npz` with no -m walks the registry; entries without a forward pass
+    (clap-2023) are skipped with a note instead of aborting the whole run."""
+    import types
+    from fadtk_b200 import cli, fad as fad_mod, package
+    from fadtk_b200.model_loader import UnbuiltModel
+
+    class _ML:
+        name, model, sr = "vggish", None, 16000
+
+    calls = []
+
+    class _FAD:
+        def __init__(self, ml, **kw): pass
+        def score_inf(self, baseline, files):
+            calls.append(("inf", baseline, len(files)))
+            return types.SimpleNamespace(score=1.5, r2=0.9, slope=0.0, points=[])
+        def score_individual(self, baseline, ev, csv):
+            calls.append(("indiv", baseline))
+        def score(self, baseline, ev):
+            calls.append(("score", baseline))
+            return 2.5
+
+    monkeypatch.setattr(cli, "_registry", lambda: {"vggish": _ML()})
+    monkeypatch.setattr(cli, "_embed_directories", lambda *a, **k: None)
+    monkeypatch.setattr(fad_mod, "FrechetAudioDistance", _FAD)
+    ev = tmp_path / "eval"
+    ev.mkdir()
+    (ev / "a.wav").write_bytes(b"")
+    out = tmp_path / "scores.csv"
+    assert cli.score_main(["vggish", "base", str(ev), str(out), "--inf", "--indiv"]) == 0
+    assert [c[0] for c in calls] == ["inf"]
+    assert out.read_text().splitlines()[1].split(",")[3:5] == ["1.5", "0.9"]
+    calls.clear()
+    assert cli.score_main(["vggish", "base", str(ev), "--indiv"]) == 0 and [c[0] for c in calls] == ["indiv"]
+
+    packed = []
+    monkeypatch.setattr(package, "pack_statistics", lambda d, o, chosen, workers=8: packed.append([m.name for m in chosen]) or o)
+    assert package.main([str(ev), str(tmp_path / "s.npz")]) == 0
+    assert packed and "clap-2023" not in packed[0] and "vggish" in packed[0]
+    assert "skipping clap-2023" in capsys.readouterr().out
+    packed.clear()
+    with pytest.raises(NotImplementedError):                    # named explicitly: the loader says what is missing
+        UnbuiltModel("clap-2023", 1024, 44100, "x").load_model()
+
+
 def test_synthetic_weights_are_an_explicit_opt_in(tmp_path, monkeypatch):
     """The reference always loads pretrained weights; a FAD from random weights is meaningless and would be cached
     under the same embeddings/<model> paths.  Without a checkpoint the loaders refuse unless FADTK_SYNTHETIC=1, and
