@@ -115,6 +115,8 @@ def test_w2v_fad_parity_on_identical_audio(engine):
     smaller than the values the fp16 GEMM operands round - not the attention kernel (tcgen05 and mma.sync agree,
     profiles/r2_attention_accuracy.json) and, since the epilogue compensates the tensor core's accumulator truncation
     (gain error of a GEMM -8e-7 -> -9e-9, profiles/r2_gemm_bias_probe_*.json), not a gain error of the GEMMs either.
+    The reference path itself with fp16-rounded Linear / Conv1d inputs moves the FAD of these sets by +6e-5 ... +1.1e-4 on the
+    CPU (benchmarks/w2v_fp16_operand_emulation.py, profiles/r2_w2v_fp16_operand_emulation_cpu.jsonl): same order, either sign.
     Round 1's 8 + 8-clip version of this test passed at 5e-5 by chance (five independent 8 + 8 sets scatter over
     -2.2e-4 ... +2.6e-4, profiles/r2_w2v_fad_parity_sweep_*.json).  The bound below is the measured level with margin -
     a regression guard, not a claim of 1e-4 parity for this family (lowest priority)."""
