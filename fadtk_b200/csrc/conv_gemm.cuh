@@ -421,7 +421,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_x,
             float acc[kColsPerWarp];
             for (int c = 0; c < n_chunks; ++c) {
                 const int len_c = min(chunk_len, ksteps - c * chunk_len);
-                const float unshrink = kAccumShrinkPerElement * (float)(len_c * kBlockK * (SPLIT_W ? 2 : 1));
+                // products accumulated per TMEM element: hi and lo share one accumulator (x 2) unless they are stacked side by side
+                const float unshrink = kAccumShrinkPerElement * (float)(len_c * kBlockK * (SPLIT_W && !STACKED ? 2 : 1));
                 mbar_wait(&tmem_full[buf], buf_ph);
                 tc_fence_after_sync();
                 const uint32_t t_row = tmem_base_e + (uint32_t(q * 32) << 16) + buf * kBufCols + half * kColsPerWarp;
